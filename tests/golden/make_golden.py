@@ -1,0 +1,130 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/ from the reference's committed fixtures (run in the build container only).
+
+/root/reference does not exist on the GPU box, so everything the tests need is copied / extracted
+here and committed together with this script:
+
+  * G.711 fixtures + the reference's golden decoded WAV payloads
+    (testdata/g711_{ulaw,alaw}/*, golden/g711_{ulaw,alaw}/*.decoded.wav; soundkit-g711/src/lib.rs:376-400)
+  * linear16 raw PCM + golden WAV payload (soundkit/src/raw_pcm.rs:286-318), linear16_8 (8 kHz source)
+  * CAF / MOV PCM payloads (4 800 stereo frames each) with the LE-canonical SHA-256 the reference asserts
+    (soundkit-audio-demux/src/caf.rs:777-842, soundkit-audio-demux/src/lib.rs:5568-5690)
+  * short slices of the s32le / 24-bit WAV / f32 WAV speech fixtures as realistic conversion inputs
+
+Only DATA is copied, no reference source.  MANIFEST.json records the SHA-256 of every file.
+"""
+import hashlib
+import json
+import os
+import struct
+import sys
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+NAME = "A_Tusk_is_used_to_make_costly_gifts"
+
+ENDIAN_HASHES = {  # LE-canonical payload hashes asserted by the reference tests
+    "s16": "7126a0d8077e0433c1e78df6c0f1074f78daf3800240ef48c936114ef7cbb563",
+    "s24": "c4e54b143defc7ce84e84c3b6fe96b1f87423477a8ca0f6676085b35eba7d087",
+    "s32": "1568245a441f20f5c94b0810fa460c820f0e7d65ab2c6091100bf8c23ad7913c",
+    "f32": "31522f2b9f09614ab868408fd95f5d826028b61407827b7b112d0ab9981ad65e",
+}
+
+
+def caf_payload(path):
+    b = open(path, "rb").read()
+    assert b[:4] == b"caff"
+    off = 8
+    while off < len(b):
+        kind, size = b[off:off + 4], struct.unpack(">q", b[off + 4:off + 12])[0]
+        off += 12
+        if kind == b"data":
+            end = len(b) if size < 0 else off + size
+            return b[off + 4:end]  # skip mEditCount
+        off += size
+    raise ValueError("no data chunk")
+
+
+def mov_payload(path):
+    b = open(path, "rb").read()
+    off = 0
+    while off < len(b):
+        size, kind = struct.unpack(">I4s", b[off:off + 8])
+        hdr = 8
+        if size == 1:
+            size = struct.unpack(">Q", b[off + 8:off + 16])[0]
+            hdr = 16
+        if kind == b"mdat":
+            return b[off + hdr:off + size]
+        off += size
+    raise ValueError("no mdat")
+
+
+def wav_payload(path):
+    b = open(path, "rb").read()
+    assert b[:4] == b"RIFF" and b[8:12] == b"WAVE"
+    off = 12
+    while off < len(b):
+        kind, size = b[off:off + 4], struct.unpack("<I", b[off + 4:off + 8])[0]
+        if kind == b"data":
+            return b[off + 8:off + 8 + size]
+        off += 8 + size + (size & 1)
+    raise ValueError("no data chunk")
+
+
+def to_le(payload, bps):
+    out = bytearray(payload)
+    for i in range(0, len(out) - bps + 1, bps):
+        out[i:i + bps] = out[i:i + bps][::-1]
+    return bytes(out)
+
+
+def main():
+    if not os.path.isdir(REF):
+        sys.exit("needs /root/reference (build container only)")
+    files = {}
+
+    def put(name, data):
+        with open(os.path.join(HERE, name), "wb") as f:
+            f.write(data)
+        files[name] = hashlib.sha256(data).hexdigest()
+
+    rd = lambda p: open(os.path.join(REF, p), "rb").read()
+    put("g711_ulaw.ulaw", rd(f"testdata/g711_ulaw/{NAME}.ulaw"))
+    put("g711_alaw.alaw", rd(f"testdata/g711_alaw/{NAME}.alaw"))
+    put("g711_ulaw.decoded.s16le", wav_payload(os.path.join(REF, f"golden/g711_ulaw/{NAME}.decoded.wav")))
+    put("g711_alaw.decoded.s16le", wav_payload(os.path.join(REF, f"golden/g711_alaw/{NAME}.decoded.wav")))
+    put("linear16.s16le", rd(f"testdata/linear16/{NAME}.s16le"))
+    put("linear16.decoded.s16le", wav_payload(os.path.join(REF, f"golden/linear16/{NAME}.decoded.wav")))
+    put("linear16_8.s16le", rd(f"testdata/linear16_8/{NAME}.s16le"))
+    # realistic conversion inputs, first 16 000 samples each
+    put("linear32.s32le", rd(f"testdata/linear32/{NAME}.s32le")[:64000])
+    put("wav_24.s24le", wav_payload(os.path.join(REF, f"testdata/wav_24/{NAME}.wav"))[:48000])
+    put("wav_32f.f32le", wav_payload(os.path.join(REF, f"testdata/wav_32f/{NAME}.wav"))[:64000])
+
+    endian = {}
+    for name, kind, bps, be in (("pcm-s16be.caf", "s16", 2, True), ("pcm-s24le.caf", "s24", 3, False),
+                                ("pcm-s32be.caf", "s32", 4, True), ("pcm-f32le.caf", "f32", 4, False)):
+        p = caf_payload(os.path.join(REF, "testdata/caf", name))[:4800 * 2 * bps]
+        le = to_le(p, bps) if be else p
+        assert hashlib.sha256(le).hexdigest() == ENDIAN_HASHES[kind], name
+        out = name.replace(".caf", ".caf.bin")
+        put(out, p)
+        endian[out] = {"kind": kind, "bytes_per_sample": bps, "big_endian": be, "le_sha256": ENDIAN_HASHES[kind]}
+    for name, kind, bps, be in (("pcm-s24be.mov", "s24", 3, True), ("pcm-s24le.mov", "s24", 3, False),
+                                ("pcm-s32be.mov", "s32", 4, True), ("pcm-s32le.mov", "s32", 4, False),
+                                ("pcm-f32be.mov", "f32", 4, True), ("pcm-f32le.mov", "f32", 4, False)):
+        p = mov_payload(os.path.join(REF, "testdata/mov-pcm", name))[:4800 * 2 * bps]
+        le = to_le(p, bps) if be else p
+        assert hashlib.sha256(le).hexdigest() == ENDIAN_HASHES[kind], name
+        out = name.replace(".mov", ".mov.bin")
+        put(out, p)
+        endian[out] = {"kind": kind, "bytes_per_sample": bps, "big_endian": be, "le_sha256": ENDIAN_HASHES[kind]}
+
+    with open(os.path.join(HERE, "MANIFEST.json"), "w") as f:
+        json.dump({"files": files, "endian_payloads": endian}, f, indent=1, sort_keys=True)
+    print(f"wrote {len(files)} fixtures")
+
+
+if __name__ == "__main__":
+    main()
