@@ -1,0 +1,222 @@
+/*
+ * soundkit_cuda.h — C ABI of libsoundkit_cuda.so (hand-written sm_100a kernels).
+ *
+ * The reference (wavey-ai/soundkit) has NO FFI layer for this path: its callers use plain Rust
+ * functions and two traits.  This header is the `extern "C"` surface a thin `soundkit-cuda-sys`
+ * crate binds; each entry point cites the reference interface it replaces
+ * (paths relative to the reference repo root).  Argument VALIDATION that produces the reference's
+ * exact error strings stays in the host layer above this ABI (rust/ and soundkit_b200/host.py);
+ * this layer returns negative status codes + sk_last_error().
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types.
+ *   - entry points without a suffix take HOST pointers: they stage through pinned memory, run the
+ *     kernel on the context's stream and return after the result is back in the caller's buffer.
+ *   - `_dev` entry points take DEVICE pointers, enqueue on the context's stream and return
+ *     immediately (call sk_ctx_synchronize or synchronize the stream yourself).
+ *   - one sk_ctx per host thread; handles are not shared across threads (the reference runs one
+ *     worker thread per DecodePipeline, soundkit-decoder/src/lib.rs:2764).
+ *   - there is NO CPU fallback: without a CUDA device sk_ctx_create fails with SK_E_NODEVICE.
+ */
+#ifndef SOUNDKIT_CUDA_H
+#define SOUNDKIT_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SK_ABI_VERSION 1
+
+typedef struct sk_ctx sk_ctx;
+typedef struct sk_resampler sk_resampler;
+
+enum sk_status {
+    SK_OK = 0,
+    SK_E_ARG = -1,      /* invalid argument (message says which) */
+    SK_E_ALLOC = -2,    /* host or device allocation failed */
+    SK_E_CUDA = -3,     /* CUDA runtime error (message carries cudaGetErrorString) */
+    SK_E_STATE = -4,    /* handle used in the wrong state */
+    SK_E_NODEVICE = -5  /* no usable CUDA device: the library has no CPU path */
+};
+
+/* soundkit-g711/src/lib.rs:17 `enum G711Law { MuLaw, ALaw }` */
+enum sk_law { SK_LAW_MULAW = 0, SK_LAW_ALAW = 1 };
+/* sample container of a typed slice (`&[i16]`, `&[i32]`, `&[f32]`) */
+enum sk_kind { SK_KIND_I16 = 0, SK_KIND_I32 = 1, SK_KIND_F32 = 2 };
+/* frame-header EncodingFlag::{PCMSigned, PCMFloat} (soundkit/src/audio_packet.rs:43-50) */
+enum sk_format { SK_FMT_SIGNED = 0, SK_FMT_FLOAT = 1 };
+/* scale convention: A = soundkit::audio_pipeline::audio_to_f32_channels (audio_pipeline.rs:74-98;
+ * always LE, 24-bit / 2^31, no NaN scrub), B = soundkit-decoder audio_data_to_f32_channels
+ * (soundkit-decoder/src/lib.rs:3563-3617; endian-aware, /2^15 /2^23 /2^31, non-finite -> 0) */
+enum sk_scale_mode { SK_MODE_A = 0, SK_MODE_B = 1 };
+/* mono mixdown order: SUM_THEN_SCALE = mixdown_to_mono_f32 (audio_pipeline.rs:105-131),
+ * SCALE_THEN_SUM = downmix_channels(.., 1) (soundkit-decoder/src/lib.rs:3500-3510) */
+enum sk_mix_mode { SK_MIX_NONE = 0, SK_MIX_SUM_THEN_SCALE = 1, SK_MIX_SCALE_THEN_SUM = 2 };
+/* resampler call semantics: ONESHOT = downsample_audio (one rubato chunk = whole buffer, no tail
+ * flush; audio_pipeline.rs:482-491), STREAMING = StreamingResampler (chunk 4096 + flush + trim;
+ * soundkit-decoder/src/lib.rs:1970-2059) */
+enum sk_resample_semantics { SK_SEM_ONESHOT = 0, SK_SEM_STREAMING = 1 };
+
+/* flat element-wise conversions of soundkit/src/audio_bytes.rs (line = `pub fn` in the reference) */
+enum sk_flat_op {
+    SK_OP_I16LE_TO_F32 = 0,  /* :3   i16le_to_f32  (also vec_i16_to_f32, audio_pipeline.rs:29) */
+    SK_OP_S16LE_TO_I16 = 1,  /* :25 i16le_to_i16, :231 s16le_to_i16 */
+    SK_OP_S16BE_TO_I16 = 2,  /* :222 */
+    SK_OP_S16LE_TO_I32 = 3,  /* :240 */
+    SK_OP_S24LE_TO_I32 = 4,  /* :36 */
+    SK_OP_S24LE_TO_I16 = 5,  /* :51 */
+    SK_OP_S24BE_TO_I16 = 6,  /* :66 */
+    SK_OP_S32LE_TO_I32 = 7,  /* :81 */
+    SK_OP_S32BE_TO_I32 = 8,  /* :91 */
+    SK_OP_S32LE_TO_S24 = 9,  /* :101 keeps the LOW 24 bits */
+    SK_OP_S32BE_TO_S24 = 10, /* :112 */
+    SK_OP_S32LE_TO_F32 = 11, /* :123 (also vec_i32_to_f32, audio_pipeline.rs:40) */
+    SK_OP_S32BE_TO_F32 = 12, /* :134 */
+    SK_OP_S32LE_TO_I16 = 13, /* :145 */
+    SK_OP_S32BE_TO_I16 = 14, /* :156 */
+    SK_OP_F32LE_TO_I16 = 15, /* :167 (also vec_f32_to_i16, audio_pipeline.rs:17) */
+    SK_OP_F32BE_TO_I16 = 16, /* :178 */
+    SK_OP_F32LE_TO_I32 = 17, /* :189 */
+    SK_OP_F32LE_TO_S24 = 18, /* :205 */
+    SK_OP_COUNT = 19
+};
+
+/* ------------------------------------------------------------------ context */
+int  sk_abi_version(void);
+int  sk_ctx_create(int device, sk_ctx** out);
+void sk_ctx_destroy(sk_ctx* ctx);
+/* last error message of this context (thread-confined); "" when none */
+const char* sk_last_error(const sk_ctx* ctx);
+/* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the ctx's own */
+int  sk_ctx_set_stream(sk_ctx* ctx, void* cuda_stream);
+int  sk_ctx_synchronize(sk_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py reports it as gpu_launches) */
+uint64_t sk_ctx_launch_count(const sk_ctx* ctx);
+/* measured FP32 FFMA peak of this device in TFLOP/s (register-resident FFMA microbenchmark) */
+int  sk_ctx_measure_ffma_peak(sk_ctx* ctx, double* tflops);
+
+/* ------------------------------------------------------------------ kernel 2: G.711 */
+/* replaces soundkit_g711::decode_i16 (soundkit-g711/src/lib.rs:52) and
+ * G711Decoder::decode_{i16,i32,f32} (:183-232); out_kind selects the output slice type. */
+int sk_g711_decode(sk_ctx*, int law, const uint8_t* in, size_t n, int out_kind, void* out);
+int sk_g711_decode_dev(sk_ctx*, int law, const uint8_t* in, size_t n, int out_kind, void* out);
+/* replaces soundkit_g711::encode_i16 (:36) and G711Encoder::encode_{i16,i32} (:120-138) */
+int sk_g711_encode(sk_ctx*, int law, int in_kind, const void* in, size_t n, uint8_t* out);
+int sk_g711_encode_dev(sk_ctx*, int law, int in_kind, const void* in, size_t n, uint8_t* out);
+
+/* ------------------------------------------------------------------ kernel 1: conversion */
+/* the 19 flat functions of soundkit/src/audio_bytes.rs; writes floor(bytes / in_width) elements */
+int sk_pcm_flat_convert(sk_ctx*, int op, const uint8_t* in, size_t bytes, void* out, size_t* n_out);
+int sk_pcm_flat_convert_dev(sk_ctx*, int op, const uint8_t* in, size_t bytes, void* out);
+/* bytes per input / output element of a flat op */
+int sk_flat_op_widths(int op, int* in_width, int* out_width);
+
+/* deinterleave_vecs_{i16,s24,f32} (audio_bytes.rs:264-310): interleaved LE bytes -> planar
+ * [channels][frames] of i16 / sign-extended i32 / f32 bits.  kind: 0 = i16, 1 = s24, 2 = f32. */
+int sk_deinterleave(sk_ctx*, int kind, const uint8_t* in, size_t bytes, int channels, void* out,
+                    size_t* frames);
+/* interleave_vecs_i16 (audio_bytes.rs:250-262): planar [channels][frames] i16 -> LE bytes */
+int sk_interleave_i16(sk_ctx*, const int16_t* planar, int channels, size_t frames, uint8_t* out);
+/* stereo_to_mono_{take_left,avg} (audio_bytes.rs:317-373): avg != 0 -> ((l + r) / 2) truncating */
+int sk_stereo_to_mono_i16(sk_ctx*, int avg, const int16_t* in, size_t n, int16_t* out);
+
+/* audio_to_f32_channels (mode A) / audio_data_to_f32_channels (mode B): interleaved PCM bytes ->
+ * planar f32 [channels][frames].  `frames` = whole frames in `bytes` (mode A silently drops a
+ * trailing partial frame like the reference; mode B rejects it: SK_E_ARG). */
+int sk_pcm_to_planar_f32(sk_ctx*, const uint8_t* in, size_t bytes, int bits, int fmt, int big_endian,
+                         int channels, int scale_mode, float* out, size_t frames_cap, size_t* frames);
+/* batched, device resident: n_streams buffers of `frames` frames each, in_stride bytes apart;
+ * out[s][c][f] with out_stride floats between streams (channel planes are `frames` apart). */
+int sk_pcm_to_planar_f32_dev(sk_ctx*, const uint8_t* in, size_t in_stride, size_t n_streams,
+                             size_t frames, int bits, int fmt, int big_endian, int channels,
+                             int scale_mode, float* out, size_t out_stride);
+/* f32_channels_to_bytes (soundkit-decoder/src/lib.rs:3619-3701): planar f32 -> interleaved LE
+ * bytes; bits 16 uses float_sample_to_i16 (:1815), 24/32 the clamp-and-truncate scalers,
+ * fmt FLOAT (bits 32) is a bit copy (interleave_vecs_f32, :3685). */
+int sk_planar_f32_to_pcm(sk_ctx*, const float* planar, size_t frames, int channels, int bits, int fmt,
+                         uint8_t* out);
+int sk_planar_f32_to_pcm_dev(sk_ctx*, const float* planar, size_t frames, int channels, int bits,
+                             int fmt, uint8_t* out);
+/* exact_signed_pcm_to_i16 (soundkit-decoder/src/lib.rs:3458-3489): 24/32-bit LE/BE -> s16 LE */
+int sk_pcm_narrow_i16(sk_ctx*, const uint8_t* in, size_t bytes, int bits, int big_endian, uint8_t* out);
+/* mixdown_to_mono_f32 / downmix_channels(.., 1): planar [channels][frames] -> mono */
+int sk_mixdown_mono(sk_ctx*, const float* planar, size_t frames, int channels, int mix_mode, float* out);
+int sk_mixdown_mono_dev(sk_ctx*, const float* planar, size_t frames, int channels, int mix_mode,
+                        float* out);
+/* downmix_channels(.., 2) for > 2 channels (soundkit-decoder/src/lib.rs:3512-3557), including the
+ * block-wide peak normalisation; out is planar [2][frames]. */
+int sk_downmix_stereo(sk_ctx*, const float* planar, size_t frames, int channels, float* out);
+
+/* ------------------------------------------------------------------ kernel 3: sinc resampler */
+/* rubato SincInterpolationParameters as soundkit hard-codes them (audio_pipeline.rs:474-480,
+ * soundkit-decoder/src/lib.rs:1939-1945).  Only these values are implemented; anything else is
+ * SK_E_ARG.  NULL = defaults. */
+typedef struct {
+    uint32_t sinc_len;      /* 256 */
+    uint32_t oversampling;  /* 256 */
+    float    f_cutoff;      /* 0.95 */
+    int      interp;        /* 0 = Linear */
+    int      window;        /* 0 = BlackmanHarris2 */
+    double   max_ratio_rel; /* 2.0 */
+} sk_resample_params;
+
+/* SincFixedIn::<f32>::new(out/in, 2.0, params, chunk, channels) — stateful, one per stream */
+int    sk_resampler_create(sk_ctx*, uint32_t in_rate, uint32_t out_rate, int channels, size_t chunk,
+                           const sk_resample_params* params, sk_resampler** out);
+void   sk_resampler_destroy(sk_resampler*);
+size_t sk_resampler_out_max(const sk_resampler*);        /* (chunk * ratio * 2.0 + 10) as usize */
+double sk_resampler_last_index(const sk_resampler*);
+/* Resampler::process(&wave_in, None): in[c] -> chunk frames, out[c] has room for out_max frames */
+int    sk_resampler_process(sk_resampler*, const float* const* in, float* const* out, size_t* n_out);
+/* Resampler::process_partial(Some(x) | None, None): zero-pads `frames` to one whole chunk */
+int    sk_resampler_process_partial(sk_resampler*, const float* const* in_or_null, size_t frames,
+                                    float* const* out, size_t* n_out);
+/* the [256][256] windowed-sinc table this resampler uses (for parity tests) */
+int    sk_resampler_copy_table(const sk_resampler*, float* out65536);
+
+/* ------------------------------------------------------------------ kernel 4: fused batch chain */
+/* Batched, device-resident normalisation of n_streams equal-length streams:
+ *   interleaved PCM (bits/fmt/endianness/channels) --convert(scale_mode)--> f32
+ *   --sinc resample in_rate -> out_rate per channel--> [--mono mixdown(mix_mode)-->] f32 planar
+ * in one kernel (one HBM read of the input, one HBM write of the output).
+ * semantics ONESHOT reproduces soundkit::audio_pipeline::downsample_audio per stream;
+ * STREAMING reproduces apply_output_options' rate-changing arm (chunk-4096 StreamingResampler,
+ * flush and trim included) for a whole stream.
+ * Output: mix_mode NONE -> out[s][c][n_out] (channel planes out_stride_ch floats apart),
+ *         otherwise     -> out[s][n_out] mono.  out_stride = floats between streams. */
+typedef struct {
+    const void* in;        /* device pointer */
+    size_t   in_stride;    /* bytes between consecutive streams */
+    size_t   n_streams;
+    size_t   frames;       /* frames per stream */
+    int      bits;         /* 16 | 24 | 32 */
+    int      fmt;          /* sk_format */
+    int      big_endian;
+    int      channels;
+    int      scale_mode;   /* sk_scale_mode */
+    uint32_t in_rate, out_rate;
+    int      semantics;    /* sk_resample_semantics */
+    int      mix_mode;     /* sk_mix_mode */
+    float*   out;          /* device pointer */
+    size_t   out_stride;   /* floats between consecutive streams */
+    size_t   out_stride_ch;/* floats between channel planes (mix_mode NONE) */
+} sk_batch_desc;
+
+/* frames each stream produces for (in_rate, out_rate, frames, semantics); builds and caches the
+ * index plan so the first sk_normalize_batch_dev call does not pay for it */
+int sk_normalize_batch_plan(sk_ctx*, uint32_t in_rate, uint32_t out_rate, size_t frames, int semantics,
+                            size_t* n_out);
+int sk_normalize_batch_dev(sk_ctx*, const sk_batch_desc* desc);
+/* host-pointer form of the same call for ONE stream (what downsample_audio / the decoder's output
+ * stage would call per AudioData): copies in, runs the fused kernel, copies out. */
+int sk_normalize_stream(sk_ctx*, const uint8_t* in, size_t bytes, int bits, int fmt, int big_endian,
+                        int channels, int scale_mode, uint32_t in_rate, uint32_t out_rate, int semantics,
+                        int mix_mode, float* out, size_t out_cap_per_plane, size_t* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOUNDKIT_CUDA_H */

@@ -1,0 +1,83 @@
+// sk_common.cuh — shared host/device helpers of libsoundkit_cuda (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/soundkit_cuda.h"
+
+#define SK_NUM_SMS_FALLBACK 148
+
+struct sk_plan;  // resampler index plan (sk_resample.cu)
+
+struct sk_ctx {
+    int device = 0;
+    int num_sms = SK_NUM_SMS_FALLBACK;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;  // stream kernels are launched on (own or caller's)
+    uint64_t launches = 0;
+    std::string err;
+    // pinned host staging + device arena for the host-pointer entry points (grow-only)
+    void* h_stage = nullptr; size_t h_cap = 0;
+    void* d_in = nullptr;    size_t d_in_cap = 0;
+    void* d_out = nullptr;   size_t d_out_cap = 0;
+    // G.711 encode tables (65536 x u8 per law) and sinc tables per ratio, built lazily on device
+    uint8_t* d_g711_enc[2] = {nullptr, nullptr};
+    std::map<uint64_t, float*> sinc_tables;          // key = (in_rate << 32) | out_rate -> device [256][256]
+    std::map<uint64_t, std::vector<float>> sinc_host; // same key -> host copy
+    std::map<std::string, sk_plan*> plans;            // batch plans keyed by rate/frames/semantics
+};
+
+#define SK_FAIL(ctx, code, ...)                                 \
+    do {                                                        \
+        char _b[512];                                           \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                  \
+        (ctx)->err = _b;                                        \
+        return (code);                                          \
+    } while (0)
+
+#define SK_CUDA(ctx, expr)                                                                        \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) SK_FAIL(ctx, SK_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define SK_LAUNCH_CHECK(ctx)                                                                         \
+    do {                                                                                             \
+        cudaError_t _e = cudaGetLastError();                                                         \
+        if (_e != cudaSuccess) SK_FAIL(ctx, SK_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(_e)); \
+        (ctx)->launches++;                                                                           \
+    } while (0)
+
+// grow-only staging buffers ----------------------------------------------------------------
+int sk_ensure_host(sk_ctx* ctx, size_t bytes);
+int sk_ensure_dev_in(sk_ctx* ctx, size_t bytes);
+int sk_ensure_dev_out(sk_ctx* ctx, size_t bytes);
+// host -> device through the pinned stage (chunked), device -> host likewise; both synchronous wrt host
+int sk_h2d(sk_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int sk_d2h(sk_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+static inline size_t sk_round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+#ifdef __CUDACC__
+// 128-bit streaming loads/stores: data touched once, keep it out of L1
+__device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_v4(void* p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream_v2(void* p, uint2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+#endif

@@ -1,0 +1,185 @@
+// sk_ctx.cu — context, pinned staging, error plumbing, FFMA peak microbenchmark.
+#include "sk_common.cuh"
+
+extern void sk_resample_free_ctx(sk_ctx* ctx);  // sk_resample.cu: frees cached tables / plans
+
+extern "C" int sk_abi_version(void) { return SK_ABI_VERSION; }
+
+extern "C" int sk_ctx_create(int device, sk_ctx** out) {
+    if (!out) return SK_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return SK_E_NODEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return SK_E_NODEVICE;
+    sk_ctx* ctx = new (std::nothrow) sk_ctx();
+    if (!ctx) return SK_E_ALLOC;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+        ctx->num_sms = prop.multiProcessorCount;
+        if (prop.major != 10) {  // sm_100a cubin only: fail loudly instead of a confusing launch error
+            delete ctx;
+            return SK_E_NODEVICE;
+        }
+    }
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return SK_E_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return SK_OK;
+}
+
+extern "C" void sk_ctx_destroy(sk_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    sk_resample_free_ctx(ctx);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->d_in) cudaFree(ctx->d_in);
+    if (ctx->d_out) cudaFree(ctx->d_out);
+    for (int i = 0; i < 2; i++)
+        if (ctx->d_g711_enc[i]) cudaFree(ctx->d_g711_enc[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" const char* sk_last_error(const sk_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int sk_ctx_set_stream(sk_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return SK_E_ARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return SK_OK;
+}
+
+extern "C" int sk_ctx_synchronize(sk_ctx* ctx) {
+    if (!ctx) return SK_E_ARG;
+    SK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SK_OK;
+}
+
+extern "C" uint64_t sk_ctx_launch_count(const sk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- staging -------------------------------------------------------------------------------
+int sk_ensure_host(sk_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->h_cap) return SK_OK;
+    if (ctx->h_stage) { cudaFreeHost(ctx->h_stage); ctx->h_stage = nullptr; ctx->h_cap = 0; }
+    size_t cap = sk_round_up(bytes, 1 << 20);
+    if (cudaMallocHost(&ctx->h_stage, cap) != cudaSuccess) SK_FAIL(ctx, SK_E_ALLOC, "pinned alloc of %zu bytes failed", cap);
+    ctx->h_cap = cap;
+    return SK_OK;
+}
+static int ensure_dev(sk_ctx* ctx, void** p, size_t* cap, size_t bytes) {
+    if (bytes <= *cap) return SK_OK;
+    if (*p) { cudaStreamSynchronize(ctx->stream); cudaFree(*p); *p = nullptr; *cap = 0; }
+    size_t ncap = sk_round_up(bytes + 256, 1 << 20);
+    if (cudaMalloc(p, ncap) != cudaSuccess) SK_FAIL(ctx, SK_E_ALLOC, "device alloc of %zu bytes failed", ncap);
+    *cap = ncap;
+    return SK_OK;
+}
+int sk_ensure_dev_in(sk_ctx* ctx, size_t bytes) { return ensure_dev(ctx, &ctx->d_in, &ctx->d_in_cap, bytes); }
+int sk_ensure_dev_out(sk_ctx* ctx, size_t bytes) { return ensure_dev(ctx, &ctx->d_out, &ctx->d_out_cap, bytes); }
+
+// Host buffers of the drop-in API are pageable (Rust Vec / slices): stage through pinned memory in
+// 8 MiB pieces so the DMA engine runs at full PCIe rate and the pinned footprint stays bounded.
+static const size_t kStagePiece = 8u << 20;
+int sk_h2d(sk_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    if (!bytes) return SK_OK;
+    int rc = sk_ensure_host(ctx, 2 * kStagePiece);
+    if (rc) return rc;
+    char* stage = (char*)ctx->h_stage;
+    cudaEvent_t ev[2];
+    for (int i = 0; i < 2; i++) SK_CUDA(ctx, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    size_t off = 0; int slot = 0; bool used[2] = {false, false};
+    while (off < bytes) {
+        size_t n = bytes - off < kStagePiece ? bytes - off : kStagePiece;
+        if (used[slot]) cudaEventSynchronize(ev[slot]);
+        memcpy(stage + slot * kStagePiece, (const char*)src_host + off, n);
+        cudaMemcpyAsync((char*)dst_dev + off, stage + slot * kStagePiece, n, cudaMemcpyHostToDevice, ctx->stream);
+        cudaEventRecord(ev[slot], ctx->stream);
+        used[slot] = true;
+        off += n; slot ^= 1;
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 2; i++) cudaEventDestroy(ev[i]);
+    if (e != cudaSuccess) SK_FAIL(ctx, SK_E_CUDA, "h2d copy failed: %s", cudaGetErrorString(e));
+    return SK_OK;
+}
+int sk_d2h(sk_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+    if (!bytes) return SK_OK;
+    int rc = sk_ensure_host(ctx, 2 * kStagePiece);
+    if (rc) return rc;
+    char* stage = (char*)ctx->h_stage;
+    size_t off = 0; int slot = 0;
+    size_t pend_off[2] = {0, 0}, pend_n[2] = {0, 0};
+    cudaEvent_t ev[2];
+    for (int i = 0; i < 2; i++) SK_CUDA(ctx, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    while (off < bytes || pend_n[0] || pend_n[1]) {
+        if (pend_n[slot]) {
+            cudaEventSynchronize(ev[slot]);
+            memcpy((char*)dst_host + pend_off[slot], stage + slot * kStagePiece, pend_n[slot]);
+            pend_n[slot] = 0;
+        }
+        if (off < bytes) {
+            size_t n = bytes - off < kStagePiece ? bytes - off : kStagePiece;
+            cudaMemcpyAsync(stage + slot * kStagePiece, (const char*)src_dev + off, n, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaEventRecord(ev[slot], ctx->stream);
+            pend_off[slot] = off; pend_n[slot] = n;
+            off += n;
+        }
+        slot ^= 1;
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 2; i++) cudaEventDestroy(ev[i]);
+    if (e != cudaSuccess) SK_FAIL(ctx, SK_E_CUDA, "d2h copy failed: %s", cudaGetErrorString(e));
+    return SK_OK;
+}
+
+// ---- FFMA peak microbenchmark ----------------------------------------------------------------
+// 16 independent accumulator chains per thread, operands in registers; the measured rate is the
+// denominator of the resampler's FP32 roofline (BASELINE.md section 2 asks for it "in the same run").
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* sink, float x, float y, int iters) {
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = (float)(threadIdx.x + i);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int i = 0; i < 16; i++) a[i] = __fmaf_rn(a[i], x, y);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += a[i];
+    if (s == 123.456f) sink[0] = s;  // never true; keeps the chains alive
+}
+
+extern "C" int sk_ctx_measure_ffma_peak(sk_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return SK_E_ARG;
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = sk_ensure_dev_out(ctx, 256);
+    if (rc) return rc;
+    const int iters = 4096, blocks = ctx->num_sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    SK_CUDA(ctx, cudaEventCreate(&e0));
+    SK_CUDA(ctx, cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0, ctx->stream);
+        ffma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((float*)ctx->d_out, 0.999f, 0.001f, iters);
+        cudaEventRecord(e1, ctx->stream);
+        SK_LAUNCH_CHECK(ctx);
+        SK_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double flops = 2.0 * (double)blocks * threads * (double)iters * 8.0 * 16.0;
+        double t = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && t > best) best = t;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return SK_OK;
+}

@@ -1,0 +1,879 @@
+// sk_resample.cu — kernels 3/4: batched polyphase windowed-sinc FIR on FP32 CUDA cores, optionally
+// fused with the PCM->f32 conversion in front of it and the mono mixdown behind it.
+//
+// Replaces rubato 0.14.1 `SincFixedIn<f32>::process_into_buffer` as soundkit reaches it from
+// soundkit/src/audio_pipeline.rs:438-493 (downsample_audio, one chunk = whole buffer) and
+// soundkit-decoder/src/lib.rs:1917-2060, 3324-3456 (StreamingResampler, chunk 4096, + downmix).
+//
+// Numerics contract (what makes the output identical to the AVX+FMA rubato path):
+//   * the [256][256] table is generated on the host with the same f32 expression tree as rubato's
+//     make_sincs / blackman_harris (libm sinf/cosf);
+//   * the f64 index walk `idx += t_ratio` is data independent, so it is executed ONCE on the host per
+//     (ratio, length, semantics) and shared by every stream of a batch (the "plan");
+//   * each dot product keeps rubato's 8 lane accumulators (lane l owns taps l, l+8, ...; fused
+//     multiply-add in tap order) and its reduction tree ((a0+a4)+(a1+a5))+((a2+a6)+(a3+a7));
+//   * out = p0 + frac * (p1 - p0) with separate mul / sub / add (file is built with -fmad=false).
+//
+// Two kernels:
+//   resample_int_kernel<STEP,...>  integer t_ratio (48k->16k: STEP 3).  idx is always an integer, so
+//       subindex 0 and frac 0: out == row-0 dot product exactly, one table row, which is passed BY
+//       VALUE as a kernel parameter -> every FFMA takes its coefficient straight from the constant
+//       bank (no register, no shared-memory traffic for taps).  Each thread owns R consecutive
+//       outputs of one channel (8*R accumulators) and walks the input window once: every input
+//       sample fetched from shared memory with LDS.128 feeds R FFMAs.
+//   resample_gen_kernel            any ratio, both interpolation products; outputs of one tile are
+//       visited phase-major (lane = period, warp = phase) so the two table rows are warp-uniform
+//       broadcast loads and the input reads are conflict-free.
+#include <math.h>
+
+#include <algorithm>
+
+#include "sk_common.cuh"
+
+#define SINC_LEN 256
+#define OVERSAMPLING 256
+#define STREAM_CHUNK 4096  // RESAMPLE_CHUNK_SIZE, soundkit-decoder/src/lib.rs:79
+
+// ================================================================================================
+// host: table and index plan
+// ================================================================================================
+
+// rubato sinc.rs make_sincs::<f32> + windows.rs blackman_harris (squared: BlackmanHarris2), f32 throughout
+static void build_sinc_table(double ratio, std::vector<float>& sincs) {
+    const float f_cutoff = ratio >= 1.0 ? 0.95f : 0.95f * (float)ratio;  // make_interpolator
+    const size_t tot = (size_t)SINC_LEN * OVERSAMPLING;
+    std::vector<float> y(tot);
+    const float pi = 3.14159265358979323846264338327950288f;
+    const float pi2 = 2.0f * pi, pi4 = 4.0f * pi, pi6 = 6.0f * pi;
+    const float npf = (float)tot;
+    float sum = 0.0f;
+    for (size_t x = 0; x < tot; x++) {
+        const float xf = (float)x;
+        float w = 0.35875f - 0.48829f * cosf(pi2 * xf / npf) + 0.14128f * cosf(pi4 * xf / npf) - 0.01168f * cosf(pi6 * xf / npf);
+        w = w * w;
+        const float v = (xf - (float)(tot / 2)) * f_cutoff / (float)OVERSAMPLING;
+        const float s = v == 0.0f ? 1.0f : sinf(v * pi) / (v * pi);
+        const float val = w * s;
+        sum += val;
+        y[x] = val;
+    }
+    sum /= (float)OVERSAMPLING;
+    sincs.resize(tot);
+    for (size_t p = 0; p < SINC_LEN; p++)
+        for (size_t n = 0; n < OVERSAMPLING; n++) sincs[(OVERSAMPLING - n - 1) * SINC_LEN + p] = y[OVERSAMPLING * p + n] / sum;
+}
+
+static uint64_t rate_key(uint32_t in_rate, uint32_t out_rate) { return ((uint64_t)in_rate << 32) | out_rate; }
+
+static int get_sinc_table(sk_ctx* ctx, uint32_t in_rate, uint32_t out_rate, const float** d_table, const std::vector<float>** h_table) {
+    const uint64_t key = rate_key(in_rate, out_rate);
+    auto it = ctx->sinc_tables.find(key);
+    if (it == ctx->sinc_tables.end()) {
+        std::vector<float>& h = ctx->sinc_host[key];
+        build_sinc_table((double)out_rate / (double)in_rate, h);
+        float* d = nullptr;
+        SK_CUDA(ctx, cudaMalloc((void**)&d, h.size() * sizeof(float)));
+        SK_CUDA(ctx, cudaMemcpyAsync(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        SK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        it = ctx->sinc_tables.emplace(key, d).first;
+    }
+    if (d_table) *d_table = it->second;
+    if (h_table) *h_table = &ctx->sinc_host[key];
+    return SK_OK;
+}
+
+// one rubato chunk: walks idx from last_index, appends (chunk_start + floor(idx), subindex, frac)
+struct WalkOut {
+    std::vector<int32_t> i0; std::vector<uint8_t> s0; std::vector<float> frac;
+    size_t count = 0; bool record = true;
+};
+static double walk_chunk(double last_index, double ratio, size_t chunk, long long chunk_start, WalkOut& w) {
+    const double t_ratio = 1.0 / ratio;
+    const long long end_idx = (long long)chunk - (SINC_LEN + 1) - (long long)ceil(t_ratio);
+    double idx = last_index;
+    while (idx < (double)end_idx) {
+        idx += t_ratio;  // sequential f64 accumulation, reproduced bit for bit
+        if (w.record) {
+            const double fl = floor(idx);
+            w.i0.push_back((int32_t)(chunk_start + (long long)fl));
+            w.s0.push_back((uint8_t)(long long)floor((idx - fl) * (double)OVERSAMPLING));  // get_nearest_times_2
+            const double f = idx * (double)OVERSAMPLING;
+            w.frac.push_back((float)(f - floor(f)));
+        }
+        w.count++;
+    }
+    return idx - (double)chunk;
+}
+
+struct sk_plan {
+    size_t n_out = 0;
+    bool integer_step = false;
+    int step = 0;
+    long long i0_first = 0;  // integer path: i0[n] = i0_first + step * n
+    // general path
+    int32_t* d_i0 = nullptr; uint8_t* d_s0 = nullptr; float* d_frac = nullptr;
+    int period = 8;          // outputs per phase period used for the phase-major tile mapping
+    int max_window = 0;      // largest input window (frames) any tile of 32*period outputs needs
+};
+
+static uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
+
+static void free_plan(sk_plan* p) {
+    if (!p) return;
+    if (p->d_i0) cudaFree(p->d_i0);
+    if (p->d_s0) cudaFree(p->d_s0);
+    if (p->d_frac) cudaFree(p->d_frac);
+    delete p;
+}
+
+void sk_resample_free_ctx(sk_ctx* ctx) {
+    for (auto& kv : ctx->sinc_tables) cudaFree(kv.second);
+    ctx->sinc_tables.clear();
+    for (auto& kv : ctx->plans) free_plan(kv.second);
+    ctx->plans.clear();
+}
+
+static const int kGenMaxWindow = 14400;  // frames of shared memory window the general kernel may use (57.6 KB)
+
+// finish a general plan from recorded walk arrays: choose the tile period and upload
+static int finalize_general_plan(sk_ctx* ctx, sk_plan* p, uint32_t in_rate, uint32_t out_rate, const WalkOut& w) {
+    p->n_out = w.i0.size();
+    const uint32_t g = gcd_u32(in_rate, out_rate);
+    const uint32_t L = out_rate / g;
+    auto window_for = [&](int period) {
+        int mw = 0;
+        const size_t tile = (size_t)period * 32;
+        for (size_t n0 = 0; n0 < p->n_out; n0 += tile) {
+            size_t n1 = std::min(p->n_out, n0 + tile) - 1;
+            int span = w.i0[n1] - w.i0[n0] + SINC_LEN + 2;
+            mw = std::max(mw, span);
+        }
+        return mw;
+    };
+    p->period = 8;
+    if (L >= 8 && L <= 512) {
+        int mw = window_for((int)L);
+        if (mw <= kGenMaxWindow) p->period = (int)L;
+    }
+    p->max_window = window_for(p->period);
+    if (p->n_out) {
+        SK_CUDA(ctx, cudaMalloc((void**)&p->d_i0, p->n_out * sizeof(int32_t)));
+        SK_CUDA(ctx, cudaMalloc((void**)&p->d_s0, p->n_out));
+        SK_CUDA(ctx, cudaMalloc((void**)&p->d_frac, p->n_out * sizeof(float)));
+        SK_CUDA(ctx, cudaMemcpyAsync(p->d_i0, w.i0.data(), p->n_out * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        SK_CUDA(ctx, cudaMemcpyAsync(p->d_s0, w.s0.data(), p->n_out, cudaMemcpyHostToDevice, ctx->stream));
+        SK_CUDA(ctx, cudaMemcpyAsync(p->d_frac, w.frac.data(), p->n_out * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        SK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // vectors die with the caller
+    }
+    return SK_OK;
+}
+
+static bool integer_step_of(uint32_t in_rate, uint32_t out_rate, int* step) {
+    if (in_rate % out_rate) return false;
+    uint32_t s = in_rate / out_rate;
+    if (s == 2 || s == 3 || s == 4 || s == 6 || s == 12) { *step = (int)s; return true; }
+    return false;
+}
+
+// whole-stream plan for the batch entry points
+static int build_stream_plan(sk_ctx* ctx, uint32_t in_rate, uint32_t out_rate, size_t frames, int semantics, sk_plan** out) {
+    char key[96];
+    snprintf(key, sizeof(key), "%u:%u:%zu:%d", in_rate, out_rate, frames, semantics);
+    auto it = ctx->plans.find(key);
+    if (it != ctx->plans.end()) { *out = it->second; return SK_OK; }
+    const double ratio = (double)out_rate / (double)in_rate;
+    sk_plan* p = new sk_plan();
+    int step = 0;
+    p->integer_step = integer_step_of(in_rate, out_rate, &step);
+    WalkOut w;
+    w.record = !p->integer_step;
+    if (semantics == SK_SEM_ONESHOT) {
+        walk_chunk(-(double)(SINC_LEN / 2), ratio, frames, 0, w);  // SincFixedIn::new(.., chunk = frames) + one process()
+    } else if (frames > 0) {  // no AudioData ever arrives for an empty stream, so no resampler exists to flush
+        // StreamingResampler::process + flush (decoder lib.rs:1970-2059)
+        double last = -(double)(SINC_LEN / 2);
+        size_t pos = 0;
+        while (frames - pos >= STREAM_CHUNK) { last = walk_chunk(last, ratio, STREAM_CHUNK, (long long)pos, w); pos += STREAM_CHUNK; }
+        const size_t remaining = frames - pos;
+        const size_t before = w.count;
+        walk_chunk(last, ratio, STREAM_CHUNK, (long long)pos, w);  // process_partial: zero-padded (or all-zero) chunk
+        if (remaining > 0) {
+            const size_t padded = STREAM_CHUNK - remaining;
+            const size_t trim = (size_t)llround(((double)padded * (double)out_rate) / (double)in_rate);
+            const size_t got = w.count - before;
+            const size_t keep = got > trim ? got - trim : 0;
+            w.count = before + keep;
+            if (w.record) { w.i0.resize(w.count); w.s0.resize(w.count); w.frac.resize(w.count); }
+        }
+    }
+    if (p->integer_step) {
+        p->step = step;
+        p->n_out = w.count;
+        p->i0_first = -(long long)(SINC_LEN / 2) + step;
+    } else {
+        int rc = finalize_general_plan(ctx, p, in_rate, out_rate, w);
+        if (rc) { free_plan(p); return rc; }
+    }
+    ctx->plans[key] = p;
+    *out = p;
+    return SK_OK;
+}
+
+// ================================================================================================
+// device: window staging (optional fused PCM conversion)
+// ================================================================================================
+struct SrcDesc {
+    const uint8_t* base;      // stream 0, lane 0
+    long long stream_stride;  // bytes between streams
+    long long lane_stride;    // planar: bytes between channel planes; interleaved: unused
+    int width;                // 0 = planar f32, 2/3/4 = interleaved sample bytes
+    int channels;             // channels per stream
+    int big_endian, is_float, scrub;
+    float scale;              // exact power of two for integer sources
+    long long origin;         // frame index i lives at element i + origin
+    long long valid_lo, valid_hi;  // frames outside [lo, hi) read as 0.0 (initial history / flush padding)
+};
+
+__device__ __forceinline__ float decode_sample_bits(uint32_t u, const SrcDesc& s) {
+    // u holds the sample bytes assembled little-endian (after the optional byte swap)
+    if (s.width == 2) return __fmul_rn((float)(int16_t)u, s.scale);
+    if (s.width == 3) return __fmul_rn((float)(((int32_t)(u << 8)) >> 8), s.scale);
+    if (s.is_float) {
+        float f = __uint_as_float(u);
+        if (s.scrub && (u & 0x7f800000u) == 0x7f800000u) f = 0.0f;
+        return f;
+    }
+    return __fmul_rn(__int2float_rn((int32_t)u), s.scale);
+}
+
+// sample of channel `ch` of frame `f` (absolute frame index, already range checked) of stream `sbase`
+__device__ __forceinline__ uint32_t load_sample_bits(const uint8_t* sbase, long long f, int ch, const SrcDesc& s) {
+    const uint8_t* p = sbase + ((f + s.origin) * s.channels + ch) * (long long)s.width;
+    uint32_t u;
+    if (s.width == 2) { u = *reinterpret_cast<const uint16_t*>(p); if (s.big_endian) u = ((u & 0xff) << 8) | (u >> 8); }
+    else if (s.width == 3) {
+        uint32_t b0 = p[0], b1 = p[1], b2 = p[2];
+        u = s.big_endian ? (b2 | (b1 << 8) | (b0 << 16)) : (b0 | (b1 << 8) | (b2 << 16));
+    } else { u = *reinterpret_cast<const uint32_t*>(p); if (s.big_endian) u = bswap32(u); }
+    return u;
+}
+
+// Fill win0/win1[0..count) with frames [w0, w0+count) of lanes (lane0, lane0+1) of one stream.
+// Thread-per-frame: consecutive threads touch consecutive frames, so global reads coalesce into
+// whole sectors and the shared-memory stores are conflict free.  Returns (block-wide OR'ed later)
+// whether a value with |x| >= 2^113 (or non-finite) was staged — only possible for float sources.
+template <int NTHREADS>
+__device__ __forceinline__ bool stage_window(const SrcDesc& s, long long stream, int lane0, bool lane1_valid, long long w0, int count,
+                                             float* win0, float* win1) {
+    bool big = false;
+    if (s.width == 0) {
+        const float* p0 = reinterpret_cast<const float*>(s.base + stream * s.stream_stride + (long long)lane0 * s.lane_stride);
+        const float* p1 = reinterpret_cast<const float*>(s.base + stream * s.stream_stride + (long long)(lane0 + 1) * s.lane_stride);
+        for (int i = threadIdx.x; i < count; i += NTHREADS) {
+            const long long f = w0 + i;
+            const bool ok = f >= s.valid_lo && f < s.valid_hi;
+            float a = ok ? __ldg(p0 + f + s.origin) : 0.0f;
+            float b = (ok && lane1_valid) ? __ldg(p1 + f + s.origin) : 0.0f;
+            big |= ((__float_as_uint(a) & 0x7f800000u) >= 0x78000000u) | ((__float_as_uint(b) & 0x7f800000u) >= 0x78000000u);
+            win0[i] = a; if (win1) win1[i] = b;
+        }
+    } else {
+        const uint8_t* sbase = s.base + stream * s.stream_stride;
+        const bool stereo_pair = (s.channels == 2) && lane1_valid && lane0 == 0;
+        for (int i = threadIdx.x; i < count; i += NTHREADS) {
+            const long long f = w0 + i;
+            float a = 0.0f, b = 0.0f;
+            if (f >= s.valid_lo && f < s.valid_hi) {
+                if (stereo_pair && s.width == 2) {
+                    uint32_t u = *reinterpret_cast<const uint32_t*>(sbase + (f + s.origin) * 4);
+                    uint32_t l = u & 0xffffu, r = u >> 16;
+                    if (s.big_endian) { l = ((l & 0xff) << 8) | (l >> 8); r = ((r & 0xff) << 8) | (r >> 8); }
+                    a = decode_sample_bits(l, s); b = decode_sample_bits(r, s);
+                } else if (stereo_pair && s.width == 3) {
+                    const uint16_t* p = reinterpret_cast<const uint16_t*>(sbase + (f + s.origin) * 6);
+                    uint32_t h0 = p[0], h1 = p[1], h2 = p[2];
+                    uint32_t l, r;
+                    if (!s.big_endian) { l = h0 | ((h1 & 0xff) << 16); r = (h1 >> 8) | (h2 << 8); }
+                    else { l = ((h0 & 0xff) << 16) | (h0 & 0xff00) | (h1 & 0xff); r = ((h1 >> 8) << 16) | ((h2 & 0xff) << 8) | (h2 >> 8); }
+                    a = decode_sample_bits(l, s); b = decode_sample_bits(r, s);
+                } else if (stereo_pair && s.width == 4) {
+                    uint2 u = *reinterpret_cast<const uint2*>(sbase + (f + s.origin) * 8);
+                    if (s.big_endian) { u.x = bswap32(u.x); u.y = bswap32(u.y); }
+                    a = decode_sample_bits(u.x, s); b = decode_sample_bits(u.y, s);
+                } else {
+                    a = decode_sample_bits(load_sample_bits(sbase, f, lane0, s), s);
+                    if (lane1_valid) b = decode_sample_bits(load_sample_bits(sbase, f, lane0 + 1, s), s);
+                }
+                if (s.is_float) big |= ((__float_as_uint(a) & 0x7f800000u) >= 0x78000000u) | ((__float_as_uint(b) & 0x7f800000u) >= 0x78000000u);
+            }
+            win0[i] = a; if (win1) win1[i] = b;
+        }
+    }
+    return big;
+}
+
+// rubato interpolator_avx.rs reduction: (hi128 + lo128) then two hadds
+__device__ __forceinline__ float reduce8(const float* a) {
+    return __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[4]), __fadd_rn(a[1], a[5])), __fadd_rn(__fadd_rn(a[2], a[6]), __fadd_rn(a[3], a[7])));
+}
+
+// generic 256-tap dot product in rubato's lane order; x in shared memory (any alignment), h 16-byte aligned global/shared
+__device__ __forceinline__ float dot256(const float* x, const float* __restrict__ h) {
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int k = 0; k < SINC_LEN; k += 8) {
+        const float4 h0 = __ldg(reinterpret_cast<const float4*>(h + k));
+        const float4 h1 = __ldg(reinterpret_cast<const float4*>(h + k + 4));
+        a[0] = __fmaf_rn(x[k + 0], h0.x, a[0]); a[1] = __fmaf_rn(x[k + 1], h0.y, a[1]);
+        a[2] = __fmaf_rn(x[k + 2], h0.z, a[2]); a[3] = __fmaf_rn(x[k + 3], h0.w, a[3]);
+        a[4] = __fmaf_rn(x[k + 4], h1.x, a[4]); a[5] = __fmaf_rn(x[k + 5], h1.y, a[5]);
+        a[6] = __fmaf_rn(x[k + 6], h1.z, a[6]); a[7] = __fmaf_rn(x[k + 7], h1.w, a[7]);
+    }
+    return reduce8(a);
+}
+
+struct OutDesc {
+    float* base;
+    long long stream_stride;  // floats between streams
+    long long lane_stride;    // floats between channel planes (mix none)
+    int mix;                  // sk_mix_mode; != NONE only with exactly two lanes per stream
+    long long n_out;
+};
+
+// ================================================================================================
+// integer-step kernel
+// ================================================================================================
+struct Taps { float h[SINC_LEN]; };
+
+template <int STEP> struct IntCfg;
+// R outputs per thread and the bank skew between the two lanes' windows, chosen so that the 8
+// threads of an LDS.128 quarter-warp (4 thread-blocks x 2 lanes) hit 8 distinct 4-bank groups:
+// thread stride S = STEP*R words; need {S*b mod 32, b<4} U {S*b + SKEW mod 32} to be 8 distinct
+// multiples of 4.
+template <> struct IntCfg<3>  { static constexpr int R = 8, SKEW = 4;  };  // S = 24: {0,24,16,8} + 4
+template <> struct IntCfg<2>  { static constexpr int R = 6, SKEW = 16; };  // S = 12: {0,12,24,4} + 16
+template <> struct IntCfg<4>  { static constexpr int R = 7, SKEW = 16; };  // S = 28: {0,28,24,20} + 16
+template <> struct IntCfg<6>  { static constexpr int R = 6, SKEW = 16; };  // S = 36: {0,4,8,12} + 16
+template <> struct IntCfg<12> { static constexpr int R = 7, SKEW = 16; };  // S = 84: {0,20,8,28} + 16
+
+constexpr int kIntThreads = 256;                 // 128 thread-blocks x 2 lanes
+constexpr int kIntBlocksPerLane = kIntThreads / 2;
+
+template <int STEP> __host__ __device__ constexpr int int_tile_outputs() { return kIntBlocksPerLane * IntCfg<STEP>::R; }
+template <int STEP> __host__ __device__ constexpr int int_window() { return STEP * (int_tile_outputs<STEP>() - 1) + SINC_LEN; }
+template <int STEP> __host__ __device__ constexpr int int_lane_stride() { return ((int_window<STEP>() + 4 + 31) / 32) * 32 + IntCfg<STEP>::SKEW; }
+template <int STEP> __host__ __device__ constexpr int int_smem_bytes() { return 2 * int_lane_stride<STEP>() * (int)sizeof(float); }
+
+// The FIR core: walk the thread's input span once; each LDS.128 feeds 4*R FFMAs whose coefficient
+// operand is a kernel-parameter constant (c[0x0][..]).  Accumulator (r, l) sees its taps in
+// increasing order, i.e. exactly rubato's per-lane fused accumulation.
+template <int STEP, int R>
+__device__ __forceinline__ void fir_core(const float* __restrict__ w, const Taps& taps, float (&acc)[R][8]) {
+    constexpr int NIN = STEP * (R - 1) + SINC_LEN;
+    constexpr int NV = (NIN + 3) / 4;
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+        const float4 q = *reinterpret_cast<const float4*>(w + 4 * v);
+        const float xs[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int m = 4 * v + e;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int j = m - STEP * r;
+                if (j >= 0 && j < SINC_LEN) acc[r][j & 7] = __fmaf_rn(xs[e], taps.h[j], acc[r][j & 7]);
+            }
+        }
+    }
+}
+
+template <int STEP>
+__global__ void __launch_bounds__(kIntThreads, 2)
+resample_int_kernel(const __grid_constant__ Taps taps, const __grid_constant__ SrcDesc src, const __grid_constant__ OutDesc dst,
+                    long long i0_first, int lanes_per_stream, const float* __restrict__ row1) {
+    constexpr int R = IntCfg<STEP>::R;
+    constexpr int T = int_tile_outputs<STEP>();
+    constexpr int W = int_window<STEP>();
+    constexpr int WS = int_lane_stride<STEP>();
+    extern __shared__ __align__(16) float smem[];
+    __shared__ int s_big;
+
+    // blockIdx.y enumerates lane pairs: pair p of stream s covers lanes 2p, 2p+1
+    const int pairs_per_stream = (lanes_per_stream + 1) >> 1;
+    const long long stream = blockIdx.y / pairs_per_stream;
+    const int lane0 = (blockIdx.y % pairs_per_stream) * 2;
+    const bool lane1_valid = lane0 + 1 < lanes_per_stream;
+    const long long n0 = (long long)blockIdx.x * T;
+    const long long w0 = i0_first + (long long)STEP * n0;
+
+    if (threadIdx.x == 0) s_big = 0;
+    __syncthreads();
+    const bool big = stage_window<kIntThreads>(src, stream, lane0, lane1_valid, w0, W, smem, smem + WS);
+    if (big) s_big = 1;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 1, b = threadIdx.x >> 1;
+    const float* w = smem + lane * WS + STEP * R * b;
+    float acc[R][8];
+#pragma unroll
+    for (int r = 0; r < R; r++)
+#pragma unroll
+        for (int l = 0; l < 8; l++) acc[r][l] = 0.0f;
+    fir_core<STEP, R>(w, taps, acc);
+
+    float y[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) y[r] = reduce8(acc[r]);
+    if (s_big) {
+        // some |x| >= 2^113 in this window: p1 may overflow where p0 does not, so evaluate the
+        // reference's full expression p0 + 0.0 * (p1 - p0) (subindex 1, same input index)
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const float p1 = dot256(w + STEP * r, row1);
+            y[r] = __fadd_rn(y[r], __fmul_rn(0.0f, __fsub_rn(p1, y[r])));
+        }
+    }
+
+    const long long nb = n0 + (long long)R * b;  // first output of this thread
+    if (dst.mix != SK_MIX_NONE) {
+        // lanes are (L, R) of one stream in adjacent threads: exchange, then each thread stores half
+        float o[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const float other = __shfl_xor_sync(0xffffffffu, y[r], 1);
+            const float l = lane == 0 ? y[r] : other, rr = lane == 0 ? other : y[r];
+            if (dst.mix == SK_MIX_SCALE_THEN_SUM) o[r] = __fadd_rn(__fadd_rn(0.0f, __fmul_rn(l, 0.5f)), __fmul_rn(rr, 0.5f));
+            else o[r] = __fmul_rn(__fadd_rn(__fadd_rn(0.0f, l), rr), 0.5f);
+        }
+        float* op = dst.base + stream * dst.stream_stride;
+        constexpr int H = (R + 1) / 2;
+        if (R == 8 && nb + 8 <= dst.n_out && ((dst.stream_stride & 3) == 0)) {
+            const float4 v = lane == 0 ? make_float4(o[0], o[1], o[2], o[3]) : make_float4(o[4], o[5], o[6], o[7]);
+            *reinterpret_cast<float4*>(op + nb + 4 * lane) = v;
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if ((r / H) == lane && nb + r < dst.n_out) op[nb + r] = o[r];
+        }
+    } else {
+        if (lane == 1 && !lane1_valid) return;
+        float* op = dst.base + stream * dst.stream_stride + (long long)(lane0 + lane) * dst.lane_stride;
+        if (R % 4 == 0 && nb + R <= dst.n_out && ((dst.stream_stride | dst.lane_stride) & 3) == 0) {
+#pragma unroll
+            for (int v = 0; v < R / 4; v++) *reinterpret_cast<float4*>(op + nb + 4 * v) = make_float4(y[4 * v], y[4 * v + 1], y[4 * v + 2], y[4 * v + 3]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if (nb + r < dst.n_out) op[nb + r] = y[r];
+        }
+    }
+}
+
+// ================================================================================================
+// general kernel (any ratio): one lane per CTA, phase-major tile
+// ================================================================================================
+constexpr int kGenThreads = 256;
+
+__global__ void __launch_bounds__(kGenThreads)
+resample_gen_kernel(const __grid_constant__ SrcDesc src, const __grid_constant__ OutDesc dst, const int32_t* __restrict__ pi0,
+                    const uint8_t* __restrict__ ps0, const float* __restrict__ pfrac, const float* __restrict__ table, int period,
+                    int lanes_per_stream) {
+    extern __shared__ __align__(16) float win[];
+    const long long stream = blockIdx.y / lanes_per_stream;
+    const int lane_ch = blockIdx.y % lanes_per_stream;
+    const long long tile = (long long)period * 32;
+    const long long n0 = (long long)blockIdx.x * tile;
+    const long long n1 = min(dst.n_out, n0 + tile) - 1;  // last output of this tile
+    const int w0 = pi0[n0];
+    const int count = pi0[n1] - w0 + SINC_LEN + 2;
+    stage_window<kGenThreads>(src, stream, lane_ch, false, (long long)w0, count, win, nullptr);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, q = threadIdx.x & 31;
+    float* op = dst.base + stream * dst.stream_stride + (long long)lane_ch * dst.lane_stride;
+    for (int phase = warp; phase < period; phase += kGenThreads / 32) {
+        const long long n = n0 + (long long)q * period + phase;
+        if (n > n1) continue;
+        const int i0 = pi0[n];
+        const int s0 = ps0[n];
+        const float frac = pfrac[n];
+        int s1 = s0 + 1, d = 0;
+        if (s1 >= OVERSAMPLING) { s1 -= OVERSAMPLING; d = 1; }  // get_nearest_times_2
+        const float* x = win + (i0 - w0);
+        const float* h0 = table + s0 * SINC_LEN;
+        const float* h1 = table + s1 * SINC_LEN;
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, c[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+        for (int k = 0; k < SINC_LEN; k += 8) {
+            float xs[9];
+#pragma unroll
+            for (int l = 0; l < 9; l++) xs[l] = x[k + l];
+            const float4 ha = __ldg(reinterpret_cast<const float4*>(h0 + k)), hb = __ldg(reinterpret_cast<const float4*>(h0 + k + 4));
+            const float4 hc = __ldg(reinterpret_cast<const float4*>(h1 + k)), hd = __ldg(reinterpret_cast<const float4*>(h1 + k + 4));
+            const float g0[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+            const float g1[8] = {hc.x, hc.y, hc.z, hc.w, hd.x, hd.y, hd.z, hd.w};
+#pragma unroll
+            for (int l = 0; l < 8; l++) {
+                a[l] = __fmaf_rn(xs[l], g0[l], a[l]);
+                c[l] = __fmaf_rn(d ? xs[l + 1] : xs[l], g1[l], c[l]);
+            }
+        }
+        const float p0 = reduce8(a), p1 = reduce8(c);
+        op[n] = __fadd_rn(p0, __fmul_rn(frac, __fsub_rn(p1, p0)));  // interp_lin
+    }
+}
+
+// ================================================================================================
+// host: launch helpers
+// ================================================================================================
+static int src_desc_for(sk_ctx* ctx, SrcDesc* s, const void* in, size_t in_stride, int bits, int fmt, int big_endian, int channels, int scale_mode,
+                        size_t frames) {
+    memset(s, 0, sizeof(*s));
+    s->base = (const uint8_t*)in;
+    s->stream_stride = (long long)in_stride;
+    s->channels = channels;
+    s->origin = 0; s->valid_lo = 0; s->valid_hi = (long long)frames;
+    if (bits != 16 && bits != 24 && bits != 32) SK_FAIL(ctx, SK_E_ARG, "Unsupported bits_per_sample: %d", bits);
+    if (fmt == SK_FMT_FLOAT && bits != 32) SK_FAIL(ctx, SK_E_ARG, "floating-point PCM must contain 32-bit samples");
+    s->width = bits / 8;
+    s->big_endian = scale_mode == SK_MODE_B ? (big_endian != 0) : 0;  // mode A is always little-endian
+    s->is_float = fmt == SK_FMT_FLOAT;
+    s->scrub = scale_mode == SK_MODE_B;
+    if (bits == 16) s->scale = 1.0f / 32768.0f;
+    else if (bits == 24) s->scale = scale_mode == SK_MODE_A ? 4.656612873077393e-10f : 1.0f / 8388608.0f;
+    else s->scale = 4.656612873077393e-10f;
+    return SK_OK;
+}
+
+template <int STEP>
+static int launch_int(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, const float* h_table, const float* d_table,
+                      size_t n_streams, int lanes_per_stream) {
+    Taps taps;
+    memcpy(taps.h, h_table, sizeof(taps.h));  // subindex 0
+    constexpr int T = int_tile_outputs<STEP>();
+    constexpr int smem = int_smem_bytes<STEP>();
+    SK_CUDA(ctx, cudaFuncSetAttribute(resample_int_kernel<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const size_t tiles = (plan->n_out + T - 1) / T;
+    const size_t pairs = (size_t)((lanes_per_stream + 1) / 2) * n_streams;
+    const size_t pps = (size_t)((lanes_per_stream + 1) / 2);
+    const size_t slab = (65535 / pps) * pps;  // gridDim.y is limited to 65535: whole streams per slab
+    for (size_t p0 = 0; p0 < pairs; p0 += slab) {
+        const size_t np = std::min<size_t>(slab, pairs - p0);
+        SrcDesc s2 = src; OutDesc d2 = dst;
+        const size_t stream0 = p0 / pps;
+        s2.base += (long long)stream0 * src.stream_stride;
+        d2.base += (long long)stream0 * dst.stream_stride;
+        dim3 grid((unsigned)tiles, (unsigned)np);
+        resample_int_kernel<STEP><<<grid, kIntThreads, smem, ctx->stream>>>(taps, s2, d2, plan->i0_first, lanes_per_stream, d_table + SINC_LEN);
+        SK_LAUNCH_CHECK(ctx);
+    }
+    return SK_OK;
+}
+
+static int launch_gen(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, const float* d_table, size_t n_streams,
+                      int lanes_per_stream) {
+    const int smem = (plan->max_window + 8) * (int)sizeof(float);
+    SK_CUDA(ctx, cudaFuncSetAttribute(resample_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const size_t tile = (size_t)plan->period * 32;
+    const size_t tiles = (plan->n_out + tile - 1) / tile;
+    const size_t lanes = (size_t)lanes_per_stream * n_streams;
+    for (size_t l0 = 0; l0 < lanes; l0 += (size_t)lanes_per_stream * (65535 / lanes_per_stream)) {
+        const size_t nl = std::min<size_t>((size_t)lanes_per_stream * (65535 / lanes_per_stream), lanes - l0);
+        SrcDesc s2 = src; OutDesc d2 = dst;
+        const size_t stream0 = l0 / lanes_per_stream;
+        s2.base += (long long)stream0 * src.stream_stride;
+        d2.base += (long long)stream0 * dst.stream_stride;
+        dim3 grid((unsigned)tiles, (unsigned)nl);
+        resample_gen_kernel<<<grid, kGenThreads, smem, ctx->stream>>>(s2, d2, plan->d_i0, plan->d_s0, plan->d_frac, d_table, plan->period, lanes_per_stream);
+        SK_LAUNCH_CHECK(ctx);
+    }
+    return SK_OK;
+}
+
+// run one plan over a batch.  mix != NONE requires exactly two lanes per stream for the fused path;
+// the caller handles other channel counts with a separate mixdown pass.
+static int run_plan(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, uint32_t in_rate, uint32_t out_rate, size_t n_streams,
+                    int lanes_per_stream) {
+    if (!plan->n_out || !n_streams) return SK_OK;
+    const float* d_table; const std::vector<float>* h_table;
+    int rc = get_sinc_table(ctx, in_rate, out_rate, &d_table, &h_table);
+    if (rc) return rc;
+    if (plan->integer_step) {
+        switch (plan->step) {
+            case 2: return launch_int<2>(ctx, src, dst, plan, h_table->data(), d_table, n_streams, lanes_per_stream);
+            case 3: return launch_int<3>(ctx, src, dst, plan, h_table->data(), d_table, n_streams, lanes_per_stream);
+            case 4: return launch_int<4>(ctx, src, dst, plan, h_table->data(), d_table, n_streams, lanes_per_stream);
+            case 6: return launch_int<6>(ctx, src, dst, plan, h_table->data(), d_table, n_streams, lanes_per_stream);
+            case 12: return launch_int<12>(ctx, src, dst, plan, h_table->data(), d_table, n_streams, lanes_per_stream);
+        }
+        SK_FAIL(ctx, SK_E_STATE, "internal: no kernel for integer step %d", plan->step);
+    }
+    if (dst.mix != SK_MIX_NONE) SK_FAIL(ctx, SK_E_STATE, "internal: general kernel does not mix");
+    return launch_gen(ctx, src, dst, plan, d_table, n_streams, lanes_per_stream);
+}
+
+// ================================================================================================
+// C ABI: batch chain
+// ================================================================================================
+extern "C" int sk_normalize_batch_plan(sk_ctx* ctx, uint32_t in_rate, uint32_t out_rate, size_t frames, int semantics, size_t* n_out) {
+    if (!ctx) return SK_E_ARG;
+    if (!in_rate || !out_rate) SK_FAIL(ctx, SK_E_ARG, "sampling_rate must be > 0");
+    if (semantics != SK_SEM_ONESHOT && semantics != SK_SEM_STREAMING) SK_FAIL(ctx, SK_E_ARG, "unknown semantics %d", semantics);
+    if (frames > 0x7fff0000ull) SK_FAIL(ctx, SK_E_ARG, "stream too long (%zu frames)", frames);
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    sk_plan* p;
+    int rc = build_stream_plan(ctx, in_rate, out_rate, frames, semantics, &p);
+    if (rc) return rc;
+    if (n_out) *n_out = p->n_out;
+    return SK_OK;
+}
+
+int sk_mixdown_strided_dev(sk_ctx* ctx, const float* planar, size_t plane_stride, size_t frames, int channels, int mix_mode, float* out);  // sk_pcm.cu
+
+extern "C" int sk_normalize_batch_dev(sk_ctx* ctx, const sk_batch_desc* d) {
+    if (!ctx || !d) return SK_E_ARG;
+    if (d->channels <= 0 || d->channels > 255) SK_FAIL(ctx, SK_E_ARG, "Channel count must be > 0");
+    if (!d->in_rate || !d->out_rate) SK_FAIL(ctx, SK_E_ARG, "sampling_rate must be > 0");
+    if (d->mix_mode < SK_MIX_NONE || d->mix_mode > SK_MIX_SCALE_THEN_SUM) SK_FAIL(ctx, SK_E_ARG, "unknown mix mode %d", d->mix_mode);
+    if (!d->n_streams) return SK_OK;
+    if (!d->in || !d->out) SK_FAIL(ctx, SK_E_ARG, "null buffer");
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    sk_plan* plan;
+    int rc = build_stream_plan(ctx, d->in_rate, d->out_rate, d->frames, d->semantics, &plan);
+    if (rc) return rc;
+    SrcDesc src;
+    if ((rc = src_desc_for(ctx, &src, d->in, d->in_stride, d->bits, d->fmt, d->big_endian, d->channels, d->scale_mode, d->frames))) return rc;
+    OutDesc dst;
+    dst.base = d->out; dst.stream_stride = (long long)d->out_stride; dst.lane_stride = (long long)d->out_stride_ch;
+    dst.n_out = (long long)plan->n_out;
+    int mix = d->channels == 1 ? SK_MIX_NONE : d->mix_mode;  // a mono source is never downmixed (emit_resampled_chunks)
+    if (mix != SK_MIX_NONE && (d->channels != 2 || !plan->integer_step)) {
+        // unfused: resample to a planar scratch, then mix down stream by stream
+        const size_t plane = sk_round_up(plan->n_out, 4);
+        const size_t per_stream = plane * d->channels;
+        // bound the scratch: process streams in slabs
+        size_t slab = std::max<size_t>(1, (size_t)(1u << 28) / std::max<size_t>(1, per_stream));  // <= 1 GiB of floats
+        slab = std::min(slab, d->n_streams);
+        if ((rc = sk_ensure_dev_out(ctx, slab * per_stream * sizeof(float)))) return rc;
+        float* scratch = (float*)ctx->d_out;
+        for (size_t s0 = 0; s0 < d->n_streams; s0 += slab) {
+            const size_t ns = std::min(slab, d->n_streams - s0);
+            SrcDesc s2 = src; s2.base += (long long)s0 * src.stream_stride;
+            OutDesc d2; d2.base = scratch; d2.stream_stride = (long long)per_stream; d2.lane_stride = (long long)plane; d2.mix = SK_MIX_NONE;
+            d2.n_out = (long long)plan->n_out;
+            if ((rc = run_plan(ctx, s2, d2, plan, d->in_rate, d->out_rate, ns, d->channels))) return rc;
+            for (size_t s = 0; s < ns; s++) {
+                if ((rc = sk_mixdown_strided_dev(ctx, scratch + s * per_stream, plane, plan->n_out, d->channels, mix, d->out + (s0 + s) * d->out_stride)))
+                    return rc;
+            }
+        }
+        return SK_OK;
+    }
+    dst.mix = mix;
+    return run_plan(ctx, src, dst, plan, d->in_rate, d->out_rate, d->n_streams, d->channels);
+}
+
+extern "C" int sk_normalize_stream(sk_ctx* ctx, const uint8_t* in, size_t bytes, int bits, int fmt, int big_endian, int channels, int scale_mode,
+                                   uint32_t in_rate, uint32_t out_rate, int semantics, int mix_mode, float* out, size_t out_cap_per_plane,
+                                   size_t* n_out) {
+    if (!ctx) return SK_E_ARG;
+    if (channels <= 0 || channels > 255) SK_FAIL(ctx, SK_E_ARG, "Channel count must be > 0");
+    if (bits != 16 && bits != 24 && bits != 32) SK_FAIL(ctx, SK_E_ARG, "Unsupported bits_per_sample: %d", bits);
+    const size_t B = (size_t)bits / 8;
+    if (scale_mode == SK_MODE_B && (bytes % B != 0 || (bytes / B) % (size_t)channels != 0))
+        SK_FAIL(ctx, SK_E_ARG, "PCM data is unsupported or contains a partial frame");
+    const size_t frames = bytes / (B * channels);
+    size_t n = 0;
+    int rc = sk_normalize_batch_plan(ctx, in_rate, out_rate, frames, semantics, &n);
+    if (rc) return rc;
+    if (n_out) *n_out = n;
+    if (!n) return SK_OK;
+    if (n > out_cap_per_plane) SK_FAIL(ctx, SK_E_ARG, "output capacity %zu < %zu frames", out_cap_per_plane, n);
+    if (!in || !out) SK_FAIL(ctx, SK_E_ARG, "null buffer");
+    const int mix = channels == 1 ? SK_MIX_NONE : mix_mode;
+    const int planes = mix == SK_MIX_NONE ? channels : 1;
+    const size_t plane = sk_round_up(n, 4);
+    // device staging: input bytes in d_in; output planes in a private allocation (d_out may be used as mix scratch)
+    const size_t in_bytes = frames * B * channels;
+    if ((rc = sk_ensure_dev_in(ctx, in_bytes + 16))) return rc;
+    if ((rc = sk_h2d(ctx, ctx->d_in, in, in_bytes))) return rc;
+    float* d_res = nullptr;
+    SK_CUDA(ctx, cudaMalloc((void**)&d_res, plane * planes * sizeof(float)));
+    sk_batch_desc d;
+    memset(&d, 0, sizeof(d));
+    d.in = ctx->d_in; d.in_stride = in_bytes; d.n_streams = 1; d.frames = frames; d.bits = bits; d.fmt = fmt; d.big_endian = big_endian;
+    d.channels = channels; d.scale_mode = scale_mode; d.in_rate = in_rate; d.out_rate = out_rate; d.semantics = semantics; d.mix_mode = mix;
+    d.out = d_res; d.out_stride = plane * planes; d.out_stride_ch = plane;
+    rc = sk_normalize_batch_dev(ctx, &d);
+    for (int c = 0; c < planes && !rc; c++) rc = sk_d2h(ctx, out + (size_t)c * out_cap_per_plane, d_res + (size_t)c * plane, n * sizeof(float));
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_res);
+    return rc;
+}
+
+// ================================================================================================
+// C ABI: stateful per-stream resampler (rubato SincFixedIn)
+// ================================================================================================
+struct sk_resampler {
+    sk_ctx* ctx;
+    uint32_t in_rate, out_rate;
+    double ratio;
+    int channels;
+    size_t chunk;
+    double last_index;
+    float* d_buf = nullptr;   // [channels][2*SINC_LEN + chunk]: history then the current chunk
+    float* d_out = nullptr;   // [channels][out_max rounded up]
+    size_t out_plane = 0;
+    sk_plan plan;             // reused per chunk (general path arrays sized for out_max)
+    size_t plan_cap = 0;
+};
+
+// buffer.copy_within(chunk .. chunk + 2*sinc_len, 0): ranges may overlap when chunk < 2*sinc_len
+__global__ void history_shift_kernel(float* buf, size_t plane, size_t chunk) {
+    float* b = buf + (size_t)blockIdx.x * plane;
+    const float v = b[chunk + threadIdx.x];
+    __syncthreads();
+    b[threadIdx.x] = v;
+}
+
+extern "C" int sk_resampler_create(sk_ctx* ctx, uint32_t in_rate, uint32_t out_rate, int channels, size_t chunk, const sk_resample_params* params,
+                                   sk_resampler** out) {
+    if (!ctx || !out) return SK_E_ARG;
+    *out = nullptr;
+    if (!in_rate || !out_rate) SK_FAIL(ctx, SK_E_ARG, "sampling_rate must be > 0");
+    if (channels <= 0 || channels > 255) SK_FAIL(ctx, SK_E_ARG, "Channel count must be > 0");
+    if (params && (params->sinc_len != SINC_LEN || params->oversampling != OVERSAMPLING || params->f_cutoff != 0.95f || params->interp != 0 ||
+                   params->window != 0))
+        SK_FAIL(ctx, SK_E_ARG, "only soundkit's parameters are implemented: sinc_len 256, oversampling 256, f_cutoff 0.95, Linear, BlackmanHarris2");
+    if (chunk > 0x7fff0000ull) SK_FAIL(ctx, SK_E_ARG, "chunk too long");
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    sk_resampler* r = new (std::nothrow) sk_resampler();
+    if (!r) SK_FAIL(ctx, SK_E_ALLOC, "out of memory");
+    r->ctx = ctx; r->in_rate = in_rate; r->out_rate = out_rate; r->ratio = (double)out_rate / (double)in_rate;
+    r->channels = channels; r->chunk = chunk; r->last_index = -(double)(SINC_LEN / 2);
+    const size_t plane = 2 * SINC_LEN + chunk;
+    const size_t omax = (size_t)((double)chunk * r->ratio * 2.0 + 10.0);
+    r->out_plane = sk_round_up(omax, 4);
+    if (cudaMalloc((void**)&r->d_buf, plane * channels * sizeof(float)) != cudaSuccess ||
+        cudaMalloc((void**)&r->d_out, r->out_plane * channels * sizeof(float)) != cudaSuccess) {
+        sk_resampler_destroy(r);
+        SK_FAIL(ctx, SK_E_ALLOC, "device allocation failed");
+    }
+    cudaMemsetAsync(r->d_buf, 0, plane * channels * sizeof(float), ctx->stream);
+    int step;
+    r->plan.integer_step = integer_step_of(in_rate, out_rate, &step);
+    r->plan.step = r->plan.integer_step ? step : 0;
+    int rc = get_sinc_table(ctx, in_rate, out_rate, nullptr, nullptr);
+    if (rc) { sk_resampler_destroy(r); return rc; }
+    *out = r;
+    return SK_OK;
+}
+
+extern "C" void sk_resampler_destroy(sk_resampler* r) {
+    if (!r) return;
+    cudaSetDevice(r->ctx->device);
+    cudaStreamSynchronize(r->ctx->stream);
+    if (r->d_buf) cudaFree(r->d_buf);
+    if (r->d_out) cudaFree(r->d_out);
+    if (r->plan.d_i0) cudaFree(r->plan.d_i0);
+    if (r->plan.d_s0) cudaFree(r->plan.d_s0);
+    if (r->plan.d_frac) cudaFree(r->plan.d_frac);
+    delete r;
+}
+
+extern "C" size_t sk_resampler_out_max(const sk_resampler* r) { return r ? (size_t)((double)r->chunk * r->ratio * 2.0 + 10.0) : 0; }
+extern "C" double sk_resampler_last_index(const sk_resampler* r) { return r ? r->last_index : 0.0; }
+
+extern "C" int sk_resampler_copy_table(const sk_resampler* r, float* out65536) {
+    if (!r || !out65536) return SK_E_ARG;
+    const std::vector<float>* h;
+    int rc = get_sinc_table(r->ctx, r->in_rate, r->out_rate, nullptr, &h);
+    if (rc) return rc;
+    memcpy(out65536, h->data(), h->size() * sizeof(float));
+    return SK_OK;
+}
+
+static int resampler_run(sk_resampler* r, const float* const* in, size_t frames, float* const* out, size_t* n_out) {
+    sk_ctx* ctx = r->ctx;
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t plane = 2 * SINC_LEN + r->chunk;
+    // history shift, then the new chunk (zero padded to `chunk`)
+    history_shift_kernel<<<r->channels, 2 * SINC_LEN, 0, ctx->stream>>>(r->d_buf, plane, r->chunk);
+    SK_LAUNCH_CHECK(ctx);
+    int rc;
+    for (int c = 0; c < r->channels; c++) {
+        float* dst = r->d_buf + (size_t)c * plane + 2 * SINC_LEN;
+        if (in && frames) {
+            if ((rc = sk_h2d(ctx, dst, in[c], frames * sizeof(float)))) return rc;
+        }
+        if (frames < r->chunk) SK_CUDA(ctx, cudaMemsetAsync(dst + frames, 0, (r->chunk - frames) * sizeof(float), ctx->stream));
+    }
+    // index walk of this chunk
+    WalkOut w;
+    w.record = !r->plan.integer_step;
+    const double next_last = walk_chunk(r->last_index, r->ratio, r->chunk, 0, w);
+    const size_t n = w.count;
+    sk_plan& p = r->plan;
+    p.n_out = n;
+    if (p.integer_step) {
+        // idx is an exact integer on this path
+        p.i0_first = (long long)r->last_index + p.step;
+    } else if (n) {
+        if (n > r->plan_cap) {
+            if (p.d_i0) cudaFree(p.d_i0);
+            if (p.d_s0) cudaFree(p.d_s0);
+            if (p.d_frac) cudaFree(p.d_frac);
+            r->plan_cap = n + 64;
+            SK_CUDA(ctx, cudaMalloc((void**)&p.d_i0, r->plan_cap * sizeof(int32_t)));
+            SK_CUDA(ctx, cudaMalloc((void**)&p.d_s0, r->plan_cap));
+            SK_CUDA(ctx, cudaMalloc((void**)&p.d_frac, r->plan_cap * sizeof(float)));
+        }
+        SK_CUDA(ctx, cudaMemcpyAsync(p.d_i0, w.i0.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        SK_CUDA(ctx, cudaMemcpyAsync(p.d_s0, w.s0.data(), n, cudaMemcpyHostToDevice, ctx->stream));
+        SK_CUDA(ctx, cudaMemcpyAsync(p.d_frac, w.frac.data(), n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        SK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        // tile mapping: same rule as the batch plans
+        const uint32_t g = gcd_u32(r->in_rate, r->out_rate);
+        const uint32_t L = r->out_rate / g;
+        auto window_for = [&](int period) {
+            int mw = 0;
+            const size_t tile = (size_t)period * 32;
+            for (size_t a = 0; a < n; a += tile) {
+                size_t b = std::min(n, a + tile) - 1;
+                mw = std::max(mw, w.i0[b] - w.i0[a] + SINC_LEN + 2);
+            }
+            return mw;
+        };
+        p.period = 8;
+        if (L >= 8 && L <= 512 && window_for((int)L) <= kGenMaxWindow) p.period = (int)L;
+        p.max_window = window_for(p.period);
+    }
+    if (n) {
+        SrcDesc src;
+        memset(&src, 0, sizeof(src));
+        src.base = (const uint8_t*)r->d_buf; src.stream_stride = 0; src.lane_stride = (long long)(plane * sizeof(float));
+        src.width = 0; src.channels = r->channels; src.scale = 1.0f;
+        src.origin = 2 * SINC_LEN; src.valid_lo = -(long long)(2 * SINC_LEN); src.valid_hi = (long long)r->chunk;
+        OutDesc dst;
+        dst.base = r->d_out; dst.stream_stride = 0; dst.lane_stride = (long long)r->out_plane; dst.mix = SK_MIX_NONE; dst.n_out = (long long)n;
+        if ((rc = run_plan(ctx, src, dst, &p, r->in_rate, r->out_rate, 1, r->channels))) return rc;
+        for (int c = 0; c < r->channels; c++)
+            if ((rc = sk_d2h(ctx, out[c], r->d_out + (size_t)c * r->out_plane, n * sizeof(float)))) return rc;
+    }
+    r->last_index = next_last;
+    if (n_out) *n_out = n;
+    return SK_OK;
+}
+
+extern "C" int sk_resampler_process(sk_resampler* r, const float* const* in, float* const* out, size_t* n_out) {
+    if (!r) return SK_E_ARG;
+    if (!in || !out) SK_FAIL(r->ctx, SK_E_ARG, "null buffer");
+    return resampler_run(r, in, r->chunk, out, n_out);
+}
+
+extern "C" int sk_resampler_process_partial(sk_resampler* r, const float* const* in_or_null, size_t frames, float* const* out, size_t* n_out) {
+    if (!r) return SK_E_ARG;
+    if (!out) SK_FAIL(r->ctx, SK_E_ARG, "null buffer");
+    if (frames > r->chunk) frames = r->chunk;
+    return resampler_run(r, in_or_null, in_or_null ? frames : 0, out, n_out);
+}
