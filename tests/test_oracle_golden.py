@@ -1,0 +1,219 @@
+"""CPU tests (-m "not gpu"): pin the ORACLE against every golden vector, known-answer test and unit
+vector the reference holds for this path.  The oracle is only the checker."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden
+
+SAMPLES = np.array([-32768, -30000, -20000, -12000, -4096, -1024, -32, -1, 0, 1, 32, 1024, 4096, 12000, 20000,
+                    30000, 32767], np.int16)  # soundkit-g711/src/lib.rs:330-348
+
+
+# ---- G.711 ---------------------------------------------------------------------------------------
+def test_g711_golden_wavs(oracle):
+    for law, stem in ((oracle.MULAW, "g711_ulaw.ulaw"), (oracle.ALAW, "g711_alaw.alaw")):
+        want = np.frombuffer(golden(stem.split(".")[0] + ".decoded.s16le"), "<i2")
+        assert len(want) == 23680
+        assert np.array_equal(oracle.g711_decode(law, golden(stem)), want)
+
+
+def test_g711_unit_asserts(oracle):
+    L = oracle.lib()
+    # soundkit-g711/src/lib.rs:402-414
+    assert L.sko_g711_decode_sample(0, 0xFF) == 0 and L.sko_g711_decode_sample(0, 0x7F) == 0
+    assert L.sko_g711_encode_sample(0, 0) == 0xFF
+    assert L.sko_g711_decode_sample(1, 0xD5) == 8 and L.sko_g711_decode_sample(1, 0x55) == -8
+    assert L.sko_g711_encode_sample(1, 0) == 0xD5
+    # :416-434 idempotent re-quantisation
+    for law in (0, 1):
+        dec = oracle.g711_decode(law, oracle.g711_encode(law, SAMPLES))
+        assert np.array_equal(oracle.g711_decode(law, oracle.g711_encode(law, dec)), dec)
+    # :453-479 i32 = i16 << 16, f32 = i16 / 32768
+    enc = np.array([0xFF, 0xD7, 0xB7, 0x37, 0x17, 0x7F], np.uint8)
+    i16 = oracle.g711_decode(0, enc, "i16")
+    assert np.array_equal(oracle.g711_decode(0, enc, "i32"), i16.astype(np.int32) << 16)
+    assert np.array_equal(oracle.g711_decode(0, enc, "f32"), i16.astype(np.float32) / np.float32(32768))
+
+
+def test_g711_table_hashes_and_known_codes(oracle):
+    """SURVEY.md 8(a) R2 known answers."""
+    want = {0: ("3dab54339e520bb2c924826e3b72a917a2b612e9fd12fc867500f1d983a75827",
+                "5ee7cf5f273f842d2234121e4cb0c98d6b20a99ac29026f94e05b36955b195be",
+                "00020c182f4d7b7ffffffbcdaf988c8280"),
+            1: ("e04788d110e58ff8c70c93b8480190d973e3b67876b6119abbaec766cc75c174",
+                "38488f6fd710f4686360edc4d38639f96c491595ef93f8eb8d62d5e07ca6ce7b",
+                "2a2826321a7a5455d5d5d7e585b2a6a8aa")}
+    for law, (dh, eh, codes) in want.items():
+        dec = oracle.g711_decode(law, np.arange(256, dtype=np.uint8))
+        enc = oracle.g711_encode(law, np.arange(-32768, 32768).astype(np.int16))
+        assert hashlib.sha256(dec.astype("<i2").tobytes()).hexdigest() == dh
+        assert hashlib.sha256(enc.tobytes()).hexdigest() == eh
+        assert oracle.g711_encode(law, SAMPLES).tobytes().hex() == codes
+
+
+def test_g711_chunk_boundaries_do_not_matter(oracle):
+    whole = oracle.g711_encode(0, SAMPLES)
+    parts = np.concatenate([oracle.g711_encode(0, SAMPLES[i:i + 3]) for i in range(0, len(SAMPLES), 3)])
+    assert np.array_equal(whole, parts)
+
+
+# ---- conversion unit vectors ------------------------------------------------------------------------
+def test_audio_bytes_unit_vectors(oracle):
+    # soundkit/src/audio_bytes.rs:380-415
+    assert oracle.deinterleave("i16", bytes([1, 0, 2, 0, 3, 0, 4, 0, 5, 0, 6, 0]), 2).tolist() == [[1, 3, 5], [2, 4, 6]]
+    assert oracle.interleave_vecs_i16([[1, 3, 5], [2, 4, 6]]).tolist() == [1, 0, 2, 0, 3, 0, 4, 0, 5, 0, 6, 0]
+    assert oracle.deinterleave("s24", bytes([1, 0, 0, 2, 0, 0, 3, 0, 0, 4, 0, 0, 5, 0, 0, 6, 0, 0]), 2).tolist() == \
+        [[1, 3, 5], [2, 4, 6]]
+    f = bytes([0, 0, 128, 63, 0, 0, 0, 64, 0, 0, 64, 64, 0, 0, 128, 64, 0, 0, 160, 64, 0, 0, 192, 64])
+    assert oracle.deinterleave("f32", f, 2).tolist() == [[1.0, 3.0, 5.0], [2.0, 4.0, 6.0]]
+    # :417-440
+    got = oracle.flat("i16le_to_f32", bytes([0, 0, 0, 64, 255, 127, 0, 192, 0, 128]))
+    assert np.allclose(got, [0.0, 0.5, 0.9999694, -0.5, -1.0], atol=1e-4)
+    # :442-468
+    assert oracle.stereo_to_mono("take_left", [10, 20, -30, -40, 50, 60]).tolist() == [10, -30, 50]
+    assert oracle.stereo_to_mono("avg", [100, -100, 50, 150, -200, 200]).tolist() == [0, 100, 0]
+
+
+def test_audio_pipeline_unit_vectors(oracle):
+    # soundkit/src/audio_pipeline.rs:698-713: +-full-scale averages to ~0
+    raw = oracle.interleave_vecs_i16([[32767, -32768], [-32768, 32767]])
+    mono = oracle.mixdown_to_mono_f32(oracle.pcm_to_planar_f32(raw, 16, oracle.SIGNED, False, 2, oracle.MODE_A))
+    assert mono.shape == (2,) and np.all(np.abs(mono) < 0.01)
+    # :715-755 normalizer scale vectors = decoder convention (mode B)
+    be = np.array([32767, -32768], ">i2").tobytes()
+    p = oracle.pcm_to_planar_f32(be, 16, oracle.SIGNED, True, 2, oracle.MODE_B)
+    assert abs(p[0, 0] - 32767.0 / 32768.0) < np.finfo(np.float32).eps and p[1, 0] == -1.0
+    p = oracle.pcm_to_planar_f32(bytes([0xFF, 0xFF, 0x7F, 0x00, 0x00, 0x80]), 24, oracle.SIGNED, False, 2, oracle.MODE_B)
+    assert abs(p[0, 0] - 8388607.0 / 8388608.0) < np.finfo(np.float32).eps and p[1, 0] == -1.0
+    p = oracle.pcm_to_planar_f32(np.array([np.nan], "<f4").tobytes(), 32, oracle.FLOAT, False, 1, oracle.MODE_B)
+    assert p.tolist() == [[0.0]]
+    # mode A: 24-bit is divided by 2^31 (the reference's quirk), NaN is kept
+    p = oracle.pcm_to_planar_f32(bytes([0xFF, 0xFF, 0x7F]), 24, oracle.SIGNED, False, 1, oracle.MODE_A)
+    assert p[0, 0] == np.float32(8388607.0 / 2147483648.0)
+    p = oracle.pcm_to_planar_f32(np.array([np.nan], "<f4").tobytes(), 32, oracle.FLOAT, False, 1, oracle.MODE_A)
+    assert np.isnan(p[0, 0])
+
+
+def test_float_sample_to_i16_rounding(oracle):
+    # soundkit-decoder/src/lib.rs:1815-1827: half away from zero, asymmetric scale, non-finite -> 0
+    f = oracle.float_sample_to_i16
+    assert f(1.0) == 32767 and f(-1.0) == -32768 and f(2.0) == 32767 and f(-2.0) == -32768
+    assert f(float("nan")) == 0 and f(float("inf")) == 0
+    # -(m + 0.5) / 32768 is exact in f32: ties go away from zero (banker's rounding would give 0 and -2)
+    assert f(-0.5 / 32768) == -1 and f(-2.5 / 32768) == -3 and f(0.5) == 16384 and f(0.49 / 32767) == 0
+
+
+def test_raw_pcm_identity_fixture(oracle):
+    # soundkit/src/raw_pcm.rs:286-318: linear16 passes through unchanged
+    raw = golden("linear16.s16le")
+    assert raw == golden("linear16.decoded.s16le")
+    assert oracle.flat("s16le_to_i16", raw).astype("<i2").tobytes() == raw
+
+
+def test_endian_swap_hashes(oracle):
+    man = json.load(open(os.path.join(GOLDEN, "MANIFEST.json")))["endian_payloads"]
+    assert len(man) == 10
+    for name, info in man.items():
+        raw, be = golden(name), info["big_endian"]
+        if info["kind"] == "s16":
+            le = oracle.flat("s16be_to_i16" if be else "s16le_to_i16", raw).astype("<i2").tobytes()
+        elif info["kind"] == "s24":
+            if be:
+                assert np.array_equal(oracle.flat("s24be_to_i16", raw), oracle.flat("s24le_to_i16", golden("pcm-s24le.mov.bin")))
+                continue
+            v = oracle.flat("s24le_to_i32", raw).astype(np.int64) & 0xFFFFFF
+            le = np.stack([v & 0xFF, (v >> 8) & 0xFF, v >> 16], 1).astype(np.uint8).tobytes()
+        elif info["kind"] == "s32":
+            le = oracle.flat("s32be_to_i32" if be else "s32le_to_i32", raw).astype("<i4").tobytes()
+        else:
+            pl = oracle.pcm_to_planar_f32(raw, 32, oracle.FLOAT, be, 2, oracle.MODE_B)
+            le = np.ascontiguousarray(pl.T).astype("<f4").tobytes()
+        assert hashlib.sha256(le).hexdigest() == info["le_sha256"], name
+
+
+def test_golden_manifest_intact():
+    man = json.load(open(os.path.join(GOLDEN, "MANIFEST.json")))["files"]
+    for name, sha in man.items():
+        assert hashlib.sha256(golden(name)).hexdigest() == sha, name
+
+
+# ---- resampler: what the reference pins (lengths) + SURVEY appendix A known answers -------------------
+def test_index_walk_known_answers(oracle):
+    table = {(48000, 16000): ([1322, 1365, 1365, 1366, 1365, 1365], -260.0),
+             (48000, 8000): ([661, 682, 683, 683, 682, 683], -260.0),
+             (16000, 8000): ([1983, 2048, 2048, 2048, 2048, 2048], -258.0),
+             (8000, 16000): ([7932, 8192, 8192, 8192, 8192, 8192], -258.0),
+             (44100, 16000): ([1439, 1486, 1486, 1486, 1486, 1486], -258.8187500005215),
+             (44100, 48000): ([4317, 4458, 4459, 4458, 4458, 4458], -257.9000000017045)}
+    x = np.zeros((1, 4096), np.float32)
+    for (i, o), (counts, last) in table.items():
+        r = oracle.Resampler(i, o, 4096, 1)
+        assert [r.process(x).shape[1] for _ in range(6)] == counts
+        assert r.last_index == last
+
+
+def test_one_shot_lengths(oracle):
+    for (i, o, n), want in {(44100, 16000, 132437): 48002, (48000, 16000, 2880000): 959956,
+                            (44100, 48000, 2646000): 2879859, (16000, 8000, 47360): 23615}.items():
+        assert len(oracle.Resampler(i, o, n, 1).walk()[0]) == want
+    i0, s0, fr = oracle.Resampler(44100, 48000, 2646000, 1).walk()
+    assert i0[:5].tolist() == [-128, -127, -126, -125, -124] and s0[:5].tolist() == [235, 214, 193, 172, 152]
+    assert len(np.unique(s0)) == 192
+    i0, s0, fr = oracle.Resampler(48000, 16000, 30000, 1).walk()
+    assert np.all(s0 == 0) and np.all(fr == 0) and i0[:3].tolist() == [-125, -122, -119]
+
+
+def test_streaming_matches_single_pass_length(oracle):
+    """soundkit-decoder/src/lib.rs:5187-5238: 44.1k -> 16k, 132 437 frames pushed 997 at a time."""
+    rng = np.random.default_rng(7)
+    frames = 132437
+    x = rng.uniform(-0.5, 0.5, (1, frames)).astype(np.float32)
+    one = oracle.downsample_audio(x.view(np.uint8).reshape(-1), 32, oracle.FLOAT, 1, 44100, 16000)
+    s = oracle.Stream(44100, 16000, 1)
+    total = 0
+    for a in range(0, frames, 997):
+        total += s.process(x[:, a:a + 997]).shape[1]
+    total += s.flush().shape[1]
+    assert total == one.shape[1] == 48002
+
+
+def test_integer_ratio_streaming_equals_one_shot_values(oracle):
+    """for integer t_ratio the walk is exact, so streaming and one-shot agree sample for sample."""
+    rng = np.random.default_rng(8)
+    frames = 50000
+    raw = rng.integers(0, 256, frames * 2 * 2, dtype=np.uint8)
+    pl = oracle.pcm_to_planar_f32(raw, 16, oracle.SIGNED, False, 2, oracle.MODE_B)
+    one = oracle.downsample_audio(raw, 16, oracle.SIGNED, 2, 48000, 16000)
+    s = oracle.Stream(48000, 16000, 2)
+    got = np.concatenate([s.process(pl), s.flush()], axis=1)
+    n = min(one.shape[1], got.shape[1])
+    assert abs(one.shape[1] - got.shape[1]) <= 2
+    assert np.array_equal(one[:, :n].view(np.uint32), got[:, :n].view(np.uint32))
+
+
+def test_resampler_dc_gain_and_sine(oracle):
+    """sanity of the restated filter itself: unity DC gain, a 1 kHz tone survives 48k -> 16k."""
+    n = 48000
+    r = oracle.Resampler(48000, 16000, n, 1)
+    y = r.process(np.ones((1, n), np.float32))[0]
+    assert np.allclose(y[200:-200], 1.0, atol=1e-3)
+    t = np.arange(n) / 48000.0
+    y = oracle.Resampler(48000, 16000, n, 1).process(np.sin(2 * np.pi * 1000 * t)[None].astype(np.float32))[0]
+    # output n is centred on input sample 3n + 3 (idx_n = -128 + 3(n+1), row 0 peaks at tap 127 -> wait: i0 + 127.x)
+    k = np.arange(len(y))
+    ref = np.sin(2 * np.pi * 1000 * (3 * k - 125 + 127 + 1 / 256.0) / 48000.0)
+    assert np.max(np.abs(y[100:-100] - ref[100:-100])) < 2e-3
+
+
+def test_scalar_and_avx_dot_products_agree(oracle):
+    """the AVX2+FMA body and the fmaf fallback are the same arithmetic (rubato's lane order)."""
+    assert oracle.lib().sko_resampler_uses_avx() in (0, 1)
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, (2, 20000)).astype(np.float32)
+    a = oracle.Resampler(44100, 48000, 20000, 2).process(x, threads=1)
+    b = oracle.Resampler(44100, 48000, 20000, 2).process(x, threads=4)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
