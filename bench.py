@@ -1,0 +1,350 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the normalization hot path (driver contract in the task brief).
+
+Workload (config.workload): one WAVE of BASELINE.json configs[4] — S streams x 600 s of s24le stereo
+48 kHz normalised to f32 mono 16 kHz (decoder convention convert -> windowed-sinc resample per channel
+-> mono downmix) by ONE fused sm_100a kernel per step.  configs[4] as a whole (32 768 streams, 6.9 TB)
+does not fit a GPU; it is processed in such waves, and at N GPUs every rank runs its own wave with no
+collective (weak scaling, independent streams).
+
+  value     output Msamples/s (mono f32 frames), inputs resident in HBM, CUDA-event timed
+  e2e       same metric through the host-buffer C-ABI call (sk_normalize_batch): pinned host input,
+            H2D + kernel + D2H inside the timed region
+  roofline  FP32 CUDA-core roofline of the dominant kernel (resample_int_kernel<3>), peak = FFMA
+            microbenchmark measured in the same run; HBM figures alongside
+  cpu_baseline  the oracle (C restatement of the reference's Rust path, rubato AVX2+FMA order) timed on
+            the box's host cores on a bounded sample
+
+`--impl reference` times that CPU path only (rank 0), same metric/unit/config.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IN_RATE, OUT_RATE = 48000, 16000
+BITS, CHANNELS = 24, 2
+FLOPS_PER_FRAME = 1024.0  # 2 channels x 256 taps x 2 flop (P = 1: integer t_ratio)
+BYTES_PER_FRAME = 22.0    # 3 input frames x 6 B + 4 B out
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=32, help="streams per GPU per step (one wave)")
+    ap.add_argument("--seconds", type=float, default=600.0, help="stream length in seconds")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary kernel measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def config_dict(args, frames, n_out):
+    return {"workload": f"BASELINE configs[4] wave: {args.streams} streams/GPU x {args.seconds:g} s s24le stereo 48 kHz -> "
+                        f"f32 mono 16 kHz (fused convert + sinc resample + downmix, streaming semantics)",
+            "streams_per_gpu": args.streams, "frames_per_stream": frames, "out_frames_per_stream": n_out,
+            "in_rate": IN_RATE, "out_rate": OUT_RATE, "bits": BITS, "channels": CHANNELS,
+            "l2": "inputs larger than L2 (each stream's input alone is %.0f MB)" % (frames * 6 / 1e6),
+            "parallelism": "streams sharded over GPUs, no collective"}
+
+
+# ------------------------------------------------------------------------------------------- CPU leg
+def cpu_chain(threads, streams_per_thread, seconds, seed=0):
+    """oracle chain on `threads` host threads, one stream per call; returns (mono frames, wall seconds)."""
+    import numpy as np
+    from oracle import oracle as O
+    O.build()
+    frames = int(seconds * IN_RATE)
+    rng = np.random.default_rng(seed)
+    raw = rng.integers(0, 256, frames * CHANNELS * 3, dtype=np.uint8)
+    O.normalize_chain_mono(raw[: 4800 * 6], BITS, O.SIGNED, False, CHANNELS, IN_RATE, OUT_RATE)  # warm the table code
+    outs = [0] * threads
+
+    def work(t):
+        n = 0
+        for _ in range(streams_per_thread):
+            n += O.normalize_chain_mono(raw, BITS, O.SIGNED, False, CHANNELS, IN_RATE, OUT_RATE).size
+        outs[t] = n
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    return sum(outs), time.perf_counter() - t0
+
+
+def cpu_baseline(seconds=30.0, target_wall=8.0):
+    cores = os.cpu_count() or 1
+    frames, wall = cpu_chain(cores, 1, seconds)
+    reps = max(1, min(16, int(target_wall / max(wall, 1e-3))))
+    if reps > 1:
+        frames, wall = cpu_chain(cores, reps, seconds)
+    else:
+        reps = 1
+    from oracle import oracle as O
+    return {"value": frames / wall / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
+            "sample": f"{cores} threads x {reps} streams x {seconds:g} s s24le stereo 48k -> f32 mono 16k, oracle C restatement "
+                      f"(rubato order, {'AVX2+FMA' if O.lib().sko_resampler_uses_avx() else 'scalar fmaf'}, both interpolation products)",
+            "wall_s": wall}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames = int(args.seconds * IN_RATE)
+    cores = os.cpu_count() or 1
+    sample_s = 30.0
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_chain(cores, 1, sample_s)
+    total_frames, total_wall = 0, 0.0
+    for _ in range(max(1, args.steps)):
+        f, w = cpu_chain(cores, 1, sample_s)
+        total_frames += f
+        total_wall += w
+    val = total_frames / total_wall / 1e6
+    from oracle import oracle as O
+    sample = (f"each step = {cores} threads x 1 stream x {sample_s:g} s of the same workload (the Rust reference cannot be built here: "
+              f"no cargo/rustc; this is its C restatement, {'AVX2+FMA' if O.lib().sko_resampler_uses_avx() else 'scalar fmaf'})")
+    line = {"impl": "reference", "metric": "output Msamples/s, 48k->16k sinc resample", "value": val, "unit": "Msamples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_wall / max(1, args.steps) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, frames, None),
+            "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------- GPU leg
+def extras(ctx, torch, peaks):
+    """secondary kernels (BASELINE configs 2-4), device resident, CUDA-event timed, each > L2 sized."""
+    from soundkit_b200 import capi
+    res = {}
+
+    def timed(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e30
+        for _ in range(reps):
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best * 1e-3
+
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    n = 1 << 30  # 1 Gi samples of G.711
+    codes = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda")
+    pcm = torch.empty((n,), dtype=torch.int16, device="cuda")
+    t = timed(lambda: ctx.g711_decode_dev(capi.LAW_MULAW, codes, n, capi.KIND_I16, pcm))
+    res["g711_decode_ulaw_i16"] = {"GB/s": 3 * n / t / 1e9, "frac_of_measured_hbm": 3 * n / t / 1e9 / hbm, "Msamples/s": n / t / 1e6}
+    t = timed(lambda: ctx.g711_encode_dev(capi.LAW_MULAW, capi.KIND_I16, pcm, n, codes))
+    res["g711_encode_ulaw_i16"] = {"GB/s": 3 * n / t / 1e9, "frac_of_measured_hbm": 3 * n / t / 1e9 / hbm, "Msamples/s": n / t / 1e6}
+    del codes, pcm
+    # conversion: 64 streams x 60 s stereo 48 kHz -> planar f32 (BASELINE configs[1] wave)
+    S, frames = 64, 2880000
+    out = torch.empty((S, 2, frames), dtype=torch.float32, device="cuda")
+    for bits, fmt, name in ((16, 0, "s16le"), (24, 0, "s24le"), (32, 1, "f32le")):
+        raw = torch.randint(0, 256, (S, frames * 2 * bits // 8), dtype=torch.uint8, device="cuda")
+        t = timed(lambda: ctx.pcm_to_planar_f32_dev(raw, raw.stride(0), S, frames, bits, fmt, False, 2, capi.MODE_B, out, 2 * frames))
+        nb = S * frames * 2 * (bits // 8 + 4)
+        res[f"convert_{name}_stereo_to_planar_f32"] = {"GB/s": nb / t / 1e9, "frac_of_measured_hbm": nb / t / 1e9 / hbm,
+                                                       "Msamples/s": S * frames * 2 / t / 1e6}
+        del raw
+    del out
+    # non-integer ratio 44.1k -> 48k stereo f32 (BASELINE configs[3] wave), one-shot semantics
+    S, frames = 16, 2646000
+    n_out = ctx.batch_plan(44100, 48000, frames, capi.SEM_ONESHOT)
+    x = (torch.rand((S, frames * 2), device="cuda") - 0.5)
+    o = torch.empty((S, 2, n_out), dtype=torch.float32, device="cuda")
+    d = capi.BatchDesc(x.data_ptr(), x.stride(0) * 4, S, frames, 32, 1, 0, 2, capi.MODE_A, 44100, 48000, capi.SEM_ONESHOT,
+                       capi.MIX_NONE, o.data_ptr(), 2 * n_out, n_out)
+    t = timed(lambda: ctx.normalize_batch_dev(d), reps=3)
+    fl = 1027.0 * S * 2 * n_out
+    res["resample_44k1_to_48k_stereo_f32"] = {"TFLOP/s": fl / t / 1e12, "Msamples/s": S * 2 * n_out / t / 1e6}
+    return res
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    from soundkit_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = capi.Context(local)
+    ctx.use_torch_stream()
+
+    S, frames = args.streams, int(args.seconds * IN_RATE)
+    n_out = ctx.batch_plan(IN_RATE, OUT_RATE, frames, capi.SEM_STREAMING)
+    stride = frames * CHANNELS * 3
+    stride = (stride + 15) // 16 * 16
+    g = torch.Generator(device="cuda"); g.manual_seed(0x5EED0000 + rank)
+    raw = torch.randint(0, 256, (S, stride), dtype=torch.uint8, device="cuda", generator=g)
+    n_pad = (n_out + 3) // 4 * 4
+    out = torch.empty((S, n_pad), dtype=torch.float32, device="cuda")
+    desc = capi.BatchDesc(raw.data_ptr(), stride, S, frames, BITS, capi.FMT_SIGNED, 0, CHANNELS, capi.MODE_B, IN_RATE, OUT_RATE,
+                          capi.SEM_STREAMING, capi.MIX_SCALE_THEN_SUM, out.data_ptr(), n_pad, 0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for _ in range(max(args.warmup, 3)):
+        ctx.normalize_batch_dev(desc)
+    barrier()
+    sampler = ClockSampler(local)
+    time.sleep(0.25)
+    l0 = ctx.launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for k in range(args.steps):
+        ctx.normalize_batch_dev(desc)
+        ev[k + 1].record()
+    barrier()
+    launches = ctx.launches - l0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    clocks = sampler.stop()
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    frames_all = float(S) * n_out * world * args.steps
+    value = frames_all / (total_ms_max * 1e-3) / 1e6
+
+    # ---- end to end through the host-buffer C-ABI call
+    h_in = torch.empty((S, stride), dtype=torch.uint8, pin_memory=True)
+    h_in.copy_(raw)
+    h_out = torch.empty((S, n_pad), dtype=torch.float32, pin_memory=True)
+    hdesc = capi.BatchDesc(h_in.data_ptr(), stride, S, frames, BITS, capi.FMT_SIGNED, 0, CHANNELS, capi.MODE_B, IN_RATE, OUT_RATE,
+                           capi.SEM_STREAMING, capi.MIX_SCALE_THEN_SUM, h_out.data_ptr(), n_pad, 0)
+    e2e_steps = max(2, min(args.steps, 5))
+    ctx.normalize_batch_host(hdesc)  # warm-up (allocates the slab pipeline)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.normalize_batch_host(hdesc)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_val = float(S) * n_out * world * e2e_steps / e2e_s / 1e6
+    same = bool(torch.equal(h_out[:, :n_out], out[:, :n_out].cpu()))
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    ffma_peak = ctx.ffma_peak_tflops()
+    launch_ms = statistics.mean(per_launch_ms)
+    kernels_per_step = max(1, launches // max(1, args.steps))
+    ach = FLOPS_PER_FRAME * S * n_out / (launch_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp32", "kernel": "resample_int_kernel<3> (fused s24->f32 + 256-tap FIR x2ch + downmix)",
+                "achieved": ach, "peak": ffma_peak, "unit": "TFLOP/s", "frac": ach / ffma_peak,
+                "peak_source": "FFMA microbenchmark measured in this run (sk_ctx_measure_ffma_peak); nominal 148 SM x 128 x 2 x 1.965 GHz = 74.4",
+                "algorithmic_flops_per_launch": FLOPS_PER_FRAME * S * n_out, "launch_ms": launch_ms,
+                "kernels_per_step": kernels_per_step, "traffic": None,
+                "hbm": {"achieved_GBs": BYTES_PER_FRAME * S * n_out / (launch_ms * 1e-3) / 1e9, "peak_GBs": hbm_peak,
+                        "frac": BYTES_PER_FRAME * S * n_out / (launch_ms * 1e-3) / 1e9 / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"}}
+    line = {"metric": "output Msamples/s, 48k->16k sinc resample", "value": value, "unit": "Msamples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (uniform random s24 samples, full range)",
+            "config": config_dict(args, frames, n_out), "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": S * frames * CHANNELS * 3,
+                    "d2h_bytes_per_step": S * n_out * 4, "steps": e2e_steps, "api": "sk_normalize_batch (host pointers, pinned)",
+                    "matches_device_path": same},
+            "gpu_launches": launches, "roofline": roofline}
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline()
+    if world == 1 and not args.no_extras:
+        try:
+            del raw, out
+            torch.cuda.empty_cache()
+            line["extras"] = extras(ctx, torch, peaks)
+        except Exception as e:  # extras must never cost the headline line
+            line["extras"] = {"error": repr(e)}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -210,6 +210,10 @@ typedef struct {
 int sk_normalize_batch_plan(sk_ctx*, uint32_t in_rate, uint32_t out_rate, size_t frames, int semantics,
                             size_t* n_out);
 int sk_normalize_batch_dev(sk_ctx*, const sk_batch_desc* desc);
+/* host-pointer form of the batch call: desc->in / desc->out are HOST pointers (pinned memory gives
+ * full PCIe rate).  Streams are processed in slabs; the H2D copy of the next slab and the D2H copy of
+ * the previous one overlap the kernel of the current one.  Returns when every result is in `out`. */
+int sk_normalize_batch(sk_ctx*, const sk_batch_desc* desc);
 /* host-pointer form of the same call for ONE stream (what downsample_audio / the decoder's output
  * stage would call per AudioData): copies in, runs the fused kernel, copies out. */
 int sk_normalize_stream(sk_ctx*, const uint8_t* in, size_t bytes, int bits, int fmt, int big_endian,

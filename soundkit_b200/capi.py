@@ -35,7 +35,7 @@ EXPORTS = (
     "sk_planar_f32_to_pcm_dev", "sk_pcm_narrow_i16", "sk_mixdown_mono", "sk_mixdown_mono_dev", "sk_downmix_stereo",
     "sk_resampler_create", "sk_resampler_destroy", "sk_resampler_out_max", "sk_resampler_last_index",
     "sk_resampler_process", "sk_resampler_process_partial", "sk_resampler_copy_table",
-    "sk_normalize_batch_plan", "sk_normalize_batch_dev", "sk_normalize_stream",
+    "sk_normalize_batch_plan", "sk_normalize_batch_dev", "sk_normalize_batch", "sk_normalize_stream",
 )
 
 
@@ -107,6 +107,7 @@ def load():
         "sk_resampler_copy_table": (i, [vp, vp]),
         "sk_normalize_batch_plan": (i, [vp, u32, u32, sz, i, psz]),
         "sk_normalize_batch_dev": (i, [vp, C.POINTER(BatchDesc)]),
+        "sk_normalize_batch": (i, [vp, C.POINTER(BatchDesc)]),
         "sk_normalize_stream": (i, [vp, vp, sz, i, i, i, i, i, u32, u32, i, i, vp, sz, psz]),
     }
     for name in EXPORTS:
@@ -290,6 +291,9 @@ class Context:
 
     def normalize_batch_dev(self, desc):
         self._ck(self.L.sk_normalize_batch_dev(self.h, C.byref(desc)))
+
+    def normalize_batch_host(self, desc):
+        self._ck(self.L.sk_normalize_batch(self.h, C.byref(desc)))
 
     def normalize_stream(self, data, bits, fmt, big_endian, channels, mode, in_rate, out_rate, semantics, mix):
         d = _u8(data)

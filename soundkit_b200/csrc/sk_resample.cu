@@ -126,7 +126,9 @@ static void free_plan(sk_plan* p) {
     delete p;
 }
 
+void sk_resample_free_pipe(sk_ctx* ctx);
 void sk_resample_free_ctx(sk_ctx* ctx) {
+    sk_resample_free_pipe(ctx);
     for (auto& kv : ctx->sinc_tables) cudaFree(kv.second);
     ctx->sinc_tables.clear();
     for (auto& kv : ctx->plans) free_plan(kv.second);
@@ -709,6 +711,106 @@ extern "C" int sk_normalize_stream(sk_ctx* ctx, const uint8_t* in, size_t bytes,
     cudaStreamSynchronize(ctx->stream);
     cudaFree(d_res);
     return rc;
+}
+
+// Host-pointer batch: the same fused chain for n_streams host-resident streams, pipelined in slabs —
+// H2D of slab i+1 and D2H of slab i-1 overlap the kernel of slab i on three streams.  `in` / `out`
+// of the descriptor are HOST pointers here (pinned memory gives full PCIe rate; pageable works).
+struct BatchPipe {
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    void* d_in[2] = {nullptr, nullptr}; size_t in_cap = 0;
+    float* d_out[2] = {nullptr, nullptr}; size_t out_cap = 0;
+};
+static std::map<sk_ctx*, BatchPipe> g_pipes;  // one per context (contexts are thread-confined)
+
+void sk_resample_free_pipe(sk_ctx* ctx) {
+    auto it = g_pipes.find(ctx);
+    if (it == g_pipes.end()) return;
+    BatchPipe& p = it->second;
+    for (int b = 0; b < 2; b++) {
+        if (p.d_in[b]) cudaFree(p.d_in[b]);
+        if (p.d_out[b]) cudaFree(p.d_out[b]);
+        if (p.ev_in[b]) cudaEventDestroy(p.ev_in[b]);
+        if (p.ev_k[b]) cudaEventDestroy(p.ev_k[b]);
+        if (p.ev_out[b]) cudaEventDestroy(p.ev_out[b]);
+    }
+    if (p.s_in) cudaStreamDestroy(p.s_in);
+    if (p.s_out) cudaStreamDestroy(p.s_out);
+    g_pipes.erase(it);
+}
+
+extern "C" int sk_normalize_batch(sk_ctx* ctx, const sk_batch_desc* d) {
+    if (!ctx || !d) return SK_E_ARG;
+    if (d->channels <= 0 || d->channels > 255) SK_FAIL(ctx, SK_E_ARG, "Channel count must be > 0");
+    if (d->bits != 16 && d->bits != 24 && d->bits != 32) SK_FAIL(ctx, SK_E_ARG, "Unsupported bits_per_sample: %d", d->bits);
+    if (!d->n_streams) return SK_OK;
+    if (!d->in || !d->out) SK_FAIL(ctx, SK_E_ARG, "null buffer");
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    sk_plan* plan;
+    int rc = build_stream_plan(ctx, d->in_rate, d->out_rate, d->frames, d->semantics, &plan);
+    if (rc) return rc;
+    if (!plan->n_out) return SK_OK;
+    const int mix = d->channels == 1 ? SK_MIX_NONE : d->mix_mode;
+    const int planes = mix == SK_MIX_NONE ? d->channels : 1;
+    const size_t in_bytes = sk_round_up(d->frames * (size_t)(d->bits / 8) * d->channels, 16);
+    const size_t plane = sk_round_up(plan->n_out, 4);
+    const size_t out_floats = plane * planes;
+    // slab: as many streams as fit ~256 MiB of input (at least one)
+    size_t slab = std::max<size_t>(1, ((size_t)256 << 20) / std::max<size_t>(1, in_bytes));
+    slab = std::min(slab, d->n_streams);
+    BatchPipe& p = g_pipes[ctx];
+    if (!p.s_in) {
+        SK_CUDA(ctx, cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking));
+        SK_CUDA(ctx, cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            SK_CUDA(ctx, cudaEventCreateWithFlags(&p.ev_in[b], cudaEventDisableTiming));
+            SK_CUDA(ctx, cudaEventCreateWithFlags(&p.ev_k[b], cudaEventDisableTiming));
+            SK_CUDA(ctx, cudaEventCreateWithFlags(&p.ev_out[b], cudaEventDisableTiming));
+        }
+    }
+    if (p.in_cap < slab * in_bytes || p.out_cap < slab * out_floats) {
+        cudaDeviceSynchronize();
+        for (int b = 0; b < 2; b++) {
+            if (p.d_in[b]) cudaFree(p.d_in[b]);
+            if (p.d_out[b]) cudaFree(p.d_out[b]);
+            p.d_in[b] = nullptr; p.d_out[b] = nullptr;
+        }
+        p.in_cap = slab * in_bytes; p.out_cap = slab * out_floats;
+        for (int b = 0; b < 2; b++) {
+            SK_CUDA(ctx, cudaMalloc(&p.d_in[b], p.in_cap));
+            SK_CUDA(ctx, cudaMalloc((void**)&p.d_out[b], p.out_cap * sizeof(float)));
+        }
+    }
+    const size_t raw_bytes = d->frames * (size_t)(d->bits / 8) * d->channels;
+    size_t islab = 0;
+    for (size_t s0 = 0; s0 < d->n_streams; s0 += slab, islab++) {
+        const int b = (int)(islab & 1);
+        const size_t ns = std::min(slab, d->n_streams - s0);
+        if (islab >= 2) {
+            SK_CUDA(ctx, cudaStreamWaitEvent(p.s_in, p.ev_k[b], 0));        // kernel of slab-2 finished reading d_in[b]
+            SK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p.ev_out[b], 0)); // D2H of slab-2 finished reading d_out[b]
+        }
+        for (size_t s = 0; s < ns; s++)
+            SK_CUDA(ctx, cudaMemcpyAsync((char*)p.d_in[b] + s * in_bytes, (const char*)d->in + (s0 + s) * d->in_stride, raw_bytes,
+                                         cudaMemcpyHostToDevice, p.s_in));
+        SK_CUDA(ctx, cudaEventRecord(p.ev_in[b], p.s_in));
+        SK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p.ev_in[b], 0));
+        sk_batch_desc dd = *d;
+        dd.in = p.d_in[b]; dd.in_stride = in_bytes; dd.n_streams = ns; dd.mix_mode = mix;
+        dd.out = p.d_out[b]; dd.out_stride = out_floats; dd.out_stride_ch = plane;
+        if ((rc = sk_normalize_batch_dev(ctx, &dd))) return rc;
+        SK_CUDA(ctx, cudaEventRecord(p.ev_k[b], ctx->stream));
+        SK_CUDA(ctx, cudaStreamWaitEvent(p.s_out, p.ev_k[b], 0));
+        for (size_t s = 0; s < ns; s++)
+            for (int c = 0; c < planes; c++)
+                SK_CUDA(ctx, cudaMemcpyAsync(d->out + (s0 + s) * d->out_stride + (size_t)c * d->out_stride_ch, p.d_out[b] + s * out_floats + (size_t)c * plane,
+                                             plan->n_out * sizeof(float), cudaMemcpyDeviceToHost, p.s_out));
+        SK_CUDA(ctx, cudaEventRecord(p.ev_out[b], p.s_out));
+    }
+    SK_CUDA(ctx, cudaStreamSynchronize(p.s_out));
+    SK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SK_OK;
 }
 
 // ================================================================================================
