@@ -90,8 +90,10 @@ int  sk_ctx_create(int device, sk_ctx** out);
 void sk_ctx_destroy(sk_ctx* ctx);
 /* last error message of this context (thread-confined); "" when none */
 const char* sk_last_error(const sk_ctx* ctx);
-/* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the ctx's own */
+/* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = CUDA's legacy default stream */
 int  sk_ctx_set_stream(sk_ctx* ctx, void* cuda_stream);
+/* back to the context's own non-blocking stream (the default after sk_ctx_create) */
+int  sk_ctx_reset_stream(sk_ctx* ctx);
 int  sk_ctx_synchronize(sk_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py reports it as gpu_launches) */
 uint64_t sk_ctx_launch_count(const sk_ctx* ctx);

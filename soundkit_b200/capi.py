@@ -27,7 +27,8 @@ FLAT_OPS = ("i16le_to_f32", "s16le_to_i16", "s16be_to_i16", "s16le_to_i32", "s24
 FLAT_OP = {name: i for i, name in enumerate(FLAT_OPS)}
 
 EXPORTS = (
-    "sk_abi_version", "sk_ctx_create", "sk_ctx_destroy", "sk_last_error", "sk_ctx_set_stream", "sk_ctx_synchronize",
+    "sk_abi_version", "sk_ctx_create", "sk_ctx_destroy", "sk_last_error", "sk_ctx_set_stream", "sk_ctx_reset_stream",
+    "sk_ctx_synchronize",
     "sk_ctx_launch_count", "sk_ctx_measure_ffma_peak",
     "sk_g711_decode", "sk_g711_decode_dev", "sk_g711_encode", "sk_g711_encode_dev",
     "sk_pcm_flat_convert", "sk_pcm_flat_convert_dev", "sk_flat_op_widths", "sk_deinterleave", "sk_interleave_i16",
@@ -77,6 +78,7 @@ def load():
         "sk_ctx_destroy": (None, [vp]),
         "sk_last_error": (C.c_char_p, [vp]),
         "sk_ctx_set_stream": (i, [vp, vp]),
+        "sk_ctx_reset_stream": (i, [vp]),
         "sk_ctx_synchronize": (i, [vp]),
         "sk_ctx_launch_count": (C.c_uint64, [vp]),
         "sk_ctx_measure_ffma_peak": (i, [vp, C.POINTER(C.c_double)]),
@@ -165,7 +167,11 @@ class Context:
 
     # -- plumbing
     def set_stream(self, stream_ptr):
+        """launch on this cudaStream_t; 0 / None is CUDA's legacy default stream"""
         self._ck(self.L.sk_ctx_set_stream(self.h, C.c_void_p(stream_ptr) if stream_ptr else None))
+
+    def reset_stream(self):
+        self._ck(self.L.sk_ctx_reset_stream(self.h))
 
     def use_torch_stream(self):
         import torch

@@ -50,7 +50,13 @@ extern "C" const char* sk_last_error(const sk_ctx* ctx) { return ctx ? ctx->err.
 
 extern "C" int sk_ctx_set_stream(sk_ctx* ctx, void* cuda_stream) {
     if (!ctx) return SK_E_ARG;
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream;  // NULL is CUDA's legacy default stream, a valid choice
+    return SK_OK;
+}
+
+extern "C" int sk_ctx_reset_stream(sk_ctx* ctx) {
+    if (!ctx) return SK_E_ARG;
+    ctx->stream = ctx->own_stream;
     return SK_OK;
 }
 

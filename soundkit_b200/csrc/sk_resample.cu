@@ -369,9 +369,9 @@ template <int STEP> __host__ __device__ constexpr int int_smem_bytes() { return 
 // The FIR core: walk the thread's input span once; each LDS.128 feeds 4*R FFMAs whose coefficient
 // operand is a kernel-parameter constant (c[0x0][..]).  Accumulator (r, l) sees its taps in
 // increasing order, i.e. exactly rubato's per-lane fused accumulation.
-template <int STEP, int R>
+template <int STEP, int R, int LEAD = 0>
 __device__ __forceinline__ void fir_core(const float* __restrict__ w, const Taps& taps, float (&acc)[R][8]) {
-    constexpr int NIN = STEP * (R - 1) + SINC_LEN;
+    constexpr int NIN = LEAD + STEP * (R - 1) + SINC_LEN;
     constexpr int NV = (NIN + 3) / 4;
 #pragma unroll
     for (int v = 0; v < NV; v++) {
@@ -382,9 +382,48 @@ __device__ __forceinline__ void fir_core(const float* __restrict__ w, const Taps
             const int m = 4 * v + e;
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                const int j = m - STEP * r;
+                const int j = m - LEAD - STEP * r;
                 if (j >= 0 && j < SINC_LEN) acc[r][j & 7] = __fmaf_rn(xs[e], taps.h[j], acc[r][j & 7]);
             }
+        }
+    }
+}
+
+// store R outputs of one thread: optional (L, R) -> mono mix through a lane-pair shuffle, 128-bit stores
+template <int R>
+__device__ __forceinline__ void int_epilogue(const float (&y)[R], const OutDesc& dst, long long stream, long long n0, int b, int lane, int lane0,
+                                             bool lane1_valid) {
+    const long long nb = n0 + (long long)R * b;  // first output of this thread
+    if (dst.mix != SK_MIX_NONE) {
+        // lanes are (L, R) of one stream in adjacent threads: exchange, then each thread stores half
+        float o[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const float other = __shfl_xor_sync(0xffffffffu, y[r], 1);
+            const float l = lane == 0 ? y[r] : other, rr = lane == 0 ? other : y[r];
+            if (dst.mix == SK_MIX_SCALE_THEN_SUM) o[r] = __fadd_rn(__fadd_rn(0.0f, __fmul_rn(l, 0.5f)), __fmul_rn(rr, 0.5f));
+            else o[r] = __fmul_rn(__fadd_rn(__fadd_rn(0.0f, l), rr), 0.5f);
+        }
+        float* op = dst.base + stream * dst.stream_stride;
+        constexpr int H = (R + 1) / 2;
+        if (R == 8 && nb + 8 <= dst.n_out && ((dst.stream_stride & 3) == 0)) {
+            const float4 v = lane == 0 ? make_float4(o[0], o[1], o[2], o[3]) : make_float4(o[4], o[5], o[6], o[7]);
+            *reinterpret_cast<float4*>(op + nb + 4 * lane) = v;
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if ((r / H) == lane && nb + r < dst.n_out) op[nb + r] = o[r];
+        }
+    } else {
+        if (lane == 1 && !lane1_valid) return;
+        float* op = dst.base + stream * dst.stream_stride + (long long)(lane0 + lane) * dst.lane_stride;
+        if (R % 4 == 0 && nb + R <= dst.n_out && ((dst.stream_stride | dst.lane_stride) & 3) == 0) {
+#pragma unroll
+            for (int v = 0; v < R / 4; v++) *reinterpret_cast<float4*>(op + nb + 4 * v) = make_float4(y[4 * v], y[4 * v + 1], y[4 * v + 2], y[4 * v + 3]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if (nb + r < dst.n_out) op[nb + r] = y[r];
         }
     }
 }
@@ -436,38 +475,204 @@ resample_int_kernel(const __grid_constant__ Taps taps, const __grid_constant__ S
         }
     }
 
-    const long long nb = n0 + (long long)R * b;  // first output of this thread
-    if (dst.mix != SK_MIX_NONE) {
-        // lanes are (L, R) of one stream in adjacent threads: exchange, then each thread stores half
-        float o[R];
+    int_epilogue<R>(y, dst, stream, n0, b, lane, lane0, lane1_valid);
+}
+
+// ================================================================================================
+// integer-step kernel v2: persistent CTAs, TMA-staged raw windows, interleaved stereo sources
+// ================================================================================================
+// One CTA per SM slot walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The raw interleaved bytes
+// of tile k+2 are fetched by the TMA engine (cp.async.bulk -> mbarrier) while tile k is converted and
+// convolved, so HBM latency never sits in front of the FMA pipe, and staging costs ~1 instruction per
+// 16 bytes instead of a scalar load / convert / store chain per frame.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+
+// window of tile geometry for the TMA kernel: the shared window starts LEAD frames before the first
+// tap so that (a) its first raw byte is 16-byte aligned in the stream and (b) every thread's LDS.128
+// base stays 16-byte aligned; the taps are shifted by LEAD at compile time instead.
+template <int STEP> __host__ __device__ constexpr int tma_lead() { return STEP % 8; }
+template <int STEP> __host__ __device__ constexpr int tma_frames() { return ((tma_lead<STEP>() + int_window<STEP>() + 7) / 8) * 8; }
+template <int STEP> __host__ __device__ constexpr int tma_lane_stride() { return ((tma_frames<STEP>() + 4 + 31) / 32) * 32 + IntCfg<STEP>::SKEW; }
+template <int STEP, int SRCW> __host__ __device__ constexpr int tma_raw_bytes() { return tma_frames<STEP>() * 2 * SRCW; }
+template <int STEP, int SRCW> __host__ __device__ constexpr int tma_smem_bytes() {
+    return 2 * tma_lane_stride<STEP>() * (int)sizeof(float) + 2 * tma_raw_bytes<STEP, SRCW>() + 64;
+}
+
+// 4 stereo frames from the raw words -> l[4], r[4] sample bits (little-endian assembled, sign handled by decode)
+template <int SRCW, bool BE>
+__device__ __forceinline__ void unpack4(const uint32_t* w, uint32_t* l, uint32_t* r) {
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            const float other = __shfl_xor_sync(0xffffffffu, y[r], 1);
-            const float l = lane == 0 ? y[r] : other, rr = lane == 0 ? other : y[r];
-            if (dst.mix == SK_MIX_SCALE_THEN_SUM) o[r] = __fadd_rn(__fadd_rn(0.0f, __fmul_rn(l, 0.5f)), __fmul_rn(rr, 0.5f));
-            else o[r] = __fmul_rn(__fadd_rn(__fadd_rn(0.0f, l), rr), 0.5f);
-        }
-        float* op = dst.base + stream * dst.stream_stride;
-        constexpr int H = (R + 1) / 2;
-        if (R == 8 && nb + 8 <= dst.n_out && ((dst.stream_stride & 3) == 0)) {
-            const float4 v = lane == 0 ? make_float4(o[0], o[1], o[2], o[3]) : make_float4(o[4], o[5], o[6], o[7]);
-            *reinterpret_cast<float4*>(op + nb + 4 * lane) = v;
+    for (int k = 0; k < 4; k++) {
+        if (SRCW == 2) {
+            uint32_t a = w[k] & 0xffffu, b = w[k] >> 16;
+            if (BE) { a = __byte_perm(a, 0, 0x3201) & 0xffffu; b = __byte_perm(b, 0, 0x3201) & 0xffffu; }
+            l[k] = a; r[k] = b;
+        } else if (SRCW == 3) {
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int o = 3 * (2 * k + c), wi = o >> 2, sh = o & 3;
+                const uint32_t lo = w[wi], hi = (sh >= 2) ? w[wi + 1] : 0u;
+                // bytes sh, sh+1, sh+2 -> result bytes 0, 1, 2 (LE) or 2, 1, 0 (BE); byte 3 = 0 via the zero source (index 4.. of hi when unused)
+                const uint32_t sel = !BE ? ((uint32_t)(sh + 2) << 8) | ((uint32_t)(sh + 1) << 4) | (uint32_t)sh
+                                         : ((uint32_t)sh << 8) | ((uint32_t)(sh + 1) << 4) | (uint32_t)(sh + 2);
+                const uint32_t v = __byte_perm(lo, hi, sel) & 0x00ffffffu;
+                if (c == 0) l[k] = v; else r[k] = v;
+            }
         } else {
-#pragma unroll
-            for (int r = 0; r < R; r++)
-                if ((r / H) == lane && nb + r < dst.n_out) op[nb + r] = o[r];
+            uint32_t a = w[2 * k], b = w[2 * k + 1];
+            if (BE) { a = bswap32(a); b = bswap32(b); }
+            l[k] = a; r[k] = b;
         }
-    } else {
-        if (lane == 1 && !lane1_valid) return;
-        float* op = dst.base + stream * dst.stream_stride + (long long)(lane0 + lane) * dst.lane_stride;
-        if (R % 4 == 0 && nb + R <= dst.n_out && ((dst.stream_stride | dst.lane_stride) & 3) == 0) {
+    }
+}
+
+template <int STEP, int SRCW>
+__global__ void __launch_bounds__(kIntThreads, 2)
+resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant__ SrcDesc src, const __grid_constant__ OutDesc dst, long long i0_first,
+                        int tiles_per_stream, long long total_tiles, const float* __restrict__ row1) {
+    constexpr int R = IntCfg<STEP>::R;
+    constexpr int T = int_tile_outputs<STEP>();
+    constexpr int LEAD = tma_lead<STEP>();
+    constexpr int WF = tma_frames<STEP>();
+    constexpr int WS = tma_lane_stride<STEP>();
+    constexpr int FB = 2 * SRCW;  // bytes per stereo frame
+    constexpr int RAWB = tma_raw_bytes<STEP, SRCW>();
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float* win = reinterpret_cast<float*>(smem_raw);
+    uint8_t* raw = smem_raw + 2 * WS * sizeof(float);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(raw + 2 * RAWB);
+
+    const long long nk = (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;  // tiles this CTA owns
+    const long long stream_bytes16 = ((src.valid_hi * FB) / 16) * 16;             // bytes of a stream the TMA may touch
+
+    // tile -> (stream, first output, first window frame, copy range in bytes relative to the stream)
+    auto tile_geom = [&](long long t, long long& stream, long long& n0, long long& wa, long long& b_lo, long long& b_hi) {
+        stream = t / tiles_per_stream;
+        n0 = (t % tiles_per_stream) * (long long)T;
+        wa = i0_first + (long long)STEP * n0 - LEAD;
+        b_lo = wa * FB; if (b_lo < 0) b_lo = 0;
+        b_hi = (wa + WF) * FB; if (b_hi > stream_bytes16) b_hi = stream_bytes16;
+        if (b_hi < b_lo) b_hi = b_lo;
+    };
+    auto issue = [&](long long k) {  // one elected thread
+        long long stream, n0, wa, b_lo, b_hi;
+        tile_geom(blockIdx.x + k * gridDim.x, stream, n0, wa, b_lo, b_hi);
+        const int buf = (int)(k & 1);
+        const uint32_t bar = smem_u32(&bars[buf]);
+        const uint32_t bytes = (uint32_t)(b_hi - b_lo);
+        mbar_expect_tx(bar, bytes);
+        if (bytes) tma_load_1d(smem_u32(raw + buf * RAWB + (b_lo - wa * FB)), src.base + stream * src.stream_stride + b_lo, bytes, bar);
+    };
+
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&bars[0]), 1);
+        mbar_init(smem_u32(&bars[1]), 1);
+        mbar_fence_init();
+        if (nk > 0) issue(0);
+        if (nk > 1) issue(1);
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 1, b = threadIdx.x >> 1;
+    for (long long k = 0; k < nk; k++) {
+        long long stream, n0, wa, b_lo, b_hi;
+        tile_geom(blockIdx.x + k * gridDim.x, stream, n0, wa, b_lo, b_hi);
+        const int buf = (int)(k & 1);
+        mbar_wait(smem_u32(&bars[buf]), (uint32_t)((k >> 1) & 1));
+
+        // ---- raw bytes -> f32 windows (4 frames per thread step, 128-bit shared stores)
+        const uint8_t* rb = raw + buf * RAWB;
+        const long long c_lo = b_lo / FB, c_hi = b_hi / FB;  // frames fully present in the raw buffer
+        bool big = false;
+        for (int g = threadIdx.x; g < WF / 4; g += kIntThreads) {
+            const long long f = wa + 4 * g;
+            float l[4], r[4];
+            if (f >= c_lo && f + 4 <= c_hi) {
+                uint32_t w[FB];  // 4 frames = FB words
+                if (SRCW == 3) {
 #pragma unroll
-            for (int v = 0; v < R / 4; v++) *reinterpret_cast<float4*>(op + nb + 4 * v) = make_float4(y[4 * v], y[4 * v + 1], y[4 * v + 2], y[4 * v + 3]);
-        } else {
+                    for (int v = 0; v < 3; v++) {
+                        const uint2 q = *reinterpret_cast<const uint2*>(rb + g * 24 + 8 * v);
+                        w[2 * v] = q.x; w[2 * v + 1] = q.y;
+                    }
+                } else {
 #pragma unroll
-            for (int r = 0; r < R; r++)
-                if (nb + r < dst.n_out) op[nb + r] = y[r];
+                    for (int v = 0; v < FB / 4; v++) {
+                        const uint4 q = *reinterpret_cast<const uint4*>(rb + g * (4 * FB) + 16 * v);
+                        w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
+                    }
+                }
+                uint32_t lb[4], rbits[4];
+                if (src.big_endian) unpack4<SRCW, true>(w, lb, rbits); else unpack4<SRCW, false>(w, lb, rbits);
+#pragma unroll
+                for (int q = 0; q < 4; q++) { l[q] = decode_sample_bits(lb[q], src); r[q] = decode_sample_bits(rbits[q], src); }
+            } else {
+                // window edge (stream start / end / last partial 16 bytes): per-frame, straight from global memory
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const long long ff = f + q;
+                    l[q] = 0.0f; r[q] = 0.0f;
+                    if (ff >= src.valid_lo && ff < src.valid_hi) {
+                        const uint8_t* sbase = src.base + stream * src.stream_stride;
+                        l[q] = decode_sample_bits(load_sample_bits(sbase, ff, 0, src), src);
+                        r[q] = decode_sample_bits(load_sample_bits(sbase, ff, 1, src), src);
+                    }
+                }
+            }
+            if (SRCW == 4) {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    big |= ((__float_as_uint(l[q]) & 0x7f800000u) >= 0x78000000u) | ((__float_as_uint(r[q]) & 0x7f800000u) >= 0x78000000u);
+            }
+            *reinterpret_cast<float4*>(win + 4 * g) = make_float4(l[0], l[1], l[2], l[3]);
+            *reinterpret_cast<float4*>(win + WS + 4 * g) = make_float4(r[0], r[1], r[2], r[3]);
         }
+        const int any_big = __syncthreads_or((SRCW == 4 && src.is_float) ? (int)big : 0);  // windows ready, raw[buf] free
+        if (threadIdx.x == 0 && k + 2 < nk) issue(k + 2);
+
+        // ---- FIR
+        const float* w = win + lane * WS + STEP * R * b;
+        float acc[R][8];
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int q = 0; q < 8; q++) acc[r][q] = 0.0f;
+        fir_core<STEP, R, LEAD>(w, taps, acc);
+        float y[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) y[r] = reduce8(acc[r]);
+        if (any_big) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const float p1 = dot256(w + LEAD + STEP * r, row1);
+                y[r] = __fadd_rn(y[r], __fmul_rn(0.0f, __fsub_rn(p1, y[r])));
+            }
+        }
+        int_epilogue<R>(y, dst, stream, n0, b, lane, 0, true);
+        __syncthreads();  // windows free for the next tile
     }
 }
 
@@ -547,11 +752,34 @@ static int src_desc_for(sk_ctx* ctx, SrcDesc* s, const void* in, size_t in_strid
     return SK_OK;
 }
 
+template <int STEP, int SRCW>
+static int launch_int_tma(sk_ctx* ctx, const Taps& taps, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, const float* d_table, size_t n_streams) {
+    constexpr int T = int_tile_outputs<STEP>();
+    constexpr int smem = tma_smem_bytes<STEP, SRCW>();
+    SK_CUDA(ctx, cudaFuncSetAttribute(resample_int_tma_kernel<STEP, SRCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const long long tiles_per_stream = (long long)((plan->n_out + T - 1) / T);
+    const long long total = tiles_per_stream * (long long)n_streams;
+    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+    const long long grid = std::min<long long>(total, (long long)ctx->num_sms * per_sm);
+    resample_int_tma_kernel<STEP, SRCW><<<(unsigned)grid, kIntThreads, smem, ctx->stream>>>(taps, src, dst, plan->i0_first, (int)tiles_per_stream, total,
+                                                                                          d_table + SINC_LEN);
+    SK_LAUNCH_CHECK(ctx);
+    return SK_OK;
+}
+
 template <int STEP>
 static int launch_int(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, const float* h_table, const float* d_table,
                       size_t n_streams, int lanes_per_stream) {
     Taps taps;
     memcpy(taps.h, h_table, sizeof(taps.h));  // subindex 0
+    // fast path: interleaved stereo, 16-byte aligned streams, canonical first index (batch plans)
+    if (src.width != 0 && src.channels == 2 && lanes_per_stream == 2 && src.origin == 0 && src.valid_lo == 0 &&
+        plan->i0_first == -(long long)(SINC_LEN / 2) + STEP && ((uintptr_t)src.base % 16) == 0 && (src.stream_stride % 16) == 0 &&
+        (long long)n_streams * (long long)((plan->n_out + int_tile_outputs<STEP>() - 1) / int_tile_outputs<STEP>()) < (1ll << 40)) {
+        if (src.width == 2) return launch_int_tma<STEP, 2>(ctx, taps, src, dst, plan, d_table, n_streams);
+        if (src.width == 3) return launch_int_tma<STEP, 3>(ctx, taps, src, dst, plan, d_table, n_streams);
+        return launch_int_tma<STEP, 4>(ctx, taps, src, dst, plan, d_table, n_streams);
+    }
     constexpr int T = int_tile_outputs<STEP>();
     constexpr int smem = int_smem_bytes<STEP>();
     SK_CUDA(ctx, cudaFuncSetAttribute(resample_int_kernel<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
