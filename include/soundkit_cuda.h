@@ -97,8 +97,10 @@ int  sk_ctx_reset_stream(sk_ctx* ctx);
 int  sk_ctx_synchronize(sk_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py reports it as gpu_launches) */
 uint64_t sk_ctx_launch_count(const sk_ctx* ctx);
-/* measured FP32 FFMA peak of this device in TFLOP/s (register-resident FFMA microbenchmark) */
+/* measured FP32 FMA peak of this device in TFLOP/s: register-resident microbenchmarks of the scalar
+ * FFMA and the packed sm_100 FFMA2 instruction; _peak returns the larger of the two */
 int  sk_ctx_measure_ffma_peak(sk_ctx* ctx, double* tflops);
+int  sk_ctx_measure_ffma_peaks(sk_ctx* ctx, double* scalar_tflops, double* packed_tflops);
 
 /* ------------------------------------------------------------------ kernel 2: G.711 */
 /* replaces soundkit_g711::decode_i16 (soundkit-g711/src/lib.rs:52) and

@@ -29,7 +29,7 @@ FLAT_OP = {name: i for i, name in enumerate(FLAT_OPS)}
 EXPORTS = (
     "sk_abi_version", "sk_ctx_create", "sk_ctx_destroy", "sk_last_error", "sk_ctx_set_stream", "sk_ctx_reset_stream",
     "sk_ctx_synchronize",
-    "sk_ctx_launch_count", "sk_ctx_measure_ffma_peak",
+    "sk_ctx_launch_count", "sk_ctx_measure_ffma_peak", "sk_ctx_measure_ffma_peaks",
     "sk_g711_decode", "sk_g711_decode_dev", "sk_g711_encode", "sk_g711_encode_dev",
     "sk_pcm_flat_convert", "sk_pcm_flat_convert_dev", "sk_flat_op_widths", "sk_deinterleave", "sk_interleave_i16",
     "sk_stereo_to_mono_i16", "sk_pcm_to_planar_f32", "sk_pcm_to_planar_f32_dev", "sk_planar_f32_to_pcm",
@@ -82,6 +82,7 @@ def load():
         "sk_ctx_synchronize": (i, [vp]),
         "sk_ctx_launch_count": (C.c_uint64, [vp]),
         "sk_ctx_measure_ffma_peak": (i, [vp, C.POINTER(C.c_double)]),
+        "sk_ctx_measure_ffma_peaks": (i, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "sk_g711_decode": (i, [vp, i, vp, sz, i, vp]),
         "sk_g711_decode_dev": (i, [vp, i, vp, sz, i, vp]),
         "sk_g711_encode": (i, [vp, i, i, vp, sz, vp]),
@@ -188,6 +189,11 @@ class Context:
         v = C.c_double()
         self._ck(self.L.sk_ctx_measure_ffma_peak(self.h, C.byref(v)))
         return v.value
+
+    def ffma_peaks_tflops(self):
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.L.sk_ctx_measure_ffma_peaks(self.h, C.byref(a), C.byref(b)))
+        return {"ffma": a.value, "ffma2": b.value}
 
     # -- G.711 (host buffers)
     def g711_decode(self, law, data, kind=KIND_I16):

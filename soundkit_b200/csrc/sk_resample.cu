@@ -345,7 +345,16 @@ struct OutDesc {
 // ================================================================================================
 // integer-step kernel
 // ================================================================================================
-struct Taps { float h[SINC_LEN]; };
+// One table row in two layouts (kernel parameter -> constant bank).  The packed FMA consumes taps in
+// adjacent pairs (j, j+1): `he` serves pairs that start at an even tap; `ho[i] = h[i-1]` (zero outside)
+// serves pairs that start at an odd tap, including the edge pairs (-1, 0) and (255, 256) whose outer
+// element is a zero coefficient.
+struct __align__(16) Taps { float he[SINC_LEN]; float ho[SINC_LEN + 8]; };
+
+// d += a * b on two packed f32 lanes (sm_100 FFMA2): both lanes are IEEE fused multiply-adds
+__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
 
 template <int STEP> struct IntCfg;
 // R outputs per thread and the bank skew between the two lanes' windows, chosen so that the 8
@@ -363,28 +372,53 @@ constexpr int kIntBlocksPerLane = kIntThreads / 2;
 
 template <int STEP> __host__ __device__ constexpr int int_tile_outputs() { return kIntBlocksPerLane * IntCfg<STEP>::R; }
 template <int STEP> __host__ __device__ constexpr int int_window() { return STEP * (int_tile_outputs<STEP>() - 1) + SINC_LEN; }
-template <int STEP> __host__ __device__ constexpr int int_lane_stride() { return ((int_window<STEP>() + 4 + 31) / 32) * 32 + IntCfg<STEP>::SKEW; }
+template <int STEP> __host__ __device__ constexpr int int_lane_stride() { return ((int_window<STEP>() + 8 + 31) / 32) * 32 + IntCfg<STEP>::SKEW; }
 template <int STEP> __host__ __device__ constexpr int int_smem_bytes() { return 2 * int_lane_stride<STEP>() * (int)sizeof(float); }
 
-// The FIR core: walk the thread's input span once; each LDS.128 feeds 4*R FFMAs whose coefficient
-// operand is a kernel-parameter constant (c[0x0][..]).  Accumulator (r, l) sees its taps in
-// increasing order, i.e. exactly rubato's per-lane fused accumulation.
-template <int STEP, int R, int LEAD = 0>
-__device__ __forceinline__ void fir_core(const float* __restrict__ w, const Taps& taps, float (&acc)[R][8]) {
-    constexpr int NIN = LEAD + STEP * (R - 1) + SINC_LEN;
-    constexpr int NV = (NIN + 3) / 4;
+// The FIR core: walk the thread's input span once.  Every LDS.128 yields two packed pairs (x[m], x[m+1]),
+// m even, and each pair feeds one FFMA2 per output r: taps (j, j+1) with j = m - LEAD - STEP*r go to the
+// accumulator pair of lanes (j & 7, (j+1) & 7).  Lane l of output r therefore still receives exactly its
+// taps l, l+8, ... in increasing order with fused multiply-adds — rubato's AVX accumulation — while the
+// instruction count is half of the scalar form (R*128 FFMA2 instead of R*256 FFMA) and the coefficient
+// pair is a uniform-register operand fed from the constant bank (kernel parameter).
+// Outputs whose j is odd for even m use the shifted table `ho` and pair lanes (1,2)(3,4)(5,6)(7,0); their
+// first / last pair carries one zero coefficient (x * 0 = +-0 leaves a non-negative-zero accumulator
+// unchanged for finite x; tiles that stage non-finite or huge floats take the exact slow path instead).
+template <int STEP, int R, int LEAD>
+__device__ __forceinline__ void fir_core2(const float* __restrict__ w, const Taps& taps, float (&lanes)[R][8]) {
+    constexpr int NIN = ((LEAD + STEP * (R - 1) + SINC_LEN + 1 + 3) / 4) * 4;
+    unsigned long long acc[R][4];
 #pragma unroll
-    for (int v = 0; v < NV; v++) {
-        const float4 q = *reinterpret_cast<const float4*>(w + 4 * v);
-        const float xs[4] = {q.x, q.y, q.z, q.w};
+    for (int r = 0; r < R; r++)
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int m = 4 * v + e;
+        for (int p = 0; p < 4; p++) acc[r][p] = 0ull;
+#pragma unroll
+    for (int v = 0; v < NIN / 4; v++) {
+        unsigned long long x[2];
+        asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(x[0]), "=l"(x[1]) : "r"((unsigned)__cvta_generic_to_shared(w + 4 * v)));
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int m = 4 * v + 2 * e;
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                const int j = m - LEAD - STEP * r;
-                if (j >= 0 && j < SINC_LEN) acc[r][j & 7] = __fmaf_rn(xs[e], taps.h[j], acc[r][j & 7]);
+                const int j = m - LEAD - STEP * r;  // tap of the pair's low element
+                const bool odd = ((LEAD + STEP * r) & 1) != 0;
+                if (!odd) {
+                    if (j >= 0 && j + 1 < SINC_LEN) ffma2(acc[r][(j & 7) >> 1], x[e], *reinterpret_cast<const unsigned long long*>(&taps.he[j]));
+                } else {
+                    if (j >= -1 && j <= SINC_LEN - 1) ffma2(acc[r][(j & 7) >> 1], x[e], *reinterpret_cast<const unsigned long long*>(&taps.ho[j + 1]));
+                }
             }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const bool odd = ((LEAD + STEP * r) & 1) != 0;
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const float lo = __uint_as_float((unsigned)(acc[r][p] & 0xffffffffull)), hi = __uint_as_float((unsigned)(acc[r][p] >> 32));
+            if (!odd) { lanes[r][2 * p] = lo; lanes[r][2 * p + 1] = hi; }
+            else { lanes[r][2 * p + 1] = lo; lanes[r][(2 * p + 2) & 7] = hi; }
         }
     }
 }
@@ -396,23 +430,28 @@ __device__ __forceinline__ void int_epilogue(const float (&y)[R], const OutDesc&
     const long long nb = n0 + (long long)R * b;  // first output of this thread
     if (dst.mix != SK_MIX_NONE) {
         // lanes are (L, R) of one stream in adjacent threads: exchange, then each thread stores half
-        float o[R];
+        // lane 0 (L) finishes outputs [0, H), lane 1 (R) outputs [H, R): each sends the other half across
+        constexpr int H = (R + 1) / 2;
+        float o[H];
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            const float other = __shfl_xor_sync(0xffffffffu, y[r], 1);
-            const float l = lane == 0 ? y[r] : other, rr = lane == 0 ? other : y[r];
-            if (dst.mix == SK_MIX_SCALE_THEN_SUM) o[r] = __fadd_rn(__fadd_rn(0.0f, __fmul_rn(l, 0.5f)), __fmul_rn(rr, 0.5f));
-            else o[r] = __fmul_rn(__fadd_rn(__fadd_rn(0.0f, l), rr), 0.5f);
+        for (int q = 0; q < H; q++) {
+            const int mine = q < R - H ? q + H : R - 1;  // index lane 0 gives away (clamped when R is odd)
+            const float give = lane == 0 ? y[mine] : y[q];
+            const float got = __shfl_xor_sync(0xffffffffu, give, 1);
+            const float keep = lane == 0 ? y[q] : y[mine];
+            const float l = lane == 0 ? keep : got, rr = lane == 0 ? got : keep;
+            if (dst.mix == SK_MIX_SCALE_THEN_SUM) o[q] = __fadd_rn(__fadd_rn(0.0f, __fmul_rn(l, 0.5f)), __fmul_rn(rr, 0.5f));
+            else o[q] = __fmul_rn(__fadd_rn(__fadd_rn(0.0f, l), rr), 0.5f);
         }
         float* op = dst.base + stream * dst.stream_stride;
-        constexpr int H = (R + 1) / 2;
+        const long long no = nb + (long long)H * lane;  // first output this thread stores
+        const int cnt = lane == 0 ? H : R - H;
         if (R == 8 && nb + 8 <= dst.n_out && ((dst.stream_stride & 3) == 0)) {
-            const float4 v = lane == 0 ? make_float4(o[0], o[1], o[2], o[3]) : make_float4(o[4], o[5], o[6], o[7]);
-            *reinterpret_cast<float4*>(op + nb + 4 * lane) = v;
+            *reinterpret_cast<float4*>(op + no) = make_float4(o[0], o[1], o[2], o[3]);
         } else {
 #pragma unroll
-            for (int r = 0; r < R; r++)
-                if ((r / H) == lane && nb + r < dst.n_out) op[nb + r] = o[r];
+            for (int q = 0; q < H; q++)
+                if (q < cnt && no + q < dst.n_out) op[no + q] = o[q];
         }
     } else {
         if (lane == 1 && !lane1_valid) return;
@@ -456,25 +495,20 @@ resample_int_kernel(const __grid_constant__ Taps taps, const __grid_constant__ S
     const int lane = threadIdx.x & 1, b = threadIdx.x >> 1;
     const float* w = smem + lane * WS + STEP * R * b;
     float acc[R][8];
-#pragma unroll
-    for (int r = 0; r < R; r++)
-#pragma unroll
-        for (int l = 0; l < 8; l++) acc[r][l] = 0.0f;
-    fir_core<STEP, R>(w, taps, acc);
+    fir_core2<STEP, R, 0>(w, taps, acc);
 
     float y[R];
 #pragma unroll
     for (int r = 0; r < R; r++) y[r] = reduce8(acc[r]);
     if (s_big) {
-        // some |x| >= 2^113 in this window: p1 may overflow where p0 does not, so evaluate the
-        // reference's full expression p0 + 0.0 * (p1 - p0) (subindex 1, same input index)
+        // some |x| >= 2^113 (or non-finite) in this window: evaluate the reference's full expression
+        // p0 + 0.0 * (p1 - p0) with plain dot products (subindex 0 and 1, same input index)
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            const float p1 = dot256(w + STEP * r, row1);
-            y[r] = __fadd_rn(y[r], __fmul_rn(0.0f, __fsub_rn(p1, y[r])));
+            const float p0 = dot256(w + STEP * r, row1 - SINC_LEN), p1 = dot256(w + STEP * r, row1);
+            y[r] = __fadd_rn(p0, __fmul_rn(0.0f, __fsub_rn(p1, p0)));
         }
     }
-
     int_epilogue<R>(y, dst, stream, n0, b, lane, lane0, lane1_valid);
 }
 
@@ -515,44 +549,96 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // base stays 16-byte aligned; the taps are shifted by LEAD at compile time instead.
 template <int STEP> __host__ __device__ constexpr int tma_lead() { return STEP % 8; }
 template <int STEP> __host__ __device__ constexpr int tma_frames() { return ((tma_lead<STEP>() + int_window<STEP>() + 7) / 8) * 8; }
-template <int STEP> __host__ __device__ constexpr int tma_lane_stride() { return ((tma_frames<STEP>() + 4 + 31) / 32) * 32 + IntCfg<STEP>::SKEW; }
+template <int STEP> __host__ __device__ constexpr int tma_lane_stride() { return ((tma_frames<STEP>() + 8 + 31) / 32) * 32 + IntCfg<STEP>::SKEW; }
 template <int STEP, int SRCW> __host__ __device__ constexpr int tma_raw_bytes() { return tma_frames<STEP>() * 2 * SRCW; }
 template <int STEP, int SRCW> __host__ __device__ constexpr int tma_smem_bytes() {
     return 2 * tma_lane_stride<STEP>() * (int)sizeof(float) + 2 * tma_raw_bytes<STEP, SRCW>() + 64;
 }
 
-// 4 stereo frames from the raw words -> l[4], r[4] sample bits (little-endian assembled, sign handled by decode)
-template <int SRCW, bool BE>
-__device__ __forceinline__ void unpack4(const uint32_t* w, uint32_t* l, uint32_t* r) {
+// 4 interleaved stereo frames (FB words in memory order) -> 4 L and 4 R f32 samples.  Everything about
+// the format is a template parameter: no per-sample branches.  Scale is an exact power of two.
+template <int SRCW, bool BE, bool ISFLOAT, bool SCRUB>
+__device__ __forceinline__ void convert4(const uint32_t* w, float scale, float* l, float* r) {
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        if (SRCW == 2) {
-            uint32_t a = w[k] & 0xffffu, b = w[k] >> 16;
-            if (BE) { a = __byte_perm(a, 0, 0x3201) & 0xffffu; b = __byte_perm(b, 0, 0x3201) & 0xffffu; }
-            l[k] = a; r[k] = b;
-        } else if (SRCW == 3) {
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
+        for (int c = 0; c < 2; c++) {
+            float f;
+            if (SRCW == 2) {
+                uint32_t h = c == 0 ? (w[k] & 0xffffu) : (w[k] >> 16);
+                if (BE) h = __byte_perm(h, 0, 0x3201) & 0xffffu;
+                f = __fmul_rn((float)(int16_t)h, scale);
+            } else if (SRCW == 3) {
                 const int o = 3 * (2 * k + c), wi = o >> 2, sh = o & 3;
                 const uint32_t lo = w[wi], hi = (sh >= 2) ? w[wi + 1] : 0u;
-                // bytes sh, sh+1, sh+2 -> result bytes 0, 1, 2 (LE) or 2, 1, 0 (BE); byte 3 = 0 via the zero source (index 4.. of hi when unused)
-                const uint32_t sel = !BE ? ((uint32_t)(sh + 2) << 8) | ((uint32_t)(sh + 1) << 4) | (uint32_t)sh
-                                         : ((uint32_t)sh << 8) | ((uint32_t)(sh + 1) << 4) | (uint32_t)(sh + 2);
-                const uint32_t v = __byte_perm(lo, hi, sel) & 0x00ffffffu;
-                if (c == 0) l[k] = v; else r[k] = v;
+                // sample bytes -> result bytes 1..3 (most significant byte on top), then arithmetic >> 8 sign-extends
+                const uint32_t sel = !BE ? ((uint32_t)(sh + 2) << 12) | ((uint32_t)(sh + 1) << 8) | ((uint32_t)sh << 4)
+                                         : ((uint32_t)sh << 12) | ((uint32_t)(sh + 1) << 8) | ((uint32_t)(sh + 2) << 4);
+                f = __fmul_rn(__int2float_rn(((int32_t)__byte_perm(lo, hi, sel)) >> 8), scale);
+            } else {
+                uint32_t u = w[2 * k + c];
+                if (BE) u = bswap32(u);
+                if (ISFLOAT) f = (SCRUB && (u & 0x7f800000u) == 0x7f800000u) ? 0.0f : __uint_as_float(u);
+                else f = __fmul_rn(__int2float_rn((int32_t)u), scale);
             }
-        } else {
-            uint32_t a = w[2 * k], b = w[2 * k + 1];
-            if (BE) { a = bswap32(a); b = bswap32(b); }
-            l[k] = a; r[k] = b;
+            if (c == 0) l[k] = f; else r[k] = f;
         }
     }
+}
+
+// raw bytes of one tile (shared memory, filled by the TMA) -> two f32 windows.  Groups [g_lo, g_hi) of 4
+// frames are completely inside the copied range; the few others (stream start / end) go frame by frame
+// through global memory with range checks.  Returns whether a huge / non-finite float was staged.
+template <int SRCW, int WF, int WS, bool BE, bool ISFLOAT, bool SCRUB>
+__device__ __forceinline__ bool convert_window(const uint8_t* __restrict__ rb, float* __restrict__ win, const SrcDesc& src, long long stream,
+                                               long long wa, int g_lo, int g_hi) {
+    constexpr int FB = 2 * SRCW;
+    bool big = false;
+    for (int g = threadIdx.x; g < WF / 4; g += kIntThreads) {
+        float l[4], r[4];
+        if (g >= g_lo && g < g_hi) {
+            uint32_t w[FB];
+            if (SRCW == 3) {
+#pragma unroll
+                for (int v = 0; v < 3; v++) {
+                    const uint2 q = *reinterpret_cast<const uint2*>(rb + g * 24 + 8 * v);
+                    w[2 * v] = q.x; w[2 * v + 1] = q.y;
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < FB / 4; v++) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(rb + g * (4 * FB) + 16 * v);
+                    w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
+                }
+            }
+            convert4<SRCW, BE, ISFLOAT, SCRUB>(w, src.scale, l, r);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const long long ff = wa + 4 * g + q;
+                l[q] = 0.0f; r[q] = 0.0f;
+                if (ff >= src.valid_lo && ff < src.valid_hi) {
+                    const uint8_t* sbase = src.base + stream * src.stream_stride;
+                    l[q] = decode_sample_bits(load_sample_bits(sbase, ff, 0, src), src);
+                    r[q] = decode_sample_bits(load_sample_bits(sbase, ff, 1, src), src);
+                }
+            }
+        }
+        if (ISFLOAT) {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                big |= ((__float_as_uint(l[q]) & 0x7f800000u) >= 0x78000000u) | ((__float_as_uint(r[q]) & 0x7f800000u) >= 0x78000000u);
+        }
+        *reinterpret_cast<float4*>(win + 4 * g) = make_float4(l[0], l[1], l[2], l[3]);
+        *reinterpret_cast<float4*>(win + WS + 4 * g) = make_float4(r[0], r[1], r[2], r[3]);
+    }
+    return big;
 }
 
 template <int STEP, int SRCW>
 __global__ void __launch_bounds__(kIntThreads, 2)
 resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant__ SrcDesc src, const __grid_constant__ OutDesc dst, long long i0_first,
-                        int tiles_per_stream, long long total_tiles, const float* __restrict__ row1) {
+                        unsigned tiles_per_stream, unsigned total_tiles, const float* __restrict__ row1) {
     constexpr int R = IntCfg<STEP>::R;
     constexpr int T = int_tile_outputs<STEP>();
     constexpr int LEAD = tma_lead<STEP>();
@@ -565,26 +651,26 @@ resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant
     uint8_t* raw = smem_raw + 2 * WS * sizeof(float);
     uint64_t* bars = reinterpret_cast<uint64_t*>(raw + 2 * RAWB);
 
-    const long long nk = (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;  // tiles this CTA owns
-    const long long stream_bytes16 = ((src.valid_hi * FB) / 16) * 16;             // bytes of a stream the TMA may touch
+    const unsigned nk = (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;  // tiles this CTA owns
+    const long long stream_bytes16 = ((src.valid_hi * FB) / 16) * 16;            // bytes of a stream the TMA may touch
 
     // tile -> (stream, first output, first window frame, copy range in bytes relative to the stream)
-    auto tile_geom = [&](long long t, long long& stream, long long& n0, long long& wa, long long& b_lo, long long& b_hi) {
+    auto tile_geom = [&](unsigned t, unsigned& stream, long long& n0, long long& wa, long long& b_lo, long long& b_hi) {
         stream = t / tiles_per_stream;
-        n0 = (t % tiles_per_stream) * (long long)T;
+        n0 = (long long)(t - stream * tiles_per_stream) * T;
         wa = i0_first + (long long)STEP * n0 - LEAD;
         b_lo = wa * FB; if (b_lo < 0) b_lo = 0;
         b_hi = (wa + WF) * FB; if (b_hi > stream_bytes16) b_hi = stream_bytes16;
         if (b_hi < b_lo) b_hi = b_lo;
     };
-    auto issue = [&](long long k) {  // one elected thread
-        long long stream, n0, wa, b_lo, b_hi;
+    auto issue = [&](unsigned k) {  // one elected thread
+        unsigned stream; long long n0, wa, b_lo, b_hi;
         tile_geom(blockIdx.x + k * gridDim.x, stream, n0, wa, b_lo, b_hi);
         const int buf = (int)(k & 1);
         const uint32_t bar = smem_u32(&bars[buf]);
         const uint32_t bytes = (uint32_t)(b_hi - b_lo);
         mbar_expect_tx(bar, bytes);
-        if (bytes) tma_load_1d(smem_u32(raw + buf * RAWB + (b_lo - wa * FB)), src.base + stream * src.stream_stride + b_lo, bytes, bar);
+        if (bytes) tma_load_1d(smem_u32(raw + buf * RAWB + (b_lo - wa * FB)), src.base + (long long)stream * src.stream_stride + b_lo, bytes, bar);
     };
 
     if (threadIdx.x == 0) {
@@ -597,78 +683,41 @@ resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant
     __syncthreads();
 
     const int lane = threadIdx.x & 1, b = threadIdx.x >> 1;
-    for (long long k = 0; k < nk; k++) {
-        long long stream, n0, wa, b_lo, b_hi;
+    for (unsigned k = 0; k < nk; k++) {
+        unsigned stream; long long n0, wa, b_lo, b_hi;
         tile_geom(blockIdx.x + k * gridDim.x, stream, n0, wa, b_lo, b_hi);
         const int buf = (int)(k & 1);
-        mbar_wait(smem_u32(&bars[buf]), (uint32_t)((k >> 1) & 1));
+        // groups of 4 frames fully inside the copied byte range [b_lo, b_hi)
+        const int g_lo = (int)((b_lo - wa * FB + 4 * FB - 1) / (4 * FB));
+        const int g_hi = (int)((b_hi - wa * FB) / (4 * FB));
+        mbar_wait(smem_u32(&bars[buf]), (k >> 1) & 1);
 
-        // ---- raw bytes -> f32 windows (4 frames per thread step, 128-bit shared stores)
         const uint8_t* rb = raw + buf * RAWB;
-        const long long c_lo = b_lo / FB, c_hi = b_hi / FB;  // frames fully present in the raw buffer
-        bool big = false;
-        for (int g = threadIdx.x; g < WF / 4; g += kIntThreads) {
-            const long long f = wa + 4 * g;
-            float l[4], r[4];
-            if (f >= c_lo && f + 4 <= c_hi) {
-                uint32_t w[FB];  // 4 frames = FB words
-                if (SRCW == 3) {
-#pragma unroll
-                    for (int v = 0; v < 3; v++) {
-                        const uint2 q = *reinterpret_cast<const uint2*>(rb + g * 24 + 8 * v);
-                        w[2 * v] = q.x; w[2 * v + 1] = q.y;
-                    }
-                } else {
-#pragma unroll
-                    for (int v = 0; v < FB / 4; v++) {
-                        const uint4 q = *reinterpret_cast<const uint4*>(rb + g * (4 * FB) + 16 * v);
-                        w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
-                    }
-                }
-                uint32_t lb[4], rbits[4];
-                if (src.big_endian) unpack4<SRCW, true>(w, lb, rbits); else unpack4<SRCW, false>(w, lb, rbits);
-#pragma unroll
-                for (int q = 0; q < 4; q++) { l[q] = decode_sample_bits(lb[q], src); r[q] = decode_sample_bits(rbits[q], src); }
-            } else {
-                // window edge (stream start / end / last partial 16 bytes): per-frame, straight from global memory
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const long long ff = f + q;
-                    l[q] = 0.0f; r[q] = 0.0f;
-                    if (ff >= src.valid_lo && ff < src.valid_hi) {
-                        const uint8_t* sbase = src.base + stream * src.stream_stride;
-                        l[q] = decode_sample_bits(load_sample_bits(sbase, ff, 0, src), src);
-                        r[q] = decode_sample_bits(load_sample_bits(sbase, ff, 1, src), src);
-                    }
-                }
-            }
-            if (SRCW == 4) {
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    big |= ((__float_as_uint(l[q]) & 0x7f800000u) >= 0x78000000u) | ((__float_as_uint(r[q]) & 0x7f800000u) >= 0x78000000u);
-            }
-            *reinterpret_cast<float4*>(win + 4 * g) = make_float4(l[0], l[1], l[2], l[3]);
-            *reinterpret_cast<float4*>(win + WS + 4 * g) = make_float4(r[0], r[1], r[2], r[3]);
+        bool big;
+        if (SRCW == 4 && src.is_float) {
+            if (src.scrub) big = src.big_endian ? convert_window<SRCW, WF, WS, true, true, true>(rb, win, src, stream, wa, g_lo, g_hi)
+                                                : convert_window<SRCW, WF, WS, false, true, true>(rb, win, src, stream, wa, g_lo, g_hi);
+            else big = src.big_endian ? convert_window<SRCW, WF, WS, true, true, false>(rb, win, src, stream, wa, g_lo, g_hi)
+                                      : convert_window<SRCW, WF, WS, false, true, false>(rb, win, src, stream, wa, g_lo, g_hi);
+        } else {
+            big = src.big_endian ? convert_window<SRCW, WF, WS, true, false, false>(rb, win, src, stream, wa, g_lo, g_hi)
+                                 : convert_window<SRCW, WF, WS, false, false, false>(rb, win, src, stream, wa, g_lo, g_hi);
         }
-        const int any_big = __syncthreads_or((SRCW == 4 && src.is_float) ? (int)big : 0);  // windows ready, raw[buf] free
+        const int any_big = __syncthreads_or((int)big);  // windows ready, raw[buf] free
         if (threadIdx.x == 0 && k + 2 < nk) issue(k + 2);
 
         // ---- FIR
         const float* w = win + lane * WS + STEP * R * b;
         float acc[R][8];
-#pragma unroll
-        for (int r = 0; r < R; r++)
-#pragma unroll
-            for (int q = 0; q < 8; q++) acc[r][q] = 0.0f;
-        fir_core<STEP, R, LEAD>(w, taps, acc);
+        fir_core2<STEP, R, LEAD>(w, taps, acc);
         float y[R];
 #pragma unroll
         for (int r = 0; r < R; r++) y[r] = reduce8(acc[r]);
-        if (any_big) {
+        if (any_big) {  // exact slow path, see resample_int_kernel
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                const float p1 = dot256(w + LEAD + STEP * r, row1);
-                y[r] = __fadd_rn(y[r], __fmul_rn(0.0f, __fsub_rn(p1, y[r])));
+                const float p0 = dot256(w + LEAD + STEP * r, row1 - SINC_LEN), p1 = dot256(w + LEAD + STEP * r, row1);
+                y[r] = __fadd_rn(p0, __fmul_rn(0.0f, __fsub_rn(p1, p0)));
             }
         }
         int_epilogue<R>(y, dst, stream, n0, b, lane, 0, true);
@@ -761,8 +810,8 @@ static int launch_int_tma(sk_ctx* ctx, const Taps& taps, const SrcDesc& src, con
     const long long total = tiles_per_stream * (long long)n_streams;
     const int per_sm = smem <= 110 * 1024 ? 2 : 1;
     const long long grid = std::min<long long>(total, (long long)ctx->num_sms * per_sm);
-    resample_int_tma_kernel<STEP, SRCW><<<(unsigned)grid, kIntThreads, smem, ctx->stream>>>(taps, src, dst, plan->i0_first, (int)tiles_per_stream, total,
-                                                                                          d_table + SINC_LEN);
+    resample_int_tma_kernel<STEP, SRCW><<<(unsigned)grid, kIntThreads, smem, ctx->stream>>>(taps, src, dst, plan->i0_first, (unsigned)tiles_per_stream,
+                                                                                          (unsigned)total, d_table + SINC_LEN);
     SK_LAUNCH_CHECK(ctx);
     return SK_OK;
 }
@@ -771,11 +820,13 @@ template <int STEP>
 static int launch_int(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, const float* h_table, const float* d_table,
                       size_t n_streams, int lanes_per_stream) {
     Taps taps;
-    memcpy(taps.h, h_table, sizeof(taps.h));  // subindex 0
+    memset(&taps, 0, sizeof(taps));
+    memcpy(taps.he, h_table, SINC_LEN * sizeof(float));      // subindex 0
+    memcpy(taps.ho + 1, h_table, SINC_LEN * sizeof(float));  // ho[i] = h[i-1]
     // fast path: interleaved stereo, 16-byte aligned streams, canonical first index (batch plans)
     if (src.width != 0 && src.channels == 2 && lanes_per_stream == 2 && src.origin == 0 && src.valid_lo == 0 &&
         plan->i0_first == -(long long)(SINC_LEN / 2) + STEP && ((uintptr_t)src.base % 16) == 0 && (src.stream_stride % 16) == 0 &&
-        (long long)n_streams * (long long)((plan->n_out + int_tile_outputs<STEP>() - 1) / int_tile_outputs<STEP>()) < (1ll << 40)) {
+        (long long)n_streams * (long long)((plan->n_out + int_tile_outputs<STEP>() - 1) / int_tile_outputs<STEP>()) < (1ll << 31)) {
         if (src.width == 2) return launch_int_tma<STEP, 2>(ctx, taps, src, dst, plan, d_table, n_streams);
         if (src.width == 3) return launch_int_tma<STEP, 3>(ctx, taps, src, dst, plan, d_table, n_streams);
         return launch_int_tma<STEP, 4>(ctx, taps, src, dst, plan, d_table, n_streams);
