@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsoundkit_cuda.so")
+LIB_PATH = os.environ.get("SOUNDKIT_CUDA_LIB") or os.path.join(_HERE, "libsoundkit_cuda.so")  # env override: A/B builds
 
 # enums of include/soundkit_cuda.h
 OK, E_ARG, E_ALLOC, E_CUDA, E_STATE, E_NODEVICE = 0, -1, -2, -3, -4, -5

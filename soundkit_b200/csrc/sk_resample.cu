@@ -635,8 +635,15 @@ __device__ __forceinline__ bool convert_window(const uint8_t* __restrict__ rb, f
     return big;
 }
 
+// per-tile geometry, computed once by the TMA-issuing thread and handed to the CTA through shared memory
+struct TileGeom { int stream; int n0; int wa; int g_lo; int g_hi; int pad[3]; };
+
+#ifndef SK_TMA_CTAS_PER_SM
+#define SK_TMA_CTAS_PER_SM 3
+#endif
+
 template <int STEP, int SRCW>
-__global__ void __launch_bounds__(kIntThreads, 2)
+__global__ void __launch_bounds__(kIntThreads, SK_TMA_CTAS_PER_SM)
 resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant__ SrcDesc src, const __grid_constant__ OutDesc dst, long long i0_first,
                         unsigned tiles_per_stream, unsigned total_tiles, const float* __restrict__ row1) {
     constexpr int R = IntCfg<STEP>::R;
@@ -650,22 +657,25 @@ resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant
     float* win = reinterpret_cast<float*>(smem_raw);
     uint8_t* raw = smem_raw + 2 * WS * sizeof(float);
     uint64_t* bars = reinterpret_cast<uint64_t*>(raw + 2 * RAWB);
+    __shared__ TileGeom geoms[4];
 
     const unsigned nk = (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;  // tiles this CTA owns
-    const long long stream_bytes16 = ((src.valid_hi * FB) / 16) * 16;            // bytes of a stream the TMA may touch
 
-    // tile -> (stream, first output, first window frame, copy range in bytes relative to the stream)
-    auto tile_geom = [&](unsigned t, unsigned& stream, long long& n0, long long& wa, long long& b_lo, long long& b_hi) {
-        stream = t / tiles_per_stream;
-        n0 = (long long)(t - stream * tiles_per_stream) * T;
-        wa = i0_first + (long long)STEP * n0 - LEAD;
-        b_lo = wa * FB; if (b_lo < 0) b_lo = 0;
-        b_hi = (wa + WF) * FB; if (b_hi > stream_bytes16) b_hi = stream_bytes16;
+    // one elected thread: geometry of tile k -> geoms[k & 3], then the TMA request for its raw bytes
+    auto issue = [&](unsigned k) {
+        const unsigned t = blockIdx.x + k * gridDim.x;
+        const unsigned stream = t / tiles_per_stream;
+        const long long n0 = (long long)(t - stream * tiles_per_stream) * T;
+        const long long wa = i0_first + (long long)STEP * n0 - LEAD;                  // first frame of the shared window
+        const long long stream_bytes16 = ((src.valid_hi * FB) / 16) * 16;             // bytes of a stream the TMA may touch
+        long long b_lo = wa * FB; if (b_lo < 0) b_lo = 0;
+        long long b_hi = (wa + WF) * FB; if (b_hi > stream_bytes16) b_hi = stream_bytes16;
         if (b_hi < b_lo) b_hi = b_lo;
-    };
-    auto issue = [&](unsigned k) {  // one elected thread
-        unsigned stream; long long n0, wa, b_lo, b_hi;
-        tile_geom(blockIdx.x + k * gridDim.x, stream, n0, wa, b_lo, b_hi);
+        TileGeom g;
+        g.stream = (int)stream; g.n0 = (int)n0; g.wa = (int)wa;
+        g.g_lo = (int)((b_lo - wa * FB + 4 * FB - 1) / (4 * FB));  // groups of 4 frames fully inside the copied bytes
+        g.g_hi = (int)((b_hi - wa * FB) / (4 * FB));
+        geoms[k & 3] = g;
         const int buf = (int)(k & 1);
         const uint32_t bar = smem_u32(&bars[buf]);
         const uint32_t bytes = (uint32_t)(b_hi - b_lo);
@@ -684,24 +694,20 @@ resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant
 
     const int lane = threadIdx.x & 1, b = threadIdx.x >> 1;
     for (unsigned k = 0; k < nk; k++) {
-        unsigned stream; long long n0, wa, b_lo, b_hi;
-        tile_geom(blockIdx.x + k * gridDim.x, stream, n0, wa, b_lo, b_hi);
+        const TileGeom g = geoms[k & 3];
         const int buf = (int)(k & 1);
-        // groups of 4 frames fully inside the copied byte range [b_lo, b_hi)
-        const int g_lo = (int)((b_lo - wa * FB + 4 * FB - 1) / (4 * FB));
-        const int g_hi = (int)((b_hi - wa * FB) / (4 * FB));
         mbar_wait(smem_u32(&bars[buf]), (k >> 1) & 1);
 
         const uint8_t* rb = raw + buf * RAWB;
         bool big;
         if (SRCW == 4 && src.is_float) {
-            if (src.scrub) big = src.big_endian ? convert_window<SRCW, WF, WS, true, true, true>(rb, win, src, stream, wa, g_lo, g_hi)
-                                                : convert_window<SRCW, WF, WS, false, true, true>(rb, win, src, stream, wa, g_lo, g_hi);
-            else big = src.big_endian ? convert_window<SRCW, WF, WS, true, true, false>(rb, win, src, stream, wa, g_lo, g_hi)
-                                      : convert_window<SRCW, WF, WS, false, true, false>(rb, win, src, stream, wa, g_lo, g_hi);
+            if (src.scrub) big = src.big_endian ? convert_window<SRCW, WF, WS, true, true, true>(rb, win, src, g.stream, g.wa, g.g_lo, g.g_hi)
+                                                : convert_window<SRCW, WF, WS, false, true, true>(rb, win, src, g.stream, g.wa, g.g_lo, g.g_hi);
+            else big = src.big_endian ? convert_window<SRCW, WF, WS, true, true, false>(rb, win, src, g.stream, g.wa, g.g_lo, g.g_hi)
+                                      : convert_window<SRCW, WF, WS, false, true, false>(rb, win, src, g.stream, g.wa, g.g_lo, g.g_hi);
         } else {
-            big = src.big_endian ? convert_window<SRCW, WF, WS, true, false, false>(rb, win, src, stream, wa, g_lo, g_hi)
-                                 : convert_window<SRCW, WF, WS, false, false, false>(rb, win, src, stream, wa, g_lo, g_hi);
+            big = src.big_endian ? convert_window<SRCW, WF, WS, true, false, false>(rb, win, src, g.stream, g.wa, g.g_lo, g.g_hi)
+                                 : convert_window<SRCW, WF, WS, false, false, false>(rb, win, src, g.stream, g.wa, g.g_lo, g.g_hi);
         }
         const int any_big = __syncthreads_or((int)big);  // windows ready, raw[buf] free
         if (threadIdx.x == 0 && k + 2 < nk) issue(k + 2);
@@ -720,7 +726,7 @@ resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant
                 y[r] = __fadd_rn(p0, __fmul_rn(0.0f, __fsub_rn(p1, p0)));
             }
         }
-        int_epilogue<R>(y, dst, stream, n0, b, lane, 0, true);
+        int_epilogue<R>(y, dst, g.stream, g.n0, b, lane, 0, true);
         __syncthreads();  // windows free for the next tile
     }
 }
@@ -808,7 +814,7 @@ static int launch_int_tma(sk_ctx* ctx, const Taps& taps, const SrcDesc& src, con
     SK_CUDA(ctx, cudaFuncSetAttribute(resample_int_tma_kernel<STEP, SRCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const long long tiles_per_stream = (long long)((plan->n_out + T - 1) / T);
     const long long total = tiles_per_stream * (long long)n_streams;
-    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+    const int per_sm = std::max(1, std::min(SK_TMA_CTAS_PER_SM, (220 * 1024) / smem));
     const long long grid = std::min<long long>(total, (long long)ctx->num_sms * per_sm);
     resample_int_tma_kernel<STEP, SRCW><<<(unsigned)grid, kIntThreads, smem, ctx->stream>>>(taps, src, dst, plan->i0_first, (unsigned)tiles_per_stream,
                                                                                           (unsigned)total, d_table + SINC_LEN);
