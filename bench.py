@@ -166,10 +166,14 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- GPU leg
-def extras(ctx, torch, peaks):
-    """secondary kernels (BASELINE configs 2-4), device resident, CUDA-event timed, each > L2 sized."""
+def extras(ctx, torch, peaks, only=None):
+    """secondary kernels (BASELINE configs 2-4), device resident, CUDA-event timed, each > L2 sized.
+    `only`: optional list of substrings selecting which groups run (g711 / convert / resample)."""
     from soundkit_b200 import capi
     res = {}
+
+    def want(group):
+        return only is None or any(o in group for o in only)
 
     def timed(fn, reps=5):
         fn(); torch.cuda.synchronize()
@@ -181,35 +185,51 @@ def extras(ctx, torch, peaks):
         return best * 1e-3
 
     hbm = peaks.get("hbm_gbs", 6650.0)
-    n = 1 << 30  # 1 Gi samples of G.711
-    codes = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda")
-    pcm = torch.empty((n,), dtype=torch.int16, device="cuda")
-    t = timed(lambda: ctx.g711_decode_dev(capi.LAW_MULAW, codes, n, capi.KIND_I16, pcm))
-    res["g711_decode_ulaw_i16"] = {"GB/s": 3 * n / t / 1e9, "frac_of_measured_hbm": 3 * n / t / 1e9 / hbm, "Msamples/s": n / t / 1e6}
-    t = timed(lambda: ctx.g711_encode_dev(capi.LAW_MULAW, capi.KIND_I16, pcm, n, codes))
-    res["g711_encode_ulaw_i16"] = {"GB/s": 3 * n / t / 1e9, "frac_of_measured_hbm": 3 * n / t / 1e9 / hbm, "Msamples/s": n / t / 1e6}
-    del codes, pcm
-    # conversion: 64 streams x 60 s stereo 48 kHz -> planar f32 (BASELINE configs[1] wave)
-    S, frames = 64, 2880000
-    out = torch.empty((S, 2, frames), dtype=torch.float32, device="cuda")
-    for bits, fmt, name in ((16, 0, "s16le"), (24, 0, "s24le"), (32, 1, "f32le")):
-        raw = torch.randint(0, 256, (S, frames * 2 * bits // 8), dtype=torch.uint8, device="cuda")
-        t = timed(lambda: ctx.pcm_to_planar_f32_dev(raw, raw.stride(0), S, frames, bits, fmt, False, 2, capi.MODE_B, out, 2 * frames))
-        nb = S * frames * 2 * (bits // 8 + 4)
-        res[f"convert_{name}_stereo_to_planar_f32"] = {"GB/s": nb / t / 1e9, "frac_of_measured_hbm": nb / t / 1e9 / hbm,
-                                                       "Msamples/s": S * frames * 2 / t / 1e6}
-        del raw
-    del out
-    # non-integer ratio 44.1k -> 48k stereo f32 (BASELINE configs[3] wave), one-shot semantics
-    S, frames = 16, 2646000
-    n_out = ctx.batch_plan(44100, 48000, frames, capi.SEM_ONESHOT)
-    x = (torch.rand((S, frames * 2), device="cuda") - 0.5)
-    o = torch.empty((S, 2, n_out), dtype=torch.float32, device="cuda")
-    d = capi.BatchDesc(x.data_ptr(), x.stride(0) * 4, S, frames, 32, 1, 0, 2, capi.MODE_A, 44100, 48000, capi.SEM_ONESHOT,
-                       capi.MIX_NONE, o.data_ptr(), 2 * n_out, n_out)
-    t = timed(lambda: ctx.normalize_batch_dev(d), reps=3)
-    fl = 1027.0 * S * 2 * n_out
-    res["resample_44k1_to_48k_stereo_f32"] = {"TFLOP/s": fl / t / 1e12, "Msamples/s": S * 2 * n_out / t / 1e6}
+
+    def hbm_entry(nbytes, t, samples):
+        return {"GB/s": nbytes / t / 1e9, "frac_of_measured_hbm": nbytes / t / 1e9 / hbm, "Msamples/s": samples / t / 1e6}
+
+    if want("g711"):
+        n = 1 << 30  # 1 Gi samples of G.711 (BASELINE configs[2] is 15.7 Gi samples; one wave)
+        codes = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda")
+        pcm = torch.empty((n,), dtype=torch.int16, device="cuda")
+        for law, lname in ((capi.LAW_MULAW, "ulaw"), (capi.LAW_ALAW, "alaw")):
+            t = timed(lambda: ctx.g711_decode_dev(law, codes, n, capi.KIND_I16, pcm))
+            res[f"g711_decode_{lname}_i16"] = hbm_entry(3 * n, t, n)
+            t = timed(lambda: ctx.g711_encode_dev(law, capi.KIND_I16, pcm, n, codes))
+            res[f"g711_encode_{lname}_i16"] = hbm_entry(3 * n, t, n)
+        del pcm
+        m = n // 2
+        f = torch.empty((m,), dtype=torch.float32, device="cuda")
+        t = timed(lambda: ctx.g711_decode_dev(capi.LAW_MULAW, codes, m, capi.KIND_F32, f))
+        res["g711_decode_ulaw_f32"] = hbm_entry(5 * m, t, m)
+        del f
+        i32 = torch.randint(-2 ** 31, 2 ** 31 - 1, (m,), dtype=torch.int32, device="cuda")
+        t = timed(lambda: ctx.g711_encode_dev(capi.LAW_ALAW, capi.KIND_I32, i32, m, codes))
+        res["g711_encode_alaw_i32"] = hbm_entry(5 * m, t, m)
+        del codes, i32
+    if want("convert"):
+        # conversion: 64 streams x 60 s stereo 48 kHz -> planar f32 (BASELINE configs[1] wave)
+        S, frames = 64, 2880000
+        out = torch.empty((S, 2, frames), dtype=torch.float32, device="cuda")
+        for bits, fmt, name in ((16, 0, "s16le"), (24, 0, "s24le"), (32, 1, "f32le")):
+            raw = torch.randint(0, 256, (S, frames * 2 * bits // 8), dtype=torch.uint8, device="cuda")
+            t = timed(lambda: ctx.pcm_to_planar_f32_dev(raw, raw.stride(0), S, frames, bits, fmt, False, 2, capi.MODE_B, out, 2 * frames))
+            nb = S * frames * 2 * (bits // 8 + 4)
+            res[f"convert_{name}_stereo_to_planar_f32"] = hbm_entry(nb, t, S * frames * 2)
+            del raw
+        del out
+    if want("resample"):
+        # non-integer ratio 44.1k -> 48k stereo f32 (BASELINE configs[3] wave), one-shot semantics
+        S, frames = 16, 2646000
+        n_out = ctx.batch_plan(44100, 48000, frames, capi.SEM_ONESHOT)
+        x = (torch.rand((S, frames * 2), device="cuda") - 0.5)
+        o = torch.empty((S, 2, n_out), dtype=torch.float32, device="cuda")
+        d = capi.BatchDesc(x.data_ptr(), x.stride(0) * 4, S, frames, 32, 1, 0, 2, capi.MODE_A, 44100, 48000, capi.SEM_ONESHOT,
+                           capi.MIX_NONE, o.data_ptr(), 2 * n_out, n_out)
+        t = timed(lambda: ctx.normalize_batch_dev(d), reps=3)
+        fl = 1027.0 * S * 2 * n_out
+        res["resample_44k1_to_48k_stereo_f32"] = {"TFLOP/s": fl / t / 1e12, "Msamples/s": S * 2 * n_out / t / 1e6}
     return res
 
 

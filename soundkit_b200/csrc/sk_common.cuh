@@ -26,8 +26,7 @@ struct sk_ctx {
     void* h_stage = nullptr; size_t h_cap = 0;
     void* d_in = nullptr;    size_t d_in_cap = 0;
     void* d_out = nullptr;   size_t d_out_cap = 0;
-    // G.711 encode tables (65536 x u8 per law) and sinc tables per ratio, built lazily on device
-    uint8_t* d_g711_enc[2] = {nullptr, nullptr};
+    // sinc tables per ratio, built lazily
     std::map<uint64_t, float*> sinc_tables;          // key = (in_rate << 32) | out_rate -> device [256][256]
     std::map<uint64_t, std::vector<float>> sinc_host; // same key -> host copy
     std::map<std::string, sk_plan*> plans;            // batch plans keyed by rate/frames/semantics
@@ -71,6 +70,25 @@ __device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
+}
+// non-volatile forms (read-only data): the compiler may hoist several of them ahead of their uses
+__device__ __forceinline__ uint4 ld_stream_v4_nv(const void* p) {
+    uint4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ld_stream_v2(const void* p) {
+    uint2 r;
+    asm("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const void* p) {
+    uint32_t r;
+    asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_u32(void* p, uint32_t v) {
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_stream_v4(void* p, uint4 v) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"

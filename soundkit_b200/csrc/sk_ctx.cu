@@ -40,8 +40,6 @@ extern "C" void sk_ctx_destroy(sk_ctx* ctx) {
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->d_in) cudaFree(ctx->d_in);
     if (ctx->d_out) cudaFree(ctx->d_out);
-    for (int i = 0; i < 2; i++)
-        if (ctx->d_g711_enc[i]) cudaFree(ctx->d_g711_enc[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }

@@ -61,7 +61,13 @@ __device__ __forceinline__ uint32_t g711_dec_word(int law, int kind, uint32_t co
 }
 
 // ---- decode ------------------------------------------------------------------------------------
+// Work split: a CTA iteration covers kDecThreads * CPT * kDecUnroll codes; in sub-iteration u thread t owns the
+// CPT consecutive codes at ((u * kDecThreads) + t) * CPT, CPT = 16 B / output width.  Every warp-wide load is one
+// contiguous 256 B (128 B) run and every warp-wide store one contiguous 512 B run: whole sectors in both directions
+// (the first version gave each thread 16 codes and two 16 B stores 32 B apart - half-written sectors, 0.70 of HBM).
+// All kDecUnroll loads are issued before the first lookup so each thread keeps 4 independent requests in flight.
 constexpr int kDecThreads = 512;
+constexpr int kDecUnroll = 4;
 
 template <int KIND>
 __global__ void __launch_bounds__(kDecThreads) g711_decode_kernel(const uint8_t* __restrict__ in, void* __restrict__ outv,
@@ -70,33 +76,44 @@ __global__ void __launch_bounds__(kDecThreads) g711_decode_kernel(const uint8_t*
     for (int i = threadIdx.x; i < 256 * 32; i += kDecThreads) lut[i] = g711_dec_word(law, KIND, (uint32_t)i >> 5);
     __syncthreads();
     const uint32_t* my = lut + (threadIdx.x & 31);
-    const size_t nvec = n / 16;  // 16 codes per 128-bit load
-    const uint4* in4 = reinterpret_cast<const uint4*>(in);
-    const size_t stride = (size_t)gridDim.x * kDecThreads;
-    for (size_t v = (size_t)blockIdx.x * kDecThreads + threadIdx.x; v < nvec; v += stride) {
-        uint4 c = ld_stream_v4(in4 + v);
-        uint32_t w[4] = {c.x, c.y, c.z, c.w};
-        uint32_t o[16];
+    constexpr int CPT = KIND == SK_KIND_I16 ? 8 : 4;   // codes per thread per sub-iteration (one 16 B store)
+    constexpr int NW = CPT / 4;                         // 32-bit words of codes per thread
+    const size_t nvec = n / CPT;
+    const uint32_t* inw = reinterpret_cast<const uint32_t*>(in);
+    uint4* out4 = reinterpret_cast<uint4*>(outv);
+    const size_t tile = (size_t)kDecThreads * kDecUnroll;
+    for (size_t base = (size_t)blockIdx.x * tile; base < nvec; base += (size_t)gridDim.x * tile) {
+        uint32_t w[kDecUnroll][NW];
 #pragma unroll
-        for (int q = 0; q < 4; q++)
+        for (int u = 0; u < kDecUnroll; u++) {
+            size_t v = base + (size_t)u * kDecThreads + threadIdx.x;
+            if (v < nvec) {
+                if (NW == 2) { uint2 c = ld_stream_v2(inw + v * 2); w[u][0] = c.x; w[u][NW - 1] = c.y; }
+                else w[u][0] = ld_stream_u32(inw + v);
+            }
+        }
 #pragma unroll
-            for (int k = 0; k < 4; k++) o[q * 4 + k] = my[((w[q] >> (8 * k)) & 0xff) << 5];
-        if (KIND == SK_KIND_I16) {
-            uint4* out4 = reinterpret_cast<uint4*>(outv) + v * 2;
-            uint4 a, b;
-            a.x = o[0] | (o[1] << 16);   a.y = o[2] | (o[3] << 16);   a.z = o[4] | (o[5] << 16);   a.w = o[6] | (o[7] << 16);
-            b.x = o[8] | (o[9] << 16);   b.y = o[10] | (o[11] << 16); b.z = o[12] | (o[13] << 16); b.w = o[14] | (o[15] << 16);
-            st_stream_v4(out4, a);
-            st_stream_v4(out4 + 1, b);
-        } else {
-            uint4* out4 = reinterpret_cast<uint4*>(outv) + v * 4;
+        for (int u = 0; u < kDecUnroll; u++) {
+            size_t v = base + (size_t)u * kDecThreads + threadIdx.x;
+            if (v >= nvec) break;
+            uint32_t o[CPT];
 #pragma unroll
-            for (int q = 0; q < 4; q++) st_stream_v4(out4 + q, make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+            for (int q = 0; q < NW; q++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) o[q * 4 + k] = my[((w[u][q] >> (8 * k)) & 0xff) << 5];
+            uint4 r;
+            if (KIND == SK_KIND_I16) {
+                r.x = __byte_perm(o[0], o[1], 0x5410); r.y = __byte_perm(o[2], o[3], 0x5410);
+                r.z = __byte_perm(o[4 % CPT], o[5 % CPT], 0x5410); r.w = __byte_perm(o[6 % CPT], o[7 % CPT], 0x5410);
+            } else {
+                r = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            st_stream_v4(out4 + v, r);
         }
     }
-    // tail (< 16 codes): one thread per sample
+    // tail (< CPT codes): one thread per sample
     if (blockIdx.x == 0) {
-        for (size_t i = nvec * 16 + threadIdx.x; i < n; i += kDecThreads) {
+        for (size_t i = nvec * CPT + threadIdx.x; i < n; i += kDecThreads) {
             uint32_t wv = my[(uint32_t)in[i] << 5];
             if (KIND == SK_KIND_I16) reinterpret_cast<uint16_t*>(outv)[i] = (uint16_t)wv;
             else reinterpret_cast<uint32_t*>(outv)[i] = wv;
@@ -114,53 +131,86 @@ __global__ void g711_decode_scalar_kernel(const uint8_t* __restrict__ in, void* 
 }
 
 // ---- encode ------------------------------------------------------------------------------------
-constexpr int kEncThreads = 512;
+// Table-free: the segment search of lib.rs:317-322 is the exponent of the (biased) magnitude, and the 4 mantissa
+// bits it keeps are the top 4 fraction bits, so one int->float conversion yields `(seg << 4) | mantissa` as bits
+// [19, 27) of the float once the value is scaled so that segment 0 has the right exponent:
+//   mu-law (lib.rs:235-254): p = min(|s| + 0x84, 32635) in [132, 32635]; p * 2^-133 has exponent field seg + 1
+//           -> enc = (bits >> 19) - 16, out = enc ^ (s < 0 ? 0x7f : 0xff) = (0x10f - (bits >> 19)) ^ (neg << 7)
+//   A-law  (lib.rs:271-294): p = s >= 0 ? s : -s - 1 = |s + 0.5| - 0.5; segments 0 and 1 share one linear step, which is
+//           exactly an IEEE subnormal: p * 2^-134 has exponent field seg (0 for p < 256) -> enc = bits >> 19,
+//           out = enc ^ (s >= 0 ? 0xd5 : 0x55)
+// Every float operation is exact (integers < 2^16 scaled by powers of two), so the result is the reference's
+// integer arithmetic bit for bit (checked over all 65 536 inputs in tests).  A 64 KiB shared-memory table of the
+// same function ran at 0.51 of HBM (random 16-bit indices: ~3.5-way bank conflicts); this form is 7 issue slots
+// per sample and streams.
+constexpr int kEncThreads = 256;
+constexpr int kEncUnroll = 4;
 
-__global__ void g711_build_enc_table_kernel(uint8_t* table, int law) {  // 65536 entries, index = (u16)sample
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 65536) {
-        int s = (int)(int16_t)(uint16_t)i;
-        table[i] = (uint8_t)(law == SK_LAW_MULAW ? g711_enc_mulaw(s) : g711_enc_alaw(s));
+template <int LAW>
+__device__ __forceinline__ uint32_t g711_enc_fast(float f) {  // f = (float)sample; returns enc + 16 (mu) / enc (A), in [0, 0x8f]
+    if (LAW == SK_LAW_MULAW) {
+        float p = fminf(__fmaf_rn(fabsf(f), 0x1p-133f, 132.0f * 0x1p-133f), 32635.0f * 0x1p-133f);
+        return __float_as_uint(p) >> 19;
+    } else {
+        float g = __fadd_rn(f, 0.5f);
+        float p = __fmaf_rn(fabsf(g), 0x1p-134f, -0x1p-135f);
+        return __float_as_uint(p) >> 19;
     }
 }
 
-template <int KIND>  // SK_KIND_I16: 8 samples / 16 B; SK_KIND_I32: 4 samples / 16 B, (s >> 16) as i16 (:133-135)
-__global__ void __launch_bounds__(kEncThreads) g711_encode_kernel(const void* __restrict__ inv, uint8_t* __restrict__ out, size_t n,
-                                                                   const uint8_t* __restrict__ table) {
-    extern __shared__ __align__(16) uint8_t lut[];  // 65536 bytes
-    {
-        const uint4* t4 = reinterpret_cast<const uint4*>(table);
-        uint4* l4 = reinterpret_cast<uint4*>(lut);
-        for (int i = threadIdx.x; i < 4096; i += kEncThreads) l4[i] = t4[i];
+// 4 samples held as two packed i16 pairs (KIND i16) or four i32 words whose high halves are the samples (KIND i32)
+template <int LAW, int KIND>
+__device__ __forceinline__ uint32_t g711_enc4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    float f0, f1, f2, f3;
+    uint32_t signs;  // byte k = high byte of sample k (bit 7 = sign)
+    if (KIND == SK_KIND_I16) {
+        f0 = (float)(int16_t)(a & 0xffff); f1 = (float)(int16_t)(a >> 16);
+        f2 = (float)(int16_t)(b & 0xffff); f3 = (float)(int16_t)(b >> 16);
+        signs = __byte_perm(a, b, 0x7531);
+    } else {
+        f0 = (float)(int16_t)(a >> 16); f1 = (float)(int16_t)(b >> 16);
+        f2 = (float)(int16_t)(c >> 16); f3 = (float)(int16_t)(d >> 16);
+        signs = __byte_perm(__byte_perm(a, b, 0x7773), __byte_perm(c, d, 0x7773), 0x5410);
     }
-    __syncthreads();
+    uint32_t e0 = g711_enc_fast<LAW>(f0), e1 = g711_enc_fast<LAW>(f1), e2 = g711_enc_fast<LAW>(f2), e3 = g711_enc_fast<LAW>(f3);
+    uint32_t packed = __byte_perm(__byte_perm(e0, e1, 0x0040), __byte_perm(e2, e3, 0x0040), 0x5410);
+    // mu: bytes hold enc + 16 >= 16, so one packed subtract removes the bias without borrows; then ^ 0xff ^ (neg << 7)
+    // A : ^ 0x55 ^ (!neg << 7) = ^ 0xd5 ^ (neg << 7)
+    if (LAW == SK_LAW_MULAW) packed = ~(packed - 0x10101010u);
+    else packed ^= 0xd5d5d5d5u;
+    return packed ^ (signs & 0x80808080u);
+}
+
+template <int LAW, int KIND>  // SK_KIND_I16: 8 samples / 16 B; SK_KIND_I32: 4 samples / 16 B, (s >> 16) as i16 (:133-135)
+__global__ void __launch_bounds__(kEncThreads) g711_encode_kernel(const void* __restrict__ inv, uint8_t* __restrict__ out, size_t n) {
     constexpr int SPV = KIND == SK_KIND_I16 ? 8 : 4;  // samples per 128-bit load
     const size_t nvec = n / SPV;
     const uint4* in4 = reinterpret_cast<const uint4*>(inv);
-    const size_t stride = (size_t)gridDim.x * kEncThreads;
-    for (size_t v = (size_t)blockIdx.x * kEncThreads + threadIdx.x; v < nvec; v += stride) {
-        uint4 c = ld_stream_v4(in4 + v);
-        uint32_t w[4] = {c.x, c.y, c.z, c.w};
-        if (KIND == SK_KIND_I16) {
-            uint32_t o[2];
+    const size_t tile = (size_t)kEncThreads * kEncUnroll;
+    for (size_t base = (size_t)blockIdx.x * tile; base < nvec; base += (size_t)gridDim.x * tile) {
+        uint4 c[kEncUnroll];
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                uint32_t a = lut[w[2 * h] & 0xffff], b = lut[w[2 * h] >> 16];
-                uint32_t c2 = lut[w[2 * h + 1] & 0xffff], d = lut[w[2 * h + 1] >> 16];
-                o[h] = a | (b << 8) | (c2 << 16) | (d << 24);
+        for (int u = 0; u < kEncUnroll; u++) {
+            size_t v = base + (size_t)u * kEncThreads + threadIdx.x;
+            if (v < nvec) c[u] = ld_stream_v4_nv(in4 + v);
+        }
+#pragma unroll
+        for (int u = 0; u < kEncUnroll; u++) {
+            size_t v = base + (size_t)u * kEncThreads + threadIdx.x;
+            if (v >= nvec) break;
+            if (KIND == SK_KIND_I16) {
+                uint32_t lo = g711_enc4<LAW, KIND>(c[u].x, c[u].y, 0, 0), hi = g711_enc4<LAW, KIND>(c[u].z, c[u].w, 0, 0);
+                st_stream_v2(reinterpret_cast<uint2*>(out) + v, make_uint2(lo, hi));
+            } else {
+                st_stream_u32(reinterpret_cast<uint32_t*>(out) + v, g711_enc4<LAW, KIND>(c[u].x, c[u].y, c[u].z, c[u].w));
             }
-            st_stream_v2(reinterpret_cast<uint2*>(out) + v, make_uint2(o[0], o[1]));
-        } else {
-            uint32_t o = lut[w[0] >> 16] | ((uint32_t)lut[w[1] >> 16] << 8) | ((uint32_t)lut[w[2] >> 16] << 16) |
-                         ((uint32_t)lut[w[3] >> 16] << 24);
-            reinterpret_cast<uint32_t*>(out)[v] = o;
         }
     }
     if (blockIdx.x == 0) {
         for (size_t i = nvec * SPV + threadIdx.x; i < n; i += kEncThreads) {
-            uint32_t idx = KIND == SK_KIND_I16 ? (uint32_t)reinterpret_cast<const uint16_t*>(inv)[i]
-                                               : (reinterpret_cast<const uint32_t*>(inv)[i] >> 16);
-            out[i] = lut[idx];
+            int s = KIND == SK_KIND_I16 ? (int)reinterpret_cast<const int16_t*>(inv)[i]
+                                        : (int)(int16_t)(reinterpret_cast<const uint32_t*>(inv)[i] >> 16);
+            out[i] = (uint8_t)(LAW == SK_LAW_MULAW ? g711_enc_mulaw(s) : g711_enc_alaw(s));
         }
     }
 }
@@ -195,18 +245,11 @@ extern "C" int sk_g711_decode_dev(sk_ctx* ctx, int law, const uint8_t* in, size_
         SK_LAUNCH_CHECK(ctx);
         return SK_OK;
     }
-    int grid = grid_for(ctx, n / 16, kDecThreads, 4);
+    const size_t nvec = n / (out_kind == SK_KIND_I16 ? 8 : 4);
+    int grid = grid_for(ctx, (nvec + kDecUnroll - 1) / kDecUnroll, kDecThreads, 4);
     if (out_kind == SK_KIND_I16) g711_decode_kernel<SK_KIND_I16><<<grid, kDecThreads, 0, ctx->stream>>>(in, out, n, law);
     else if (out_kind == SK_KIND_I32) g711_decode_kernel<SK_KIND_I32><<<grid, kDecThreads, 0, ctx->stream>>>(in, out, n, law);
     else g711_decode_kernel<SK_KIND_F32><<<grid, kDecThreads, 0, ctx->stream>>>(in, out, n, law);
-    SK_LAUNCH_CHECK(ctx);
-    return SK_OK;
-}
-
-static int ensure_enc_table(sk_ctx* ctx, int law) {
-    if (ctx->d_g711_enc[law]) return SK_OK;
-    SK_CUDA(ctx, cudaMalloc((void**)&ctx->d_g711_enc[law], 65536));
-    g711_build_enc_table_kernel<<<256, 256, 0, ctx->stream>>>(ctx->d_g711_enc[law], law);
     SK_LAUNCH_CHECK(ctx);
     return SK_OK;
 }
@@ -223,17 +266,14 @@ extern "C" int sk_g711_encode_dev(sk_ctx* ctx, int law, int in_kind, const void*
         SK_LAUNCH_CHECK(ctx);
         return SK_OK;
     }
-    int rc = ensure_enc_table(ctx, law);
-    if (rc) return rc;
-    // the attribute is per device; setting it is cheap enough to do on every call
-    SK_CUDA(ctx, cudaFuncSetAttribute(g711_encode_kernel<SK_KIND_I16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    SK_CUDA(ctx, cudaFuncSetAttribute(g711_encode_kernel<SK_KIND_I32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    if (in_kind == SK_KIND_I16) {
-        int grid = grid_for(ctx, n / 8, kEncThreads, 3);
-        g711_encode_kernel<SK_KIND_I16><<<grid, kEncThreads, 65536, ctx->stream>>>(in, out, n, ctx->d_g711_enc[law]);
+    const size_t nvec = n / (in_kind == SK_KIND_I16 ? 8 : 4);
+    int grid = grid_for(ctx, (nvec + kEncUnroll - 1) / kEncUnroll, kEncThreads, 8);
+    if (law == SK_LAW_MULAW) {
+        if (in_kind == SK_KIND_I16) g711_encode_kernel<SK_LAW_MULAW, SK_KIND_I16><<<grid, kEncThreads, 0, ctx->stream>>>(in, out, n);
+        else g711_encode_kernel<SK_LAW_MULAW, SK_KIND_I32><<<grid, kEncThreads, 0, ctx->stream>>>(in, out, n);
     } else {
-        int grid = grid_for(ctx, n / 4, kEncThreads, 3);
-        g711_encode_kernel<SK_KIND_I32><<<grid, kEncThreads, 65536, ctx->stream>>>(in, out, n, ctx->d_g711_enc[law]);
+        if (in_kind == SK_KIND_I16) g711_encode_kernel<SK_LAW_ALAW, SK_KIND_I16><<<grid, kEncThreads, 0, ctx->stream>>>(in, out, n);
+        else g711_encode_kernel<SK_LAW_ALAW, SK_KIND_I32><<<grid, kEncThreads, 0, ctx->stream>>>(in, out, n);
     }
     SK_LAUNCH_CHECK(ctx);
     return SK_OK;
