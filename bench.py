@@ -251,11 +251,15 @@ def run_ours(args):
     ctx = capi.Context(local)
     ctx.use_torch_stream()
 
-    S, frames = args.streams, int(args.seconds * IN_RATE)
+    from soundkit_b200 import shard
+    # weak scaling: the job is a batch of streams_per_gpu x world streams; rank g owns the contiguous range
+    # [g*S/G, (g+1)*S/G) of it and nothing crosses NVLink on the data path
+    lo, hi = shard.stream_range(args.streams * world, world, rank)
+    S, frames = hi - lo, int(args.seconds * IN_RATE)
     n_out = ctx.batch_plan(IN_RATE, OUT_RATE, frames, capi.SEM_STREAMING)
     stride = frames * CHANNELS * 3
     stride = (stride + 15) // 16 * 16
-    g = torch.Generator(device="cuda"); g.manual_seed(0x5EED0000 + rank)
+    g = torch.Generator(device="cuda"); g.manual_seed(shard.stream_seed(0x5EED0000, 4, lo))
     raw = torch.randint(0, 256, (S, stride), dtype=torch.uint8, device="cuda", generator=g)
     n_pad = (n_out + 3) // 4 * 4
     out = torch.empty((S, n_pad), dtype=torch.float32, device="cuda")
@@ -285,10 +289,7 @@ def run_ours(args):
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     clocks = sampler.stop()
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    total_ms_max = shard.max_over_ranks(total_ms, dist, "cuda")
     frames_all = float(S) * n_out * world * args.steps
     value = frames_all / (total_ms_max * 1e-3) / 1e6
 
@@ -306,10 +307,7 @@ def run_ours(args):
         ctx.normalize_batch_host(hdesc)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    e2e_s = shard.max_over_ranks(e2e_s, dist, "cuda")
     e2e_val = float(S) * n_out * world * e2e_steps / e2e_s / 1e6
     same = bool(torch.equal(h_out[:, :n_out], out[:, :n_out].cpu()))
 

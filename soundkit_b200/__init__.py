@@ -3,8 +3,9 @@
 Layout:
   csrc/       hand-written CUDA kernels + the C ABI (include/soundkit_cuda.h) -> libsoundkit_cuda.so
   capi.py     ctypes binding of that ABI (what tests and bench.py call)
-  host.py     host-side mirror of the reference's Rust interface for this path (same names, argument
-              meaning and error strings), on top of the C ABI
+  csrc/host/  C++ host-side mirror of the reference's Rust interface for this path (same names, argument
+              meaning and error strings) on top of the C ABI; `_host` is its pybind11 view for pytest
+  shard.py    multi-GPU partition of a batch of independent streams (no data-path collective)
 
 There is no CPU fallback anywhere in this package.
 """
