@@ -219,6 +219,16 @@ def extras(ctx, torch, peaks, only=None):
             res[f"convert_{name}_stereo_to_planar_f32"] = hbm_entry(nb, t, S * frames * 2)
             del raw
         del out
+    if want("norm48k"):
+        # StreamingStereo48kNormalizer, 64 whole streams x 60 s s16le stereo 44.1 kHz -> f32 stereo 48 kHz
+        S, frames, rate = 64, 2646000, 44100
+        raw = torch.randint(0, 256, (S, frames * 4), dtype=torch.uint8, device="cuda")
+        n_out = ctx.normalize48k_out_frames(frames, rate)
+        plane = (n_out + 3) // 4 * 4
+        o = torch.empty((S, 2, plane), dtype=torch.float32, device="cuda")
+        t = timed(lambda: ctx.normalize48k_batch_dev(raw, raw.stride(0), S, frames, 16, 0, False, 2, rate, o, 2 * plane, plane))
+        res["normalizer48k_s16le_stereo_44k1"] = hbm_entry(S * (frames * 4 + n_out * 8), t, S * n_out * 2)
+        del raw, o
     if want("resample"):
         # non-integer ratio 44.1k -> 48k stereo f32 (BASELINE configs[3] wave), one-shot semantics
         S, frames = 16, 2646000

@@ -224,6 +224,32 @@ int sk_normalize_stream(sk_ctx*, const uint8_t* in, size_t bytes, int bits, int 
                         int channels, int scale_mode, uint32_t in_rate, uint32_t out_rate, int semantics,
                         int mix_mode, float* out, size_t out_cap_per_plane, size_t* n_out);
 
+/* ------------------------------------------------------------------ 48 kHz stereo normalizer */
+/* StreamingStereo48kNormalizer (soundkit/src/audio_pipeline.rs:256-394): decoder-convention conversion, mono
+ * duplicated / first two channels, finite_pcm clamp, 2-tap linear interpolation to 48 kHz over the whole-stream
+ * timeline, exact rounded-duration tail.  Stateful, one per stream; the reference's error strings are produced by the
+ * host layer, this layer reports SK_E_ARG / SK_E_STATE with the same text in sk_last_error(). */
+typedef struct sk_norm48k sk_norm48k;
+int      sk_norm48k_create(sk_ctx*, sk_norm48k** out);
+void     sk_norm48k_destroy(sk_norm48k*);
+/* push(&AudioData) (:288-363): writes *n_out frames to left/right (0 = Ok(None)); cap >= sk_norm48k_max_output() */
+int      sk_norm48k_push(sk_norm48k*, const uint8_t* data, size_t bytes, int bits, int fmt, int big_endian, int channels,
+                         uint32_t rate, float* left, float* right, size_t cap, size_t* n_out);
+/* finish() (:366-394): the repeated-final-sample tail */
+int      sk_norm48k_finish(sk_norm48k*, float* left, float* right, size_t cap, size_t* n_out);
+uint64_t sk_norm48k_source_frames(const sk_norm48k*);      /* :280 */
+uint64_t sk_norm48k_output_frames(const sk_norm48k*);      /* :284 */
+uint32_t sk_norm48k_source_sample_rate(const sk_norm48k*); /* :272 */
+int      sk_norm48k_source_channels(const sk_norm48k*);    /* :276 */
+size_t   sk_norm48k_max_output(size_t frames, uint32_t rate); /* (frames * 48000).div_ceil(rate) + 4, :318-320 */
+/* whole streams, batched and device resident: push(whole) + finish() for n_streams equal-length streams in one
+ * launch.  out[s][0][n] = left, out[s][1][n] = right (out_stride floats between streams, out_stride_ch between the
+ * two planes); *n_out = sk_normalize48k_out_frames(frames, rate). */
+size_t   sk_normalize48k_out_frames(size_t frames, uint32_t rate);
+int      sk_normalize48k_batch_dev(sk_ctx*, const void* in, size_t in_stride, size_t n_streams, size_t frames, int bits,
+                                   int fmt, int big_endian, int channels, uint32_t rate, float* out, size_t out_stride,
+                                   size_t out_stride_ch, size_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

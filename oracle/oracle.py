@@ -104,6 +104,18 @@ def _proto(L):
                                      C.POINTER(C.c_size_t)]
     L.sko_stream_flush.restype = C.c_int
     L.sko_stream_flush.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.sko_norm48k_new.restype = C.c_void_p
+    L.sko_norm48k_free.restype = None
+    L.sko_norm48k_free.argtypes = [C.c_void_p]
+    L.sko_norm48k_source_frames.restype = C.c_uint64
+    L.sko_norm48k_source_frames.argtypes = [C.c_void_p]
+    L.sko_norm48k_output_frames.restype = C.c_uint64
+    L.sko_norm48k_output_frames.argtypes = [C.c_void_p]
+    L.sko_norm48k_push.restype = C.c_int
+    L.sko_norm48k_push.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p,
+                                   C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.sko_norm48k_finish.restype = C.c_int
+    L.sko_norm48k_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.sko_normalize_chain_mono.restype = C.c_size_t
     L.sko_normalize_chain_mono.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_uint32,
                                            C.c_uint32, C.c_void_p, C.c_size_t]
@@ -334,3 +346,53 @@ def normalize_chain_mono(data, bits, fmt, big_endian, channels, in_rate, out_rat
     n = lib().sko_normalize_chain_mono(_ptr(d), d.size, bits, fmt, int(big_endian), channels, in_rate, out_rate,
                                        _ptr(out), cap)
     return None if n == ERR else out[:n].copy()
+
+
+class Normalizer48k:
+    """StreamingStereo48kNormalizer restatement (soundkit/src/audio_pipeline.rs:256-394).  push/finish return
+    (left, right) float32 arrays (empty = Ok(None)) or raise ValueError(code) for the reference's Err arms."""
+
+    def __init__(self):
+        self.h = lib().sko_norm48k_new()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().sko_norm48k_free(self.h)
+            self.h = None
+
+    def source_frames(self):
+        return lib().sko_norm48k_source_frames(self.h)
+
+    def output_frames(self):
+        return lib().sko_norm48k_output_frames(self.h)
+
+    def push(self, data, bits, fmt, big_endian, channels, rate):
+        d = _bytes(data)
+        frames = d.size // max(1, (bits // 8) * max(channels, 1))
+        cap = frames * 48000 // max(rate, 1) + 8 if rate != 48000 else frames + 1
+        l, r = np.empty(cap, np.float32), np.empty(cap, np.float32)
+        n = C.c_size_t(0)
+        rc = lib().sko_norm48k_push(self.h, _ptr(d), d.size, bits, fmt, int(big_endian), channels, rate, _ptr(l), _ptr(r), cap, C.byref(n))
+        if rc:
+            raise ValueError(rc)
+        return l[:n.value].copy(), r[:n.value].copy()
+
+    def finish(self, cap=1 << 16):
+        l, r = np.empty(cap, np.float32), np.empty(cap, np.float32)
+        n = C.c_size_t(0)
+        rc = lib().sko_norm48k_finish(self.h, _ptr(l), _ptr(r), cap, C.byref(n))
+        if rc:
+            raise ValueError(rc)
+        return l[:n.value].copy(), r[:n.value].copy()
+
+
+def normalize48k(blocks):
+    """normalize_blocks of the reference tests (audio_pipeline.rs:781-795): blocks = [(data, bits, fmt, be, channels, rate)]"""
+    nz = Normalizer48k()
+    ls, rs = [], []
+    for b in blocks:
+        l, r = nz.push(*b)
+        ls.append(l); rs.append(r)
+    l, r = nz.finish()
+    ls.append(l); rs.append(r)
+    return np.concatenate(ls), np.concatenate(rs)

@@ -147,6 +147,16 @@ size_t sko_normalize_chain_mono(const uint8_t* in, size_t bytes, int bits, int f
                                 size_t channels, uint32_t in_rate, uint32_t out_rate, float* out,
                                 size_t out_cap);
 
+/* ---- 8(f) next row 2: StreamingStereo48kNormalizer (soundkit/src/audio_pipeline.rs:133-413), norm48k.c ---- */
+typedef struct sko_norm48k sko_norm48k;
+sko_norm48k* sko_norm48k_new(void);
+void sko_norm48k_free(sko_norm48k*);
+uint64_t sko_norm48k_source_frames(const sko_norm48k*);
+uint64_t sko_norm48k_output_frames(const sko_norm48k*);
+int sko_norm48k_push(sko_norm48k*, const uint8_t* data, size_t bytes, int bits, int fmt, int be, int channels, uint32_t rate,
+                     float* left, float* right, size_t cap, size_t* n_out);
+int sko_norm48k_finish(sko_norm48k*, float* left, float* right, size_t cap, size_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,9 @@ EXPORTS = (
     "sk_resampler_create", "sk_resampler_destroy", "sk_resampler_out_max", "sk_resampler_last_index",
     "sk_resampler_process", "sk_resampler_process_partial", "sk_resampler_copy_table",
     "sk_normalize_batch_plan", "sk_normalize_batch_dev", "sk_normalize_batch", "sk_normalize_stream",
+    "sk_norm48k_create", "sk_norm48k_destroy", "sk_norm48k_push", "sk_norm48k_finish", "sk_norm48k_source_frames",
+    "sk_norm48k_output_frames", "sk_norm48k_source_sample_rate", "sk_norm48k_source_channels", "sk_norm48k_max_output",
+    "sk_normalize48k_out_frames", "sk_normalize48k_batch_dev",
 )
 
 
@@ -112,6 +115,17 @@ def load():
         "sk_normalize_batch_dev": (i, [vp, C.POINTER(BatchDesc)]),
         "sk_normalize_batch": (i, [vp, C.POINTER(BatchDesc)]),
         "sk_normalize_stream": (i, [vp, vp, sz, i, i, i, i, i, u32, u32, i, i, vp, sz, psz]),
+        "sk_norm48k_create": (i, [vp, C.POINTER(vp)]),
+        "sk_norm48k_destroy": (None, [vp]),
+        "sk_norm48k_push": (i, [vp, vp, sz, i, i, i, i, u32, vp, vp, sz, psz]),
+        "sk_norm48k_finish": (i, [vp, vp, vp, sz, psz]),
+        "sk_norm48k_source_frames": (C.c_uint64, [vp]),
+        "sk_norm48k_output_frames": (C.c_uint64, [vp]),
+        "sk_norm48k_source_sample_rate": (u32, [vp]),
+        "sk_norm48k_source_channels": (i, [vp]),
+        "sk_norm48k_max_output": (sz, [sz, u32]),
+        "sk_normalize48k_out_frames": (sz, [sz, u32]),
+        "sk_normalize48k_batch_dev": (i, [vp, vp, sz, sz, sz, i, i, i, i, u32, vp, sz, sz, psz]),
     }
     for name in EXPORTS:
         fn = getattr(L, name)  # AttributeError if the header and the library disagree
@@ -320,6 +334,63 @@ class Context:
 
     def resampler(self, in_rate, out_rate, channels, chunk):
         return Resampler(self, in_rate, out_rate, channels, chunk)
+
+    # -- 48 kHz stereo normalizer (StreamingStereo48kNormalizer)
+    def normalizer48k(self):
+        return Normalizer48k(self)
+
+    def normalize48k_out_frames(self, frames, rate):
+        return self.L.sk_normalize48k_out_frames(frames, rate)
+
+    def normalize48k_batch_dev(self, d_in, in_stride, n_streams, frames, bits, fmt, big_endian, channels, rate, d_out, out_stride,
+                               out_stride_ch):
+        n = C.c_size_t()
+        self._ck(self.L.sk_normalize48k_batch_dev(self.h, _p(d_in), in_stride, n_streams, frames, bits, fmt, int(big_endian), channels,
+                                                  rate, _p(d_out), out_stride, out_stride_ch, C.byref(n)))
+        return n.value
+
+
+class Normalizer48k:
+    """sk_norm48k: soundkit's StreamingStereo48kNormalizer, arithmetic on the device."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx._ck(ctx.L.sk_norm48k_create(ctx.h, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.L.sk_norm48k_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def source_frames(self):
+        return self.ctx.L.sk_norm48k_source_frames(self.h)
+
+    def output_frames(self):
+        return self.ctx.L.sk_norm48k_output_frames(self.h)
+
+    def push(self, data, bits, fmt, big_endian, channels, rate):
+        d = _u8(data)
+        frames = d.size // max(1, (bits // 8) * max(channels, 1))
+        cap = max(1, self.ctx.L.sk_norm48k_max_output(frames, rate))
+        l, r = np.empty(cap, np.float32), np.empty(cap, np.float32)
+        n = C.c_size_t()
+        self.ctx._ck(self.ctx.L.sk_norm48k_push(self.h, _p(d), d.size, bits, fmt, int(big_endian), channels, rate, _p(l), _p(r), cap,
+                                                C.byref(n)))
+        return l[:n.value], r[:n.value]
+
+    def finish(self, cap=1 << 16):
+        l, r = np.empty(cap, np.float32), np.empty(cap, np.float32)
+        n = C.c_size_t()
+        self.ctx._ck(self.ctx.L.sk_norm48k_finish(self.h, _p(l), _p(r), cap, C.byref(n)))
+        return l[:n.value], r[:n.value]
 
 
 class Resampler:

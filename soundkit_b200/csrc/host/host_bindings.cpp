@@ -92,6 +92,24 @@ PYBIND11_MODULE(_host, m) {
     ap.def("f32s_from_le_bytes", [](const py::buffer& b) { return arr(audio_pipeline::f32s_from_le_bytes(to_bytes(b))); });
     ap.def("downsample_audio", [](const AudioData& a, size_t rate) { return arrs(audio_pipeline::downsample_audio(a, rate)); });
 
+    py::class_<audio_pipeline::StreamingStereo48kNormalizer>(ap, "StreamingStereo48kNormalizer")
+        .def(py::init<>())
+        .def("source_sample_rate", &audio_pipeline::StreamingStereo48kNormalizer::source_sample_rate)
+        .def("source_channels", &audio_pipeline::StreamingStereo48kNormalizer::source_channels)
+        .def("source_frames", &audio_pipeline::StreamingStereo48kNormalizer::source_frames)
+        .def("output_frames", &audio_pipeline::StreamingStereo48kNormalizer::output_frames)
+        // Option<Stereo48kBlock> -> None | (left, right)
+        .def("push", [](audio_pipeline::StreamingStereo48kNormalizer& n, const AudioData& a) -> py::object {
+            auto b = n.push(a);
+            if (!b) return py::none();
+            return py::make_tuple(arr(b->left), arr(b->right));
+        })
+        .def("finish", [](audio_pipeline::StreamingStereo48kNormalizer& n) -> py::object {
+            auto b = n.finish();
+            if (!b) return py::none();
+            return py::make_tuple(arr(b->left), arr(b->right));
+        });
+
     // ---- raw_pcm
     auto rp = m.def_submodule("raw_pcm");
     rp.attr("MAX_INPUT_CHUNK_BYTES") = raw_pcm::MAX_INPUT_CHUNK_BYTES;

@@ -314,6 +314,71 @@ inline std::vector<std::vector<float>> downsample_audio(const AudioData& audio, 
     for (size_t c = 0; c < ch; c++) out[c].assign(flat.begin() + c * (n ? n : 1), flat.begin() + c * (n ? n : 1) + got);
     return out;
 }
+// ---- StreamingStereo48kNormalizer (soundkit/src/audio_pipeline.rs:229-394) ---------------------------------
+struct Stereo48kBlock {  // :234-248
+    std::vector<float> left, right;
+    size_t frame_count() const { return left.size(); }
+    bool is_empty() const { return left.empty(); }
+};
+class StreamingStereo48kNormalizer {  // :256-394; conversion + interpolation run on the device (sk_norm48k)
+public:
+    StreamingStereo48kNormalizer() {
+        sk_norm48k* h = nullptr;
+        Gpu::check(sk_norm48k_create(Gpu::ctx(), &h));
+        h_.reset(h, sk_norm48k_destroy);
+    }
+    uint32_t source_sample_rate() const { return source_sample_rate_; }
+    uint8_t source_channels() const { return source_channels_; }
+    uint64_t source_frames() const { return sk_norm48k_source_frames(h_.get()); }
+    uint64_t output_frames() const { return sk_norm48k_output_frames(h_.get()); }
+
+    std::optional<Stereo48kBlock> push(const AudioData& audio) {  // :288
+        if (finished_) throw Error("48 kHz stereo normalizer is already finished");
+        const uint32_t sample_rate = audio.sampling_rate();
+        const uint8_t channel_count = audio.channel_count();
+        if (sample_rate == 0 || channel_count == 0) throw Error("decoded audio has invalid PCM geometry");
+        if (source_sample_rate_ == 0) { source_sample_rate_ = sample_rate; source_channels_ = channel_count; }
+        else if (source_sample_rate_ != sample_rate || source_channels_ != channel_count)
+            throw Error("decoded PCM geometry changed from " + std::to_string(source_sample_rate_) + " Hz/" + std::to_string(source_channels_) +
+                        " ch to " + std::to_string(sample_rate) + " Hz/" + std::to_string(channel_count) + " ch");
+        // audio_to_stereo_f32, :133-174
+        const int bits = audio.bits_per_sample();
+        if (bits != 16 && bits != 24 && bits != 32) throw Error("unsupported PCM bit depth " + std::to_string(bits));
+        const size_t frame_bytes = (size_t)(bits / 8) * channel_count;
+        if (audio.data().empty() || audio.data().size() % frame_bytes) throw Error("decoded audio contained an incomplete PCM frame");
+        const size_t frames = audio.data().size() / frame_bytes;
+        const size_t cap = sk_norm48k_max_output(frames, sample_rate);
+        Stereo48kBlock block;
+        block.left.resize(cap); block.right.resize(cap);
+        size_t n = 0;
+        Gpu::check(sk_norm48k_push(h_.get(), audio.data().data(), audio.data().size(), bits,
+                                   audio.audio_format() == EncodingFlag::PCMFloat ? SK_FMT_FLOAT : SK_FMT_SIGNED,
+                                   audio.endianness() == Endianness::BigEndian, channel_count, sample_rate, block.left.data(), block.right.data(), cap, &n));
+        block.left.resize(n); block.right.resize(n);
+        if (block.is_empty()) return std::nullopt;
+        return block;
+    }
+    std::optional<Stereo48kBlock> finish() {  // :366
+        if (finished_) throw Error("48 kHz stereo normalizer is already finished");
+        finished_ = true;
+        if (source_frames() == 0 || source_sample_rate_ == 0) throw Error("decoded source contained no PCM");
+        if (source_sample_rate_ == 48000) { size_t n = 0; Gpu::check(sk_norm48k_finish(h_.get(), nullptr, nullptr, 0, &n)); return std::nullopt; }
+        // remaining <= round(frames * 48000 / rate) - emitted <= 48000 / rate + 5
+        const size_t cap = (size_t)(48000 / source_sample_rate_) + 8;
+        Stereo48kBlock block;
+        block.left.resize(cap); block.right.resize(cap);
+        size_t n = 0;
+        Gpu::check(sk_norm48k_finish(h_.get(), block.left.data(), block.right.data(), cap, &n));
+        block.left.resize(n); block.right.resize(n);
+        if (block.is_empty()) return std::nullopt;
+        return block;
+    }
+private:
+    std::shared_ptr<sk_norm48k> h_;
+    uint32_t source_sample_rate_ = 0;
+    uint8_t source_channels_ = 0;
+    bool finished_ = false;
+};
 }  // namespace audio_pipeline
 }  // namespace soundkit
 

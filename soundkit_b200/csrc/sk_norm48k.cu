@@ -1,0 +1,287 @@
+// sk_norm48k.cu — SURVEY.md 8(f) row 2: soundkit's StreamingStereo48kNormalizer on the device.
+//
+// Replaces soundkit/src/audio_pipeline.rs:133-413: decoder-convention sample conversion (pcm_sample_to_f32,
+// :176-227), mono duplicated / first two channels (:155-166), finite_pcm (:396-402) and the 2-tap linear
+// interpolation to 48 kHz over the whole-stream timeline (:326-347) with the repeated-final-sample tail (:366-394).
+//
+// Numerics (bit-exact to the reference):
+//   * source_position = output_frames as f64 * f64::from(rate) / 48_000.0 is evaluated per output with the same two
+//     IEEE f64 operations (__dmul_rn, __ddiv_rn); `lower` is its floor, `fraction = (pos - lower) as f32`;
+//   * out = lower + ((upper - lower) * fraction) with separate sub / mul / add (file built with -fmad=false);
+//   * integer samples scale by exact powers of two, finite_pcm is applied to inputs and outputs.
+// HBM bound: per output frame 8 B written + 2 * channels * width * rate / 48000 read.  One thread owns 4 consecutive
+// output frames (two 128-bit stores) and gathers the few source frames they touch through L1; the f64 position
+// arithmetic is done once per thread and reused for every stream of its grid.y slice.
+#include <math.h>
+
+#include <algorithm>
+#include <new>
+
+#include "sk_common.cuh"
+
+struct N48Src {
+    const uint8_t* base;      // first byte of stream 0
+    long long stream_stride;  // bytes between streams
+    int width;                // sample bytes 2 / 3 / 4
+    int channels;
+    int big_endian, is_float;
+    unsigned long long start_frame;  // global index of the buffer's first frame (streaming push)
+    unsigned long long frames;       // frames in the buffer
+};
+
+__device__ __forceinline__ float n48_finite_pcm(float s) {  // audio_pipeline.rs:396-402
+    if ((__float_as_uint(s) & 0x7f800000u) == 0x7f800000u) return 0.0f;
+    return s < -1.0f ? -1.0f : (s > 1.0f ? 1.0f : s);
+}
+
+// sample `ch` of local frame `f` -> f32 (pcm_sample_to_f32, :176-227) -> finite_pcm
+__device__ __forceinline__ float n48_sample(const uint8_t* sbase, const N48Src& s, unsigned long long f, int ch) {
+    const uint8_t* p = sbase + (f * (unsigned long long)s.channels + ch) * (unsigned long long)s.width;
+    float v;
+    if (s.width == 2) {
+        uint32_t u = *reinterpret_cast<const uint16_t*>(p);
+        if (s.big_endian) u = ((u & 0xff) << 8) | (u >> 8);
+        v = __fmul_rn((float)(int16_t)u, 1.0f / 32768.0f);
+    } else if (s.width == 3) {
+        const uint32_t b0 = p[0], b1 = p[1], b2 = p[2];
+        const uint32_t u = s.big_endian ? (b2 | (b1 << 8) | (b0 << 16)) : (b0 | (b1 << 8) | (b2 << 16));
+        v = __fmul_rn((float)(((int32_t)(u << 8)) >> 8), 1.0f / 8388608.0f);
+    } else {
+        uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+        if (s.big_endian) u = bswap32(u);
+        v = s.is_float ? __uint_as_float(u) : __fmul_rn(__int2float_rn((int32_t)u), 4.656612873077393e-10f);
+    }
+    return n48_finite_pcm(v);
+}
+
+constexpr int kN48Threads = 256;
+
+// out_l/out_r: [stream][n_total] planes (out_stride floats between streams).  Outputs [0, n_lerp) are interpolated
+// (global output index o_start + i), outputs [n_lerp, n_total) repeat the stream's final sample (finish()).
+// prev: value of global frame start_frame - 1 (streaming push only; ignored when start_frame == 0).
+// final_lr (optional): [stream][2] <- the last frame of each stream's buffer (the next push's `previous`).
+__global__ void __launch_bounds__(kN48Threads)
+norm48k_kernel(const __grid_constant__ N48Src src, unsigned long long o_start, unsigned long long n_lerp, unsigned long long n_total,
+               unsigned rate, float prev_l, float prev_r, float* __restrict__ out_l, float* __restrict__ out_r, long long out_stride,
+               unsigned n_streams, float* __restrict__ final_lr) {
+    const unsigned long long i0 = ((unsigned long long)blockIdx.x * kN48Threads + threadIdx.x) * 4ull;
+    const bool writes_final = final_lr != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    if (i0 >= n_total && !writes_final) return;
+    const bool need_last = writes_final || i0 + 4 > n_lerp;  // tail outputs repeat the stream's final frame
+    // positions of the (up to) 4 outputs this thread owns: shared by every stream
+    long long lo[4];   // local frame index of `lower` (-1 = the previous push's final frame)
+    float fr[4];
+    const bool passthrough = rate == 48000u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const unsigned long long o = o_start + i0 + k;
+        if (passthrough) { lo[k] = (long long)(o - src.start_frame); fr[k] = 0.0f; continue; }
+        const double pos = __ddiv_rn(__dmul_rn((double)o, (double)rate), 48000.0);
+        const double fl = floor(pos);
+        lo[k] = (long long)((unsigned long long)fl - src.start_frame);  // >= -1 by construction of n_lerp
+        fr[k] = __double2float_rn(__dsub_rn(pos, fl));
+    }
+    const int c1 = src.channels > 1 ? 1 : 0;
+    for (unsigned s = blockIdx.y; s < n_streams; s += gridDim.y) {
+        const uint8_t* sbase = src.base + (long long)s * src.stream_stride;
+        float last_l = prev_l, last_r = prev_r;
+        if (need_last && src.frames) { last_l = n48_sample(sbase, src, src.frames - 1, 0); last_r = n48_sample(sbase, src, src.frames - 1, c1); }
+        if (writes_final) { final_lr[2 * s] = last_l; final_lr[2 * s + 1] = last_r; }
+        if (i0 >= n_total) continue;
+        float ol[4], orr[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (i0 + k >= n_lerp) { ol[k] = last_l; orr[k] = last_r; continue; }  // finish(): vec![previous; remaining]
+            const long long f = lo[k];
+            const float ll = f < 0 ? prev_l : n48_sample(sbase, src, (unsigned long long)f, 0);
+            const float rl = f < 0 ? prev_r : n48_sample(sbase, src, (unsigned long long)f, c1);
+            if (passthrough) { ol[k] = ll; orr[k] = rl; continue; }
+            const float lu = n48_sample(sbase, src, (unsigned long long)(f + 1), 0);
+            const float ru = n48_sample(sbase, src, (unsigned long long)(f + 1), c1);
+            ol[k] = n48_finite_pcm(__fadd_rn(ll, __fmul_rn(__fsub_rn(lu, ll), fr[k])));
+            orr[k] = n48_finite_pcm(__fadd_rn(rl, __fmul_rn(__fsub_rn(ru, rl), fr[k])));
+        }
+        float* pl = out_l + (long long)s * out_stride + i0;
+        float* pr = out_r + (long long)s * out_stride + i0;
+        if (i0 + 4 <= n_total && (((uintptr_t)pl | (uintptr_t)pr) & 15) == 0) {
+            st_stream_v4(pl, make_uint4(__float_as_uint(ol[0]), __float_as_uint(ol[1]), __float_as_uint(ol[2]), __float_as_uint(ol[3])));
+            st_stream_v4(pr, make_uint4(__float_as_uint(orr[0]), __float_as_uint(orr[1]), __float_as_uint(orr[2]), __float_as_uint(orr[3])));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (i0 + k < n_total) { pl[k] = ol[k]; pr[k] = orr[k]; }
+        }
+    }
+}
+
+// ---- host arithmetic of the block / stream lengths (exact integer forms of the reference's f64 expressions) ----
+// outputs a push may emit once `end` source frames are known: every o with floor(o*rate/48000) + 1 < end, i.e.
+// o * rate < (end - 1) * 48000  ->  o < ceil((end - 1) * 48000 / rate).  (o * rate is exact in f64 below 2^53 and the
+// quotient's fractional part is a multiple of 1/48000, far above half an ulp, so floor() of the f64 quotient equals
+// the integer quotient.)
+static unsigned long long n48_lerp_limit(unsigned long long end_frame, unsigned rate) {
+    if (end_frame < 2) return 0;
+    const unsigned __int128 num = (unsigned __int128)(end_frame - 1) * 48000u;
+    return (unsigned long long)((num + rate - 1) / rate);
+}
+// finish(): ((source_frames as f64 * 48000.0) / rate as f64).round().max(1.0) as u64
+static unsigned long long n48_target(unsigned long long frames, unsigned rate) {
+    double t = round(((double)frames * 48000.0) / (double)rate);
+    if (t < 1.0) t = 1.0;
+    return (unsigned long long)t;
+}
+
+extern "C" size_t sk_normalize48k_out_frames(size_t frames, uint32_t rate) {
+    if (!frames || !rate) return 0;
+    if (rate == 48000u) return frames;
+    const unsigned long long a = n48_lerp_limit(frames, rate), b = n48_target(frames, rate);
+    return (size_t)(a > b ? a : b);
+}
+
+static int n48_fill_src(sk_ctx* ctx, N48Src* s, const void* in, size_t in_stride, int bits, int fmt, int big_endian, int channels,
+                        unsigned long long start_frame, unsigned long long frames) {
+    if (bits != 16 && bits != 24 && bits != 32) SK_FAIL(ctx, SK_E_ARG, "unsupported PCM bit depth %d", bits);
+    if (channels <= 0) SK_FAIL(ctx, SK_E_ARG, "decoded audio contained no channels");
+    if (bits != 24 && ((((uintptr_t)in) | in_stride) & (uintptr_t)(bits / 8 - 1))) SK_FAIL(ctx, SK_E_ARG, "input not aligned to the sample width");
+    s->base = (const uint8_t*)in; s->stream_stride = (long long)in_stride;
+    s->width = bits / 8; s->channels = channels; s->big_endian = big_endian != 0;
+    s->is_float = (bits == 32 && fmt == SK_FMT_FLOAT);
+    s->start_frame = start_frame; s->frames = frames;
+    return SK_OK;
+}
+
+static int n48_launch(sk_ctx* ctx, const N48Src& src, unsigned long long o_start, unsigned long long n_lerp, unsigned long long n_total,
+                      unsigned rate, float prev_l, float prev_r, float* out_l, float* out_r, long long out_stride, size_t n_streams,
+                      float* final_lr) {
+    const unsigned long long groups = (n_total + 3) / 4;
+    unsigned long long gx = (groups + kN48Threads - 1) / kN48Threads;
+    if (gx < 1) gx = 1;
+    if (gx > 0x7fffffffull) SK_FAIL(ctx, SK_E_ARG, "stream too long for one launch");
+    // enough CTAs to fill the machine; beyond that, streams are looped inside the thread (position math amortised)
+    unsigned gy = 1;
+    const unsigned long long want = (unsigned long long)ctx->num_sms * 16;
+    if (gx < want) gy = (unsigned)std::min<unsigned long long>(n_streams, (want + gx - 1) / gx);
+    if (gy > 65535u) gy = 65535u;
+    norm48k_kernel<<<dim3((unsigned)gx, gy), kN48Threads, 0, ctx->stream>>>(src, o_start, n_lerp, n_total, rate, prev_l, prev_r, out_l, out_r,
+                                                                           out_stride, (unsigned)n_streams, final_lr);
+    SK_LAUNCH_CHECK(ctx);
+    return SK_OK;
+}
+
+// whole streams, device resident: normalize_blocks(&[whole]) of the reference tests for every stream of a batch
+extern "C" int sk_normalize48k_batch_dev(sk_ctx* ctx, const void* in, size_t in_stride, size_t n_streams, size_t frames, int bits, int fmt,
+                                         int big_endian, int channels, uint32_t rate, float* out, size_t out_stride, size_t out_stride_ch,
+                                         size_t* n_out) {
+    if (!ctx) return SK_E_ARG;
+    if (rate == 0) SK_FAIL(ctx, SK_E_ARG, "decoded audio has invalid PCM geometry");
+    N48Src src;
+    int rc = n48_fill_src(ctx, &src, in, in_stride, bits, fmt, big_endian, channels, 0, frames);
+    if (rc) return rc;
+    const size_t total = sk_normalize48k_out_frames(frames, rate);
+    if (n_out) *n_out = total;
+    if (!total || !n_streams) return SK_OK;
+    if (!in || !out) SK_FAIL(ctx, SK_E_ARG, "null buffer");
+    if (n_streams > 0xffffffffull) SK_FAIL(ctx, SK_E_ARG, "too many streams");
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const unsigned long long n_lerp = rate == 48000u ? frames : n48_lerp_limit(frames, rate);
+    return n48_launch(ctx, src, 0, n_lerp, total, rate, 0.0f, 0.0f, out, out + out_stride_ch, (long long)out_stride, n_streams, nullptr);
+}
+
+// ---- stateful handle: StreamingStereo48kNormalizer (:256-394) -------------------------------------------------
+struct sk_norm48k {
+    sk_ctx* ctx;
+    uint32_t rate = 0; int channels = 0;
+    unsigned long long source_frames = 0, output_frames = 0;
+    float prev_l = 0.0f, prev_r = 0.0f;
+    bool has_previous = false, finished = false;
+};
+
+extern "C" int sk_norm48k_create(sk_ctx* ctx, sk_norm48k** out) {
+    if (!ctx || !out) return SK_E_ARG;
+    sk_norm48k* n = new (std::nothrow) sk_norm48k();
+    if (!n) SK_FAIL(ctx, SK_E_ALLOC, "out of memory");
+    n->ctx = ctx;
+    *out = n;
+    return SK_OK;
+}
+extern "C" void sk_norm48k_destroy(sk_norm48k* n) { delete n; }
+extern "C" uint64_t sk_norm48k_source_frames(const sk_norm48k* n) { return n ? n->source_frames : 0; }
+extern "C" uint64_t sk_norm48k_output_frames(const sk_norm48k* n) { return n ? n->output_frames : 0; }
+extern "C" uint32_t sk_norm48k_source_sample_rate(const sk_norm48k* n) { return n ? n->rate : 0; }
+extern "C" int sk_norm48k_source_channels(const sk_norm48k* n) { return n ? n->channels : 0; }
+
+// maximum_output of push(): (frame_count * 48000).div_ceil(rate) + 4 (:318-320); frames for 48 kHz sources
+extern "C" size_t sk_norm48k_max_output(size_t frames, uint32_t rate) {
+    if (!rate) return 0;
+    if (rate == 48000u) return frames;
+    return (size_t)(((unsigned __int128)frames * 48000u + rate - 1) / rate) + 4;
+}
+
+extern "C" int sk_norm48k_push(sk_norm48k* n, const uint8_t* data, size_t bytes, int bits, int fmt, int big_endian, int channels, uint32_t rate,
+                               float* left, float* right, size_t cap, size_t* n_out) {
+    if (!n) return SK_E_ARG;
+    sk_ctx* ctx = n->ctx;
+    if (n_out) *n_out = 0;
+    if (n->finished) SK_FAIL(ctx, SK_E_STATE, "48 kHz stereo normalizer is already finished");
+    if (rate == 0 || channels <= 0) SK_FAIL(ctx, SK_E_ARG, "decoded audio has invalid PCM geometry");
+    if (n->rate != 0 && (n->rate != rate || n->channels != channels))
+        SK_FAIL(ctx, SK_E_STATE, "decoded PCM geometry changed from %u Hz/%d ch to %u Hz/%d ch", n->rate, n->channels, rate, channels);
+    if (bits != 16 && bits != 24 && bits != 32) SK_FAIL(ctx, SK_E_ARG, "unsupported PCM bit depth %d", bits);
+    const size_t fb = (size_t)(bits / 8) * (size_t)channels;
+    if (bytes == 0 || bytes % fb) SK_FAIL(ctx, SK_E_ARG, "decoded audio contained an incomplete PCM frame");
+    if (!data) SK_FAIL(ctx, SK_E_ARG, "null buffer");
+    if (n->rate == 0) { n->rate = rate; n->channels = channels; }
+    const size_t frames = bytes / fb;
+    const unsigned long long start = n->source_frames, end = start + frames;
+    unsigned long long count;
+    if (rate == 48000u) count = frames;
+    else {
+        const unsigned long long lim = n48_lerp_limit(end, rate);
+        count = lim > n->output_frames ? lim - n->output_frames : 0;
+    }
+    if (count > cap) SK_FAIL(ctx, SK_E_ARG, "output buffers too small: need %llu frames, have %zu", count, cap);
+    if (count && (!left || !right)) SK_FAIL(ctx, SK_E_ARG, "null buffer");
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    const size_t plane = sk_round_up((size_t)count, 4) + 4;
+    if ((rc = sk_ensure_dev_in(ctx, bytes))) return rc;
+    if ((rc = sk_ensure_dev_out(ctx, (2 * plane + 4) * sizeof(float)))) return rc;
+    if ((rc = sk_h2d(ctx, ctx->d_in, data, bytes))) return rc;
+    N48Src src;
+    if ((rc = n48_fill_src(ctx, &src, ctx->d_in, 0, bits, fmt, big_endian, channels, start, frames))) return rc;
+    float* d_out = (float*)ctx->d_out;
+    float* d_final = d_out + 2 * plane;
+    // 48 kHz sources: output index == source frame index
+    const unsigned long long o_start = rate == 48000u ? start : n->output_frames;
+    if ((rc = n48_launch(ctx, src, o_start, count, count, rate, n->prev_l, n->prev_r, d_out, d_out + plane, 0, 1, d_final))) return rc;
+    float fin[2];
+    if ((rc = sk_d2h(ctx, fin, d_final, sizeof(fin)))) return rc;
+    if (count) {
+        if ((rc = sk_d2h(ctx, left, d_out, (size_t)count * sizeof(float)))) return rc;
+        if ((rc = sk_d2h(ctx, right, d_out + plane, (size_t)count * sizeof(float)))) return rc;
+    }
+    n->output_frames += count;
+    n->source_frames = end;
+    n->prev_l = fin[0]; n->prev_r = fin[1];
+    n->has_previous = true;
+    if (n_out) *n_out = (size_t)count;
+    return SK_OK;
+}
+
+// finish(): the tail is `remaining` copies of the retained final sample — state the host already holds, so no launch
+extern "C" int sk_norm48k_finish(sk_norm48k* n, float* left, float* right, size_t cap, size_t* n_out) {
+    if (!n) return SK_E_ARG;
+    sk_ctx* ctx = n->ctx;
+    if (n_out) *n_out = 0;
+    if (n->finished) SK_FAIL(ctx, SK_E_STATE, "48 kHz stereo normalizer is already finished");
+    n->finished = true;
+    if (!n->has_previous || n->source_frames == 0 || n->rate == 0) SK_FAIL(ctx, SK_E_STATE, "decoded source contained no PCM");
+    if (n->rate == 48000u) return SK_OK;
+    const unsigned long long target = n48_target(n->source_frames, n->rate);
+    const unsigned long long remaining = target > n->output_frames ? target - n->output_frames : 0;
+    n->output_frames = target;
+    if (remaining > cap) SK_FAIL(ctx, SK_E_ARG, "output buffers too small: need %llu frames, have %zu", remaining, cap);
+    for (unsigned long long i = 0; i < remaining; i++) { left[i] = n->prev_l; right[i] = n->prev_r; }
+    if (n_out) *n_out = (size_t)remaining;
+    return SK_OK;
+}

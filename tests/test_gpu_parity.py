@@ -345,3 +345,93 @@ def test_batch_dev_matches_per_stream_and_linearity():
     torch.cuda.synchronize()
     assert torch.max(torch.abs(res[0] + res[1] - res[2])).item() < 1e-5
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------- 8(f) row 2: 48 kHz stereo normalizer
+def _n48_source(bits, fmt, be, channels, frames, rng):
+    if fmt == 1:
+        x = rng.uniform(-1.3, 1.3, frames * channels).astype(np.float32)
+        x[::53] = np.nan; x[1::59] = np.inf; x[2::61] = -np.inf; x[3::67] = -0.0
+        b = x.view(np.uint8).reshape(-1, 4)
+        return np.ascontiguousarray(b[:, ::-1] if be else b).reshape(-1)
+    n = bits // 8
+    raw = rng.integers(0, 256, frames * channels * n, dtype=np.uint8)
+    raw[: 2 * n] = 0x7f if not be else raw[: 2 * n]  # a couple of near-full-scale samples
+    return raw
+
+
+@pytest.mark.parametrize("bits,fmt", [(16, 0), (24, 0), (32, 0), (32, 1)])
+@pytest.mark.parametrize("be", [False, True])
+@pytest.mark.parametrize("channels", [1, 2, 6])
+@pytest.mark.parametrize("rate", [8000, 44100, 48000, 96000])
+def test_normalizer48k_streaming_matches_oracle(ctx, oracle, bits, fmt, be, channels, rate):
+    rng = np.random.default_rng(bits * 1000 + channels * 10 + rate % 97 + int(be))
+    frames = 1237
+    data = _n48_source(bits, fmt, be, channels, frames, rng)
+    fb = (bits // 8) * channels
+    cuts = [0, 1, 2, 37, 400, 401, 1000, frames]  # includes 1-frame pushes (Ok(None) for most rates)
+    gn, on = ctx.normalizer48k(), oracle.Normalizer48k()
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        gl, gr = gn.push(data[a * fb:b * fb], bits, fmt, be, channels, rate)
+        ol, orr = on.push(data[a * fb:b * fb], bits, fmt, be, channels, rate)
+        assert np.array_equal(gl.view(np.uint32), ol.view(np.uint32)) and np.array_equal(gr.view(np.uint32), orr.view(np.uint32)), (a, b)
+        assert gn.source_frames() == on.source_frames() and gn.output_frames() == on.output_frames()
+    gl, gr = gn.finish()
+    ol, orr = on.finish()
+    assert np.array_equal(gl.view(np.uint32), ol.view(np.uint32)) and np.array_equal(gr.view(np.uint32), orr.view(np.uint32))
+    assert gn.output_frames() == on.output_frames() == (frames if rate == 48000 else max(1, int(np.floor(frames * 48000.0 / rate + 0.5))))
+    gn.close()
+
+
+def test_normalizer48k_error_states(ctx):
+    n = ctx.normalizer48k()
+    with pytest.raises(capi.SoundkitError, match="decoded source contained no PCM"):
+        n.finish()
+    n = ctx.normalizer48k()
+    n.push(np.zeros(8, np.uint8), 16, 0, False, 2, 8000)
+    with pytest.raises(capi.SoundkitError, match=r"geometry changed from 8000 Hz/2 ch to 16000 Hz/2 ch"):
+        n.push(np.zeros(8, np.uint8), 16, 0, False, 2, 16000)
+    with pytest.raises(capi.SoundkitError, match="incomplete PCM frame"):
+        n.push(np.zeros(7, np.uint8), 16, 0, False, 2, 8000)
+    with pytest.raises(capi.SoundkitError, match="unsupported PCM bit depth 8"):
+        n.push(np.zeros(8, np.uint8), 8, 0, False, 2, 8000)
+    n.finish()
+    with pytest.raises(capi.SoundkitError, match="already finished"):
+        n.push(np.zeros(8, np.uint8), 16, 0, False, 2, 8000)
+
+
+@pytest.mark.parametrize("bits,fmt,channels,rate", [(16, 0, 2, 44100), (24, 0, 2, 96000), (32, 1, 1, 16000), (16, 0, 2, 48000)])
+def test_normalizer48k_batch_dev_matches_oracle_per_stream(oracle, bits, fmt, channels, rate):
+    """device-resident batch of whole streams == push(whole) + finish() per stream; also the chunking-independence
+    property of soundkit/src/audio_pipeline.rs:806-823 at a larger size (streams of 30 011 frames)"""
+    import torch
+    c = capi.Context(0)
+    c.use_torch_stream()
+    S, frames = 5, 30011
+    rng = np.random.default_rng(rate + bits)
+    fb = (bits // 8) * channels
+    stride = (frames * fb + 15) // 16 * 16
+    host = np.zeros((S, stride), np.uint8)
+    for s in range(S):
+        host[s, : frames * fb] = _n48_source(bits, fmt, False, channels, frames, rng)
+    d_in = torch.from_numpy(host).cuda()
+    n_out = c.normalize48k_out_frames(frames, rate)
+    plane = (n_out + 3) // 4 * 4
+    d_out = torch.full((S, 2, plane), float("nan"), dtype=torch.float32, device="cuda")
+    got_n = c.normalize48k_batch_dev(d_in, stride, S, frames, bits, fmt, False, channels, rate, d_out, 2 * plane, plane)
+    torch.cuda.synchronize()
+    assert got_n == n_out
+    out = d_out.cpu().numpy()
+    for s in range(S):
+        wl, wr = oracle.normalize48k([(host[s, : frames * fb], bits, fmt, False, channels, rate)])
+        assert len(wl) == n_out
+        assert np.array_equal(out[s, 0, :n_out].view(np.uint32), wl.view(np.uint32))
+        assert np.array_equal(out[s, 1, :n_out].view(np.uint32), wr.view(np.uint32))
+    # chunked == whole through the stateful handle
+    nz = c.normalizer48k()
+    ls = []
+    for a in range(0, frames, 4097):
+        ls.append(nz.push(host[0, a * fb:min(frames, a + 4097) * fb], bits, fmt, False, channels, rate)[0].copy())
+    ls.append(nz.finish()[0].copy())
+    assert np.array_equal(np.concatenate(ls).view(np.uint32), out[0, 0, :n_out].view(np.uint32))
+    c.close()

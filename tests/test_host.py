@@ -358,3 +358,71 @@ def test_apply_output_options_width_and_channel_arms(oracle):
     mono = (np.float32(0.0) + x[0] * np.float32(0.5)) + x[1] * np.float32(0.5)
     want = np.array([D.float_sample_to_i16(float(s)) for s in mono], np.int16)
     assert np.array_equal(np.frombuffer(out[0].data(), "<i2"), want)
+
+
+# ---------------------------------------------------------------------------------------------- GPU: 48 kHz stereo normalizer
+def pcm16_audio(rate, channels):  # audio_pipeline.rs:770-779
+    return audio(16, len(channels), rate, AB.interleave_vecs_i16([list(map(int, c)) for c in channels]))
+
+
+def normalize_blocks(blocks):  # audio_pipeline.rs:781-795
+    nz = AP.StreamingStereo48kNormalizer()
+    left, right = [], []
+    for b in blocks:
+        out = nz.push(b)
+        if out is not None:
+            left += out[0].tolist(); right += out[1].tolist()
+    out = nz.finish()
+    if out is not None:
+        left += out[0].tolist(); right += out[1].tolist()
+    return left, right
+
+
+@pytest.mark.gpu
+def test_streaming_normalizer_converts_pcm_without_intermediate_channel_planes():  # audio_pipeline.rs:715-755
+    eps = float(np.finfo(np.float32).eps)
+    l, r = AP.StreamingStereo48kNormalizer().push(audio(16, 2, 48000, struct.pack(">hh", 32767, -32768), SIGNED, BE))
+    assert abs(l[0] - 32767.0 / 32768.0) < eps and r[0] == -1.0
+    l, r = AP.StreamingStereo48kNormalizer().push(audio(24, 2, 48000, bytes([0xff, 0xff, 0x7f, 0x00, 0x00, 0x80])))
+    assert abs(l[0] - 8388607.0 / 8388608.0) < eps and r[0] == -1.0
+    l, r = AP.StreamingStereo48kNormalizer().push(audio(32, 1, 48000, struct.pack("<f", float("nan")), FLOAT))
+    assert l.tolist() == [0.0] and r.tolist() == l.tolist()
+
+
+@pytest.mark.gpu
+def test_streaming_stereo_normalizer_duplicates_mono_without_resampling():  # audio_pipeline.rs:797-804
+    left, right = normalize_blocks([pcm16_audio(48000, [[-32768, 0, 32767]])])
+    assert left == right and len(left) == 3 and left[0] == -1.0 and left[1] == 0.0
+
+
+@pytest.mark.gpu
+def test_streaming_stereo_normalizer_is_independent_of_decoder_chunking():  # audio_pipeline.rs:806-823
+    left = [s * 211 - 10000 for s in range(100)]
+    right = [10000 - s * 173 for s in range(100)]
+    whole = pcm16_audio(44100, [left, right])
+    chunks = [pcm16_audio(44100, [left[:37], right[:37]]), pcm16_audio(44100, [left[37:73], right[37:73]]),
+              pcm16_audio(44100, [left[73:], right[73:]])]
+    expected, actual = normalize_blocks([whole]), normalize_blocks(chunks)
+    assert actual == expected and len(actual[0]) == 109
+
+
+@pytest.mark.gpu
+def test_streaming_normalizer_error_strings():  # audio_pipeline.rs:288-309, 366-373, 133-148
+    nz = AP.StreamingStereo48kNormalizer()
+    with pytest.raises(H.SoundkitError, match="decoded source contained no PCM"):
+        nz.finish()
+    with pytest.raises(H.SoundkitError, match="48 kHz stereo normalizer is already finished"):
+        nz.push(pcm16_audio(8000, [[1, 2]]))
+    nz = AP.StreamingStereo48kNormalizer()
+    with pytest.raises(H.SoundkitError, match="decoded audio has invalid PCM geometry"):
+        nz.push(audio(16, 0, 8000, b"\0\0"))
+    with pytest.raises(H.SoundkitError, match="unsupported PCM bit depth 8"):
+        nz.push(audio(8, 1, 8000, b"\0\0"))
+    with pytest.raises(H.SoundkitError, match="decoded audio contained an incomplete PCM frame"):
+        nz.push(audio(16, 1, 8000, b"\0\0\0"))
+    assert nz.push(pcm16_audio(8000, [[5]])) is None  # one frame: nothing to interpolate yet
+    with pytest.raises(H.SoundkitError, match=r"decoded PCM geometry changed from 8000 Hz/1 ch to 8000 Hz/2 ch"):
+        nz.push(pcm16_audio(8000, [[1], [2]]))
+    assert (nz.source_sample_rate(), nz.source_channels(), nz.source_frames()) == (8000, 1, 1)
+    tail = nz.finish()
+    assert len(tail[0]) == 6 and nz.output_frames() == 6  # round(1 * 48000 / 8000)

@@ -217,3 +217,49 @@ def test_scalar_and_avx_dot_products_agree(oracle):
     a = oracle.Resampler(44100, 48000, 20000, 2).process(x, threads=1)
     b = oracle.Resampler(44100, 48000, 20000, 2).process(x, threads=4)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------- 8(f) row 2: 48 kHz normalizer
+def _pcm16_block(rate, chans):
+    a = np.stack([np.asarray(c, np.int16) for c in chans], axis=1).astype("<i2").tobytes()
+    return (np.frombuffer(a, np.uint8), 16, 0, False, len(chans), rate)
+
+
+def test_normalizer48k_reference_unit_vectors(oracle):
+    """soundkit/src/audio_pipeline.rs:715-755 and :797-823 restated against the oracle"""
+    import struct
+    # streaming_normalizer_converts_pcm_without_intermediate_channel_planes
+    l, r = oracle.Normalizer48k().push(np.frombuffer(struct.pack(">hh", 32767, -32768), np.uint8), 16, 0, True, 2, 48000)
+    assert abs(l[0] - 32767.0 / 32768.0) < np.finfo(np.float32).eps and r[0] == -1.0
+    l, r = oracle.Normalizer48k().push(np.frombuffer(bytes([0xff, 0xff, 0x7f, 0x00, 0x00, 0x80]), np.uint8), 24, 0, False, 2, 48000)
+    assert abs(l[0] - 8388607.0 / 8388608.0) < np.finfo(np.float32).eps and r[0] == -1.0
+    l, r = oracle.Normalizer48k().push(np.frombuffer(struct.pack("<f", float("nan")), np.uint8), 32, 1, False, 1, 48000)
+    assert l.tolist() == [0.0] and r.tolist() == [0.0]
+    # streaming_stereo_normalizer_duplicates_mono_without_resampling
+    l, r = oracle.normalize48k([_pcm16_block(48000, [[-32768, 0, 32767]])])
+    assert np.array_equal(l, r) and len(l) == 3 and l[0] == -1.0 and l[1] == 0.0
+    # streaming_stereo_normalizer_is_independent_of_decoder_chunking
+    left = [s * 211 - 10000 for s in range(100)]
+    right = [10000 - s * 173 for s in range(100)]
+    whole = oracle.normalize48k([_pcm16_block(44100, [left, right])])
+    parts = oracle.normalize48k([_pcm16_block(44100, [left[:37], right[:37]]), _pcm16_block(44100, [left[37:73], right[37:73]]),
+                                 _pcm16_block(44100, [left[73:], right[73:]])])
+    assert np.array_equal(whole[0], parts[0]) and np.array_equal(whole[1], parts[1])
+    assert len(parts[0]) == 109
+
+
+def test_normalizer48k_error_arms_and_lengths(oracle):
+    nz = oracle.Normalizer48k()
+    with pytest.raises(ValueError):
+        nz.finish()                      # "decoded source contained no PCM"
+    nz = oracle.Normalizer48k()
+    nz.push(*_pcm16_block(8000, [[1, 2, 3]]))
+    with pytest.raises(ValueError):
+        nz.push(*_pcm16_block(16000, [[1, 2, 3]]))   # geometry changed
+    with pytest.raises(ValueError):
+        nz.push(np.zeros(3, np.uint8), 16, 0, False, 1, 8000)  # incomplete frame
+    # total length == max(1, round(frames * 48000 / rate)) for every common rate
+    for rate in (8000, 16000, 22050, 24000, 32000, 44100, 88200, 96000):
+        for frames in (1, 2, 3, 100, 1001):
+            l, r = oracle.normalize48k([_pcm16_block(rate, [list(range(frames))])])
+            assert len(l) == len(r) == max(1, int(np.floor(frames * 48000.0 / rate + 0.5))), (rate, frames)
