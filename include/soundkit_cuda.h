@@ -81,7 +81,14 @@ enum sk_flat_op {
     SK_OP_F32BE_TO_I16 = 16, /* :178 */
     SK_OP_F32LE_TO_I32 = 17, /* :189 */
     SK_OP_F32LE_TO_S24 = 18, /* :205 */
-    SK_OP_COUNT = 19
+    /* SURVEY.md 8(f) row 3 — the packet scalers of soundkit/src/audio_packet.rs (a third scale convention) and the
+     * container-PCM unpackers that feed the output stage */
+    SK_OP_PKT_S16LE_TO_F32 = 19, /* audio_packet.rs:176-180, 243-247: f32::from(i16) / f32::from(i16::MAX) (true division by 32767) */
+    SK_OP_PKT_S24LE_TO_F32 = 20, /* audio_packet.rs:182-186, 250-254: i24 as f32 / (1 << 23) */
+    SK_OP_PKT_S32LE_TO_I16 = 21, /* audio_packet.rs:108-112: (s as i64 * 32767 / 2147483647) clamped to i16 */
+    SK_OP_PKT_F32LE_TO_I16 = 22, /* audio_packet.rs:113-121: ((x * 32767.0) as i32) clamped to i16 (no pre-clamp of x) */
+    SK_OP_U8_TO_S16 = 23,        /* soundkit-decoder/src/lib.rs:362-367 (AVI 8-bit PCM): (i16::from(u8) - 128) << 8 */
+    SK_OP_COUNT = 24
 };
 
 /* ------------------------------------------------------------------ context */
@@ -117,6 +124,14 @@ int sk_pcm_flat_convert(sk_ctx*, int op, const uint8_t* in, size_t bytes, void* 
 int sk_pcm_flat_convert_dev(sk_ctx*, int op, const uint8_t* in, size_t bytes, void* out);
 /* bytes per input / output element of a flat op */
 int sk_flat_op_widths(int op, int* in_width, int* out_width);
+
+/* unpack_dvd_lpcm (soundkit-decoder/src/lib.rs:750-804): DVD / MPEG-PS LPCM payload -> little-endian interleaved PCM of
+ * the same byte length.  bits 16: byte swap per sample; bits 24: every 12-byte group (4 x 16 high bits big-endian, then
+ * 4 low bytes) -> 4 s24le samples.  A partial block is SK_E_ARG with the reference's message in sk_last_error()
+ * ("DVD LPCM ends with a partial sample block" / "... partial 24-bit sample block"; bits 20: "20-bit DVD LPCM decoding is
+ * not implemented"). */
+int sk_dvd_lpcm_unpack(sk_ctx*, const uint8_t* packed, size_t bytes, int bits, int channels, uint8_t* out);
+int sk_dvd_lpcm_unpack_dev(sk_ctx*, const uint8_t* packed, size_t bytes, int bits, int channels, uint8_t* out);
 
 /* deinterleave_vecs_{i16,s24,f32} (audio_bytes.rs:264-310): interleaved LE bytes -> planar
  * [channels][frames] of i16 / sign-extended i32 / f32 bits.  kind: 0 = i16, 1 = s24, 2 = f32. */

@@ -130,6 +130,8 @@ _FLAT = {
     "s32be_to_f32": (4, np.float32), "s32le_to_i16": (4, np.int16), "s32be_to_i16": (4, np.int16),
     "f32le_to_i16": (4, np.int16), "f32be_to_i16": (4, np.int16), "f32le_to_i32": (4, np.int32),
     "f32le_to_s24": (4, np.int32),
+    "pkt_s16le_to_f32": (2, np.float32), "pkt_s24le_to_f32": (3, np.float32), "pkt_s32le_to_i16": (4, np.int16),
+    "pkt_f32le_to_i16": (4, np.int16), "u8_to_s16": (1, np.int16),
 }
 FLAT_NAMES = tuple(_FLAT)
 
@@ -346,6 +348,16 @@ def normalize_chain_mono(data, bits, fmt, big_endian, channels, in_rate, out_rat
     n = lib().sko_normalize_chain_mono(_ptr(d), d.size, bits, fmt, int(big_endian), channels, in_rate, out_rate,
                                        _ptr(out), cap)
     return None if n == ERR else out[:n].copy()
+
+
+def unpack_dvd_lpcm(packed, bits, channels):
+    """unpack_dvd_lpcm (soundkit-decoder/src/lib.rs:750-804); None for the Err arms"""
+    d = _bytes(packed)
+    out = np.empty(d.size, np.uint8)
+    lib().sko_unpack_dvd_lpcm.restype = C.c_size_t
+    lib().sko_unpack_dvd_lpcm.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+    n = lib().sko_unpack_dvd_lpcm(_ptr(d), d.size, bits, channels, _ptr(out))
+    return None if n == ERR else out[:n]
 
 
 class Normalizer48k:

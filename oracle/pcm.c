@@ -367,3 +367,72 @@ size_t sko_exact_signed_pcm_to_i16(const uint8_t* in, size_t bytes, int bits, in
     }
     return n * 2;
 }
+
+
+/* ---- packet scalers (soundkit/src/audio_packet.rs) and container-PCM unpackers ---------- */
+/* audio_packet.rs:176-180, 243-247: f32::from(i16) / f32::from(i16::MAX) */
+size_t sko_pkt_s16le_to_f32(const uint8_t* in, size_t bytes, float* out) {
+    size_t n = bytes / 2;
+    for (size_t i = 0; i < n; i++) out[i] = (float)(int16_t)(in[2 * i] | (in[2 * i + 1] << 8)) / 32767.0f;
+    return n;
+}
+/* audio_packet.rs:182-186, 250-254: LE::read_i24 as f32 / (1 << 23) as f32 */
+size_t sko_pkt_s24le_to_f32(const uint8_t* in, size_t bytes, float* out) {
+    size_t n = bytes / 3;
+    for (size_t i = 0; i < n; i++) {
+        uint32_t u = in[3 * i] | ((uint32_t)in[3 * i + 1] << 8) | ((uint32_t)in[3 * i + 2] << 16);
+        int32_t v = (u & 0x800000u) ? (int32_t)(u | 0xff000000u) : (int32_t)u;
+        out[i] = (float)v / 8388608.0f;
+    }
+    return n;
+}
+/* audio_packet.rs:105-124 (PCMSigned arm): (s32 as i64 * i16::MAX as i64 / i32::MAX as i64) as i32, clamped to i16 */
+size_t sko_pkt_s32le_to_i16(const uint8_t* in, size_t bytes, int16_t* out) {
+    size_t n = bytes / 4;
+    for (size_t i = 0; i < n; i++) {
+        int32_t s = (int32_t)(in[4 * i] | ((uint32_t)in[4 * i + 1] << 8) | ((uint32_t)in[4 * i + 2] << 16) | ((uint32_t)in[4 * i + 3] << 24));
+        int32_t q = (int32_t)(((int64_t)s * 32767) / 2147483647);
+        out[i] = (int16_t)(q < -32768 ? -32768 : (q > 32767 ? 32767 : q));
+    }
+    return n;
+}
+/* audio_packet.rs:113-124 (float arm): (x * 32767.0) as i32 (Rust `as`: truncates, saturates, NaN -> 0), clamped to i16 */
+size_t sko_pkt_f32le_to_i16(const uint8_t* in, size_t bytes, int16_t* out) {
+    size_t n = bytes / 4;
+    for (size_t i = 0; i < n; i++) {
+        float x; memcpy(&x, in + 4 * i, 4);
+        float y = x * 32767.0f;
+        int32_t q = (y != y) ? 0 : (y >= 2147483648.0f ? INT32_MAX : (y <= -2147483648.0f ? INT32_MIN : (int32_t)y));
+        out[i] = (int16_t)(q < -32768 ? -32768 : (q > 32767 ? 32767 : q));
+    }
+    return n;
+}
+/* soundkit-decoder/src/lib.rs:362-367 (AVI 8-bit PCM): (i16::from(sample) - 128) << 8 */
+size_t sko_u8_to_s16(const uint8_t* in, size_t bytes, int16_t* out) {
+    for (size_t i = 0; i < bytes; i++) out[i] = (int16_t)(((int)in[i] - 128) * 256);
+    return bytes;
+}
+/* unpack_dvd_lpcm, soundkit-decoder/src/lib.rs:750-804.  Returns bytes written, or (size_t)-1 for the Err arms
+ * (partial block / 20-bit). */
+size_t sko_unpack_dvd_lpcm(const uint8_t* packed, size_t bytes, int bits, int channels, uint8_t* out) {
+    if (bits == 16) {
+        if (bytes % ((size_t)channels * 2)) return (size_t)-1;
+        for (size_t i = 0; i + 1 < bytes; i += 2) { out[i] = packed[i + 1]; out[i + 1] = packed[i]; }
+        return bytes;
+    }
+    if (bits == 20) return (size_t)-1;
+    size_t groups_per_block = (channels == 1 || channels == 2 || channels == 4) ? 1 : (channels == 8 ? 2 : (size_t)channels);
+    size_t block_size = (channels == 1 || channels == 2 || channels == 4) ? 12 : (channels == 8 ? 24 : (size_t)channels * 12);
+    if (bytes % block_size) return (size_t)-1;
+    size_t w = 0;
+    for (size_t b = 0; b < bytes; b += block_size) {
+        size_t cursor = 0;
+        for (size_t g = 0; g < groups_per_block; g++) {
+            const uint8_t* high = packed + b + cursor;
+            const uint8_t* low = packed + b + cursor + 8;
+            for (int s = 0; s < 4; s++) { out[w++] = low[s]; out[w++] = high[2 * s + 1]; out[w++] = high[2 * s]; }
+            cursor += 12;
+        }
+    }
+    return w;
+}

@@ -147,6 +147,15 @@ size_t sko_normalize_chain_mono(const uint8_t* in, size_t bytes, int bits, int f
                                 size_t channels, uint32_t in_rate, uint32_t out_rate, float* out,
                                 size_t out_cap);
 
+/* ---- 8(f) next row 3: packet scalers (soundkit/src/audio_packet.rs:105-124, 176-186, 243-254), AVI u8 (soundkit-decoder/
+ * src/lib.rs:362-367) and unpack_dvd_lpcm (soundkit-decoder/src/lib.rs:750-804); pcm.c ---- */
+size_t sko_pkt_s16le_to_f32(const uint8_t* in, size_t bytes, float* out);
+size_t sko_pkt_s24le_to_f32(const uint8_t* in, size_t bytes, float* out);
+size_t sko_pkt_s32le_to_i16(const uint8_t* in, size_t bytes, int16_t* out);
+size_t sko_pkt_f32le_to_i16(const uint8_t* in, size_t bytes, int16_t* out);
+size_t sko_u8_to_s16(const uint8_t* in, size_t bytes, int16_t* out);
+size_t sko_unpack_dvd_lpcm(const uint8_t* packed, size_t bytes, int bits, int channels, uint8_t* out);
+
 /* ---- 8(f) next row 2: StreamingStereo48kNormalizer (soundkit/src/audio_pipeline.rs:133-413), norm48k.c ---- */
 typedef struct sko_norm48k sko_norm48k;
 sko_norm48k* sko_norm48k_new(void);

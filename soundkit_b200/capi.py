@@ -23,7 +23,7 @@ SEM_ONESHOT, SEM_STREAMING = 0, 1
 FLAT_OPS = ("i16le_to_f32", "s16le_to_i16", "s16be_to_i16", "s16le_to_i32", "s24le_to_i32", "s24le_to_i16",
             "s24be_to_i16", "s32le_to_i32", "s32be_to_i32", "s32le_to_s24", "s32be_to_s24", "s32le_to_f32",
             "s32be_to_f32", "s32le_to_i16", "s32be_to_i16", "f32le_to_i16", "f32be_to_i16", "f32le_to_i32",
-            "f32le_to_s24")
+            "f32le_to_s24", "pkt_s16le_to_f32", "pkt_s24le_to_f32", "pkt_s32le_to_i16", "pkt_f32le_to_i16", "u8_to_s16")
 FLAT_OP = {name: i for i, name in enumerate(FLAT_OPS)}
 
 EXPORTS = (
@@ -31,7 +31,8 @@ EXPORTS = (
     "sk_ctx_synchronize",
     "sk_ctx_launch_count", "sk_ctx_measure_ffma_peak", "sk_ctx_measure_ffma_peaks",
     "sk_g711_decode", "sk_g711_decode_dev", "sk_g711_encode", "sk_g711_encode_dev",
-    "sk_pcm_flat_convert", "sk_pcm_flat_convert_dev", "sk_flat_op_widths", "sk_deinterleave", "sk_interleave_i16",
+    "sk_pcm_flat_convert", "sk_pcm_flat_convert_dev", "sk_flat_op_widths", "sk_dvd_lpcm_unpack", "sk_dvd_lpcm_unpack_dev",
+    "sk_deinterleave", "sk_interleave_i16",
     "sk_stereo_to_mono_i16", "sk_pcm_to_planar_f32", "sk_pcm_to_planar_f32_dev", "sk_planar_f32_to_pcm",
     "sk_planar_f32_to_pcm_dev", "sk_pcm_narrow_i16", "sk_mixdown_mono", "sk_mixdown_mono_dev", "sk_downmix_stereo",
     "sk_resampler_create", "sk_resampler_destroy", "sk_resampler_out_max", "sk_resampler_last_index",
@@ -93,6 +94,8 @@ def load():
         "sk_pcm_flat_convert": (i, [vp, i, vp, sz, vp, psz]),
         "sk_pcm_flat_convert_dev": (i, [vp, i, vp, sz, vp]),
         "sk_flat_op_widths": (i, [i, C.POINTER(i), C.POINTER(i)]),
+        "sk_dvd_lpcm_unpack": (i, [vp, vp, sz, i, i, vp]),
+        "sk_dvd_lpcm_unpack_dev": (i, [vp, vp, sz, i, i, vp]),
         "sk_deinterleave": (i, [vp, i, vp, sz, i, vp, psz]),
         "sk_interleave_i16": (i, [vp, vp, i, sz, vp]),
         "sk_stereo_to_mono_i16": (i, [vp, i, vp, sz, vp]),
@@ -244,6 +247,12 @@ class Context:
         n = C.c_size_t()
         self._ck(self.L.sk_pcm_flat_convert(self.h, op, _p(d), d.size, _p(out), C.byref(n)))
         return out[:n.value]
+
+    def dvd_lpcm_unpack(self, packed, bits, channels):
+        d = _u8(packed)
+        out = np.empty(d.size, np.uint8)
+        self._ck(self.L.sk_dvd_lpcm_unpack(self.h, _p(d), d.size, bits, channels, _p(out)))
+        return out
 
     def flat_convert_dev(self, name, d_in, nbytes, d_out):
         self._ck(self.L.sk_pcm_flat_convert_dev(self.h, FLAT_OP[name], _p(d_in), nbytes, _p(d_out)))

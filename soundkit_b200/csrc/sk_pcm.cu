@@ -19,7 +19,9 @@
 // ------------------------------------------------------------------------------------------------
 template <int B, bool BE>
 __device__ __forceinline__ int32_t get_sample(const uint32_t* w, int k) {  // k is compile-time after unrolling
-    if (B == 2) {
+    if (B == 1) {
+        return (int32_t)((w[k >> 2] >> (8 * (k & 3))) & 0xffu);  // unsigned byte
+    } else if (B == 2) {
         uint32_t word = w[k >> 1];
         uint32_t h = (k & 1) ? (word >> 16) : (word & 0xffffu);
         if (BE) h = ((h & 0xff) << 8) | (h >> 8);
@@ -86,6 +88,11 @@ __host__ __device__ constexpr FlatOpInfo flat_info(int op) {
         case SK_OP_F32BE_TO_I16: return {4, true, 2};
         case SK_OP_F32LE_TO_I32: return {4, false, 4};
         case SK_OP_F32LE_TO_S24: return {4, false, 4};
+        case SK_OP_PKT_S16LE_TO_F32: return {2, false, 4};
+        case SK_OP_PKT_S24LE_TO_F32: return {3, false, 4};
+        case SK_OP_PKT_S32LE_TO_I16: return {4, false, 2};
+        case SK_OP_PKT_F32LE_TO_I16: return {4, false, 2};
+        case SK_OP_U8_TO_S16: return {1, false, 2};
         default: return {0, false, 0};
     }
 }
@@ -104,6 +111,14 @@ __device__ __forceinline__ uint32_t flat_apply(int32_t raw) {
         case SK_OP_F32LE_TO_I16: case SK_OP_F32BE_TO_I16: return (uint32_t)f32_to_i16_trunc_dev(__int_as_float(raw)) & 0xffffu;
         case SK_OP_F32LE_TO_I32: return (uint32_t)f32_to_i32_dev(__int_as_float(raw));
         case SK_OP_F32LE_TO_S24: return (uint32_t)f32_to_s24_dev(__int_as_float(raw));
+        case SK_OP_PKT_S16LE_TO_F32: return __float_as_uint(__fdiv_rn((float)raw, 32767.0f));
+        case SK_OP_PKT_S24LE_TO_F32: return __float_as_uint(__fmul_rn((float)raw, 1.0f / 8388608.0f));
+        case SK_OP_PKT_S32LE_TO_I16: {  // i64 product, truncating division, clamp (the clamp never bites: |q| <= 32767)
+            long long q = ((long long)raw * 32767ll) / 2147483647ll;
+            return (uint32_t)max(-32768ll, min(32767ll, q)) & 0xffffu;
+        }
+        case SK_OP_PKT_F32LE_TO_I16: return (uint32_t)max(-32768, min(32767, __float2int_rz(__fmul_rn(__int_as_float(raw), 32767.0f)))) & 0xffffu;
+        case SK_OP_U8_TO_S16: return (uint32_t)((raw - 128) << 8) & 0xffffu;
         default: return 0;
     }
 }
@@ -115,7 +130,7 @@ template <int OP>
 __global__ void __launch_bounds__(kPcmThreads) flat_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t ngroups) {
     constexpr FlatOpInfo I = flat_info(OP);
     constexpr int B = I.in_b, OB = I.out_b;
-    constexpr int G = B == 2 ? 8 : (B == 3 ? 16 : (OB == 2 ? 8 : 4));
+    constexpr int G = B == 1 ? 16 : (B == 2 ? 8 : (B == 3 ? 16 : (OB == 2 ? 8 : 4)));
     constexpr int NV_IN = G * B / 16, NW_OUT = G * OB / 4;
     const size_t stride = (size_t)gridDim.x * kPcmThreads;
     for (size_t g = (size_t)blockIdx.x * kPcmThreads + threadIdx.x; g < ngroups; g += stride) {
@@ -148,7 +163,7 @@ __global__ void flat_scalar_kernel(const uint8_t* __restrict__ in, uint8_t* __re
         uint32_t u = 0;
         if (!I.be) { for (int b = 0; b < I.in_b; b++) u |= (uint32_t)p[b] << (8 * b); }
         else       { for (int b = 0; b < I.in_b; b++) u = (u << 8) | p[b]; }
-        int32_t raw = I.in_b == 2 ? (int32_t)(int16_t)u : (I.in_b == 3 ? ((int32_t)(u << 8)) >> 8 : (int32_t)u);
+        int32_t raw = I.in_b == 1 ? (int32_t)u : (I.in_b == 2 ? (int32_t)(int16_t)u : (I.in_b == 3 ? ((int32_t)(u << 8)) >> 8 : (int32_t)u));
         uint32_t r = flat_apply<OP>(raw);
         if (I.out_b == 2) reinterpret_cast<uint16_t*>(out)[i] = (uint16_t)r;
         else reinterpret_cast<uint32_t*>(out)[i] = r;
@@ -166,7 +181,7 @@ static inline int grid_for(sk_ctx* ctx, size_t work_items, int threads) {
 template <int OP>
 static int launch_flat(sk_ctx* ctx, const uint8_t* in, size_t n, uint8_t* out) {
     constexpr FlatOpInfo I = flat_info(OP);
-    constexpr int G = I.in_b == 2 ? 8 : (I.in_b == 3 ? 16 : (I.out_b == 2 ? 8 : 4));
+    constexpr int G = I.in_b == 1 ? 16 : (I.in_b == 2 ? 8 : (I.in_b == 3 ? 16 : (I.out_b == 2 ? 8 : 4)));
     size_t ngroups = (aligned16(in) && aligned16(out)) ? n / G : 0;
     if (ngroups) {
         flat_kernel<OP><<<grid_for(ctx, ngroups, kPcmThreads), kPcmThreads, 0, ctx->stream>>>(in, out, ngroups);
@@ -204,7 +219,8 @@ extern "C" int sk_pcm_flat_convert_dev(sk_ctx* ctx, int op, const uint8_t* in, s
         SK_FLAT_CASE(SK_OP_S32LE_TO_S24) SK_FLAT_CASE(SK_OP_S32BE_TO_S24) SK_FLAT_CASE(SK_OP_S32LE_TO_F32)
         SK_FLAT_CASE(SK_OP_S32BE_TO_F32) SK_FLAT_CASE(SK_OP_S32LE_TO_I16) SK_FLAT_CASE(SK_OP_S32BE_TO_I16)
         SK_FLAT_CASE(SK_OP_F32LE_TO_I16) SK_FLAT_CASE(SK_OP_F32BE_TO_I16) SK_FLAT_CASE(SK_OP_F32LE_TO_I32)
-        SK_FLAT_CASE(SK_OP_F32LE_TO_S24)
+        SK_FLAT_CASE(SK_OP_F32LE_TO_S24) SK_FLAT_CASE(SK_OP_PKT_S16LE_TO_F32) SK_FLAT_CASE(SK_OP_PKT_S24LE_TO_F32)
+        SK_FLAT_CASE(SK_OP_PKT_S32LE_TO_I16) SK_FLAT_CASE(SK_OP_PKT_F32LE_TO_I16) SK_FLAT_CASE(SK_OP_U8_TO_S16)
 #undef SK_FLAT_CASE
     }
     return SK_E_ARG;
@@ -225,6 +241,77 @@ extern "C" int sk_pcm_flat_convert(sk_ctx* ctx, int op, const uint8_t* in, size_
     if ((rc = sk_h2d(ctx, ctx->d_in, in, n * I.in_b))) return rc;
     if ((rc = sk_pcm_flat_convert_dev(ctx, op, (const uint8_t*)ctx->d_in, n * I.in_b, ctx->d_out))) return rc;
     return sk_d2h(ctx, out, ctx->d_out, n * I.out_b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// unpack_dvd_lpcm, soundkit-decoder/src/lib.rs:750-804
+// ------------------------------------------------------------------------------------------------
+// 24-bit: a 12-byte group holds the 16 high bits of 4 samples (big-endian) followed by their 4 low bytes; the output is
+// the same 4 samples as packed little-endian 24-bit: out[3s..3s+3] = {in[8+s], in[2s+1], in[2s]}.  Pure byte permutation:
+// 3 words in, 4 PRMT, 3 words out; a thread owns 4 groups (48 B) so every access is a 128-bit vector.
+__device__ __forceinline__ void dvd24_group(const uint32_t* w, uint32_t* o) {
+    o[0] = __byte_perm(w[0], w[2], 0x5014);                                   // in8 in1 in0 in9
+    o[1] = __byte_perm(__byte_perm(w[0], w[2], 0x0623), w[1], 0x5210);         // in3 in2 in10 in5
+    o[2] = __byte_perm(w[1], w[2], 0x2370);                                   // in4 in11 in7 in6
+}
+__global__ void __launch_bounds__(kPcmThreads) dvd_lpcm24_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t nquads,
+                                                                  size_t ngroups, int vec) {
+    const size_t stride = (size_t)gridDim.x * kPcmThreads;
+    if (vec) {
+        for (size_t q = (size_t)blockIdx.x * kPcmThreads + threadIdx.x; q < nquads; q += stride) {
+            uint32_t w[12], o[12];
+            const uint4* p = reinterpret_cast<const uint4*>(in + q * 48);
+#pragma unroll
+            for (int v = 0; v < 3; v++) { uint4 t = __ldg(p + v); w[4 * v] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w; }
+#pragma unroll
+            for (int g = 0; g < 4; g++) dvd24_group(w + 3 * g, o + 3 * g);
+            uint4* d = reinterpret_cast<uint4*>(out + q * 48);
+#pragma unroll
+            for (int v = 0; v < 3; v++) st_stream_v4(d + v, make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]));
+        }
+    }
+    // groups not covered by whole quads (or everything, for unaligned buffers): one thread per group, byte accesses
+    const size_t first = vec ? nquads * 4 : 0;
+    for (size_t g = first + (size_t)blockIdx.x * kPcmThreads + threadIdx.x; g < ngroups; g += stride) {
+        const uint8_t* p = in + g * 12;
+        uint8_t* d = out + g * 12;
+#pragma unroll
+        for (int s = 0; s < 4; s++) { d[3 * s] = p[8 + s]; d[3 * s + 1] = p[2 * s + 1]; d[3 * s + 2] = p[2 * s]; }
+    }
+}
+
+extern "C" int sk_dvd_lpcm_unpack_dev(sk_ctx* ctx, const uint8_t* packed, size_t bytes, int bits, int channels, uint8_t* out) {
+    if (!ctx) return SK_E_ARG;
+    if (channels <= 0 || channels > 8) SK_FAIL(ctx, SK_E_ARG, "DVD LPCM channel count %d out of range", channels);
+    if (bits == 20) SK_FAIL(ctx, SK_E_ARG, "20-bit DVD LPCM decoding is not implemented");
+    if (bits != 16 && bits != 24) SK_FAIL(ctx, SK_E_ARG, "unsupported DVD LPCM sample size %d", bits);
+    if (bits == 16) {
+        if (bytes % ((size_t)channels * 2)) SK_FAIL(ctx, SK_E_ARG, "DVD LPCM ends with a partial sample block");
+        return sk_pcm_flat_convert_dev(ctx, SK_OP_S16BE_TO_I16, packed, bytes, out);  // [sample[1], sample[0]]
+    }
+    const size_t block = (channels == 1 || channels == 2 || channels == 4) ? 12 : (channels == 8 ? 24 : (size_t)channels * 12);
+    if (bytes % block) SK_FAIL(ctx, SK_E_ARG, "DVD LPCM ends with a partial 24-bit sample block");
+    if (!bytes) return SK_OK;
+    if (!packed || !out) SK_FAIL(ctx, SK_E_ARG, "null buffer");
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t ngroups = bytes / 12;
+    const int vec = aligned16(packed) && aligned16(out);
+    const size_t nquads = vec ? ngroups / 4 : 0;
+    dvd_lpcm24_kernel<<<grid_for(ctx, vec ? nquads + 1 : ngroups, kPcmThreads), kPcmThreads, 0, ctx->stream>>>(packed, out, nquads, ngroups, vec);
+    SK_LAUNCH_CHECK(ctx);
+    return SK_OK;
+}
+
+extern "C" int sk_dvd_lpcm_unpack(sk_ctx* ctx, const uint8_t* packed, size_t bytes, int bits, int channels, uint8_t* out) {
+    if (!ctx) return SK_E_ARG;
+    if (bytes && (!packed || !out)) SK_FAIL(ctx, SK_E_ARG, "null buffer");
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = sk_ensure_dev_in(ctx, bytes + 16))) return rc;
+    if ((rc = sk_ensure_dev_out(ctx, bytes + 16))) return rc;
+    if ((rc = sk_h2d(ctx, ctx->d_in, packed, bytes))) return rc;
+    if ((rc = sk_dvd_lpcm_unpack_dev(ctx, (const uint8_t*)ctx->d_in, bytes, bits, channels, (uint8_t*)ctx->d_out))) return rc;
+    return sk_d2h(ctx, out, ctx->d_out, bytes);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -61,8 +61,8 @@ def test_flat_op_widths_table():
     for name, op in capi.FLAT_OP.items():
         a, b = C.c_int(), C.c_int()
         assert L.sk_flat_op_widths(op, C.byref(a), C.byref(b)) == 0
-        src = name.split("_to_")[0]
+        src = name.split("_to_")[0].replace("pkt_", "")
         assert a.value == {"i16le": 2, "s16le": 2, "s16be": 2, "s24le": 3, "s24be": 3, "s32le": 4, "s32be": 4,
-                           "f32le": 4, "f32be": 4}[src]
-        assert b.value == (2 if name.endswith("i16") else 4)
+                           "f32le": 4, "f32be": 4, "u8": 1}[src]
+        assert b.value == (2 if name.endswith(("i16", "s16")) else 4)
     assert L.sk_flat_op_widths(99, None, None) == capi.E_ARG

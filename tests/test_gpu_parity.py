@@ -435,3 +435,30 @@ def test_normalizer48k_batch_dev_matches_oracle_per_stream(oracle, bits, fmt, ch
     ls.append(nz.finish()[0].copy())
     assert np.array_equal(np.concatenate(ls).view(np.uint32), out[0, 0, :n_out].view(np.uint32))
     c.close()
+
+
+# ---------------------------------------------------------------------------------------------- 8(f) row 3: unpackers
+@pytest.mark.parametrize("bits,channels,nbytes", [(16, 2, 0), (16, 2, 4 * 1001), (16, 6, 12 * 333), (24, 1, 12 * 7), (24, 2, 12 * 4099),
+                                                   (24, 8, 24 * 1000), (24, 3, 36 * 501), (24, 4, 12 * 65537)])
+def test_dvd_lpcm_unpack_bit_exact(ctx, oracle, bits, channels, nbytes):
+    packed = RNG.integers(0, 256, nbytes, dtype=np.uint8)
+    assert np.array_equal(ctx.dvd_lpcm_unpack(packed, bits, channels), oracle.unpack_dvd_lpcm(packed, bits, channels))
+
+
+def test_dvd_lpcm_unpack_errors(ctx):
+    with pytest.raises(capi.SoundkitError, match="DVD LPCM ends with a partial sample block"):
+        ctx.dvd_lpcm_unpack(np.zeros(6, np.uint8), 16, 2)
+    with pytest.raises(capi.SoundkitError, match="DVD LPCM ends with a partial 24-bit sample block"):
+        ctx.dvd_lpcm_unpack(np.zeros(12, np.uint8), 24, 8)
+    with pytest.raises(capi.SoundkitError, match="20-bit DVD LPCM decoding is not implemented"):
+        ctx.dvd_lpcm_unpack(np.zeros(12, np.uint8), 20, 2)
+
+
+def test_dvd_lpcm24_is_an_involution_free_permutation_at_full_size(ctx):
+    """size-independent property on 48 MiB: the unpacker is a byte permutation (multiset preserved per group) and its
+    output reinterpreted as s24le equals (hi << 16 | mid << 8 | low) of the packed fields"""
+    n = 4 << 20  # groups
+    packed = RNG.integers(0, 256, n * 12, dtype=np.uint8)
+    out = ctx.dvd_lpcm_unpack(packed, 24, 2).reshape(n, 4, 3)
+    g = packed.reshape(n, 12)
+    assert np.array_equal(out[:, :, 2], g[:, 0:8:2]) and np.array_equal(out[:, :, 1], g[:, 1:8:2]) and np.array_equal(out[:, :, 0], g[:, 8:12])

@@ -263,3 +263,30 @@ def test_normalizer48k_error_arms_and_lengths(oracle):
         for frames in (1, 2, 3, 100, 1001):
             l, r = oracle.normalize48k([_pcm16_block(rate, [list(range(frames))])])
             assert len(l) == len(r) == max(1, int(np.floor(frames * 48000.0 / rate + 0.5))), (rate, frames)
+
+
+# ---------------------------------------------------------------------------------------------- 8(f) row 3: packet scalers, unpackers
+def test_packet_scalers_and_unpackers_known_answers(oracle):
+    """hand-computed from the reference source (no reference test pins these): soundkit/src/audio_packet.rs:105-124,
+    176-186; soundkit-decoder/src/lib.rs:362-367, 750-804"""
+    s16 = np.array([0, 32767, -32767, -32768, 1], "<i2").view(np.uint8)
+    got = oracle.flat("pkt_s16le_to_f32", s16)
+    assert got.tolist() == [0.0, 1.0, -1.0, float(np.float32(-32768.0) / np.float32(32767.0)), float(np.float32(1.0) / np.float32(32767.0))]
+    s24 = np.array([0xff, 0xff, 0x7f, 0x00, 0x00, 0x80, 0x00, 0x00, 0x40], np.uint8)
+    assert oracle.flat("pkt_s24le_to_f32", s24).tolist() == [8388607 / 8388608, -1.0, 0.5]
+    s32 = np.array([2147483647, -2147483648, 65536 * 3, -131074, 0], "<i4").view(np.uint8)
+    # (s * 32767) / 2147483647 in i64, truncating toward zero
+    assert oracle.flat("pkt_s32le_to_i16", s32).tolist() == [32767, -32767, 2, -1, 0]
+    f = np.array([1.0, -1.0, -1.5, 2.0, 0.5, float("nan"), float("inf"), -float("inf"), 0.99999], "<f4").view(np.uint8)
+    assert oracle.flat("pkt_f32le_to_i16", f).tolist() == [32767, -32767, -32768, 32767, 16383, 0, 32767, -32768, 32766]
+    assert oracle.flat("u8_to_s16", np.array([0, 127, 128, 129, 255], np.uint8)).tolist() == [-32768, -256, 0, 256, 32512]
+    # DVD LPCM 16-bit: byte swap; partial block -> Err
+    assert oracle.unpack_dvd_lpcm(np.array([0x12, 0x34, 0xab, 0xcd], np.uint8), 16, 2).tolist() == [0x34, 0x12, 0xcd, 0xab]
+    assert oracle.unpack_dvd_lpcm(np.zeros(6, np.uint8), 16, 2) is None
+    # 24-bit: group = 4 x (hi, mid) big-endian then 4 low bytes -> 4 x (low, mid, hi)
+    grp = np.array([0xA1, 0xA2, 0xB1, 0xB2, 0xC1, 0xC2, 0xD1, 0xD2, 0xA3, 0xB3, 0xC3, 0xD3], np.uint8)
+    assert oracle.unpack_dvd_lpcm(grp, 24, 2).tolist() == [0xA3, 0xA2, 0xA1, 0xB3, 0xB2, 0xB1, 0xC3, 0xC2, 0xC1, 0xD3, 0xD2, 0xD1]
+    assert oracle.unpack_dvd_lpcm(np.zeros(12, np.uint8), 24, 8) is None      # 8 channels: 24-byte blocks
+    assert oracle.unpack_dvd_lpcm(np.zeros(36, np.uint8), 24, 3) is not None  # 3 channels: 36-byte blocks
+    assert oracle.unpack_dvd_lpcm(np.zeros(24, np.uint8), 24, 3) is None
+    assert oracle.unpack_dvd_lpcm(np.zeros(12, np.uint8), 20, 2) is None      # "20-bit DVD LPCM decoding is not implemented"
