@@ -239,6 +239,26 @@ int sk_normalize_stream(sk_ctx*, const uint8_t* in, size_t bytes, int bits, int 
                         int channels, int scale_mode, uint32_t in_rate, uint32_t out_rate, int semantics,
                         int mix_mode, float* out, size_t out_cap_per_plane, size_t* n_out);
 
+/* ------------------------------------------------------------------ G.726 ADPCM */
+/* soundkit-g726/src/lib.rs: G726Core (:198-462) as SK_G726_STATE_INTS int32 words in the order
+ * yl yu dms dml ap a[2] b[6] pk[2] dq[6] sr[2] td.  bits = code size 2 / 3 / 4 / 5 (G726Rate::bits_per_sample, :84-91:
+ * 16 / 24 / 32 / 40 kbit/s); packing 0 = G726Packing::Left (`ffmpeg -f g726`), 1 = Right (`g726le`) (:191-197).
+ * Inputs must be whole code groups (1 / 3 / 1 / 5 bytes = 4 / 8 / 2 / 8 samples, :114-130): the Rust G726Decoder /
+ * G726Encoder keep the partial group in pending_bytes / pending_samples (:631-742, :821-860) and stay in the host layer. */
+#define SK_G726_STATE_INTS 24
+void sk_g726_state_init(int32_t* state);                 /* Default for G726Core, :214-230 */
+/* G726Decoder::decode_{i16,i32,f32} on whole groups (:821-951); out gets bytes / group_bytes * group_samples elements */
+int  sk_g726_decode(sk_ctx*, int bits, int packing, int32_t* state, const uint8_t* in, size_t bytes, int out_kind, void* out);
+/* G726Encoder::encode_{i16,i32} on whole groups (:700-738); out gets n / group_samples * group_bytes bytes */
+int  sk_g726_encode(sk_ctx*, int bits, int packing, int32_t* state, int in_kind, const void* in, size_t n, uint8_t* out);
+/* batched, device resident: n_streams independent streams (one thread per stream); in_stride / out_stride in bytes for
+ * code buffers and in ELEMENTS for sample buffers; state = [n_streams][SK_G726_STATE_INTS] device words carried across
+ * calls, or NULL to start every stream from the default state and discard it */
+int  sk_g726_decode_batch_dev(sk_ctx*, int bits, int packing, const uint8_t* in, size_t in_stride, size_t n_streams, size_t bytes,
+                              int out_kind, void* out, size_t out_stride, int32_t* state);
+int  sk_g726_encode_batch_dev(sk_ctx*, int bits, int packing, int in_kind, const void* in, size_t in_stride, size_t n_streams, size_t n,
+                              uint8_t* out, size_t out_stride, int32_t* state);
+
 /* ------------------------------------------------------------------ 48 kHz stereo normalizer */
 /* StreamingStereo48kNormalizer (soundkit/src/audio_pipeline.rs:256-394): decoder-convention conversion, mono
  * duplicated / first two channels, finite_pcm clamp, 2-tap linear interpolation to 48 kHz over the whole-stream

@@ -360,6 +360,39 @@ def unpack_dvd_lpcm(packed, bits, channels):
     return None if n == ERR else out[:n]
 
 
+G726_BITS = {16000: 2, 24000: 3, 32000: 4, 40000: 5}
+G726_GROUP = {2: (4, 1), 3: (8, 3), 4: (2, 1), 5: (8, 5)}  # bits -> (samples, bytes) per group
+
+
+class G726:
+    """G726Core + whole-group packing (soundkit-g726/src/lib.rs:215-596); state persists across calls"""
+
+    def __init__(self, bits, packing=0):
+        self.bits, self.packing = bits, packing
+        self.state = np.zeros(24, np.int32)
+        L = lib()
+        L.sko_g726_state_init.restype = None
+        L.sko_g726_state_init.argtypes = [C.c_void_p]
+        for f in (L.sko_g726_decode, L.sko_g726_encode):
+            f.restype = C.c_size_t
+            f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.sko_g726_state_init(_ptr(self.state))
+
+    def decode(self, data):
+        d = _bytes(data)
+        gs, gb = G726_GROUP[self.bits]
+        out = np.empty(d.size // gb * gs, np.int16)
+        n = lib().sko_g726_decode(self.bits, self.packing, _ptr(self.state), _ptr(d), d.size, _ptr(out))
+        return None if n == ERR else out[:n]
+
+    def encode(self, samples):
+        s = np.ascontiguousarray(samples, np.int16)
+        gs, gb = G726_GROUP[self.bits]
+        out = np.empty(s.size // gs * gb, np.uint8)
+        n = lib().sko_g726_encode(self.bits, self.packing, _ptr(self.state), _ptr(s), s.size, _ptr(out))
+        return None if n == ERR else out[:n]
+
+
 class Normalizer48k:
     """StreamingStereo48kNormalizer restatement (soundkit/src/audio_pipeline.rs:256-394).  push/finish return
     (left, right) float32 arrays (empty = Ok(None)) or raise ValueError(code) for the reference's Err arms."""

@@ -147,6 +147,12 @@ size_t sko_normalize_chain_mono(const uint8_t* in, size_t bytes, int bits, int f
                                 size_t channels, uint32_t in_rate, uint32_t out_rate, float* out,
                                 size_t out_cap);
 
+/* ---- 8(f) next row 4: G.726 ADPCM 16/24/32/40 kbit/s (soundkit-g726/src/lib.rs:215-860), g726.c ---- */
+#define SKO_G726_STATE_INTS 24
+void   sko_g726_state_init(int32_t* state);
+size_t sko_g726_decode(int bits, int packing, int32_t* state, const uint8_t* in, size_t bytes, int16_t* out);
+size_t sko_g726_encode(int bits, int packing, int32_t* state, const int16_t* in, size_t n, uint8_t* out);
+
 /* ---- 8(f) next row 3: packet scalers (soundkit/src/audio_packet.rs:105-124, 176-186, 243-254), AVI u8 (soundkit-decoder/
  * src/lib.rs:362-367) and unpack_dvd_lpcm (soundkit-decoder/src/lib.rs:750-804); pcm.c ---- */
 size_t sko_pkt_s16le_to_f32(const uint8_t* in, size_t bytes, float* out);

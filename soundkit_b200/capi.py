@@ -25,6 +25,8 @@ FLAT_OPS = ("i16le_to_f32", "s16le_to_i16", "s16be_to_i16", "s16le_to_i32", "s24
             "s32be_to_f32", "s32le_to_i16", "s32be_to_i16", "f32le_to_i16", "f32be_to_i16", "f32le_to_i32",
             "f32le_to_s24", "pkt_s16le_to_f32", "pkt_s24le_to_f32", "pkt_s32le_to_i16", "pkt_f32le_to_i16", "u8_to_s16")
 FLAT_OP = {name: i for i, name in enumerate(FLAT_OPS)}
+G726_GROUP = {2: (4, 1), 3: (8, 3), 4: (2, 1), 5: (8, 5)}  # code bits -> (samples, bytes) per group
+G726_LEFT, G726_RIGHT = 0, 1
 
 EXPORTS = (
     "sk_abi_version", "sk_ctx_create", "sk_ctx_destroy", "sk_last_error", "sk_ctx_set_stream", "sk_ctx_reset_stream",
@@ -41,6 +43,7 @@ EXPORTS = (
     "sk_norm48k_create", "sk_norm48k_destroy", "sk_norm48k_push", "sk_norm48k_finish", "sk_norm48k_source_frames",
     "sk_norm48k_output_frames", "sk_norm48k_source_sample_rate", "sk_norm48k_source_channels", "sk_norm48k_max_output",
     "sk_normalize48k_out_frames", "sk_normalize48k_batch_dev",
+    "sk_g726_state_init", "sk_g726_decode", "sk_g726_encode", "sk_g726_decode_batch_dev", "sk_g726_encode_batch_dev",
 )
 
 
@@ -129,6 +132,11 @@ def load():
         "sk_norm48k_max_output": (sz, [sz, u32]),
         "sk_normalize48k_out_frames": (sz, [sz, u32]),
         "sk_normalize48k_batch_dev": (i, [vp, vp, sz, sz, sz, i, i, i, i, u32, vp, sz, sz, psz]),
+        "sk_g726_state_init": (None, [vp]),
+        "sk_g726_decode": (i, [vp, i, i, vp, vp, sz, i, vp]),
+        "sk_g726_encode": (i, [vp, i, i, vp, i, vp, sz, vp]),
+        "sk_g726_decode_batch_dev": (i, [vp, i, i, vp, sz, sz, sz, i, vp, sz, vp]),
+        "sk_g726_encode_batch_dev": (i, [vp, i, i, i, vp, sz, sz, sz, vp, sz, vp]),
     }
     for name in EXPORTS:
         fn = getattr(L, name)  # AttributeError if the header and the library disagree
@@ -343,6 +351,35 @@ class Context:
 
     def resampler(self, in_rate, out_rate, channels, chunk):
         return Resampler(self, in_rate, out_rate, channels, chunk)
+
+    # -- G.726 ADPCM
+    def g726_state(self):
+        st = np.zeros(24, np.int32)
+        self.L.sk_g726_state_init(_p(st))
+        return st
+
+    def g726_decode(self, bits, packing, state, data, kind=KIND_I16):
+        d = _u8(data)
+        gs, gb = G726_GROUP.get(bits, (1, 1))  # an unknown code size is the library's error to report
+        out = np.empty(d.size // gb * gs, (np.int16, np.int32, np.float32)[kind])
+        self._ck(self.L.sk_g726_decode(self.h, bits, packing, _p(state), _p(d), d.size, kind, _p(out)))
+        return out
+
+    def g726_encode(self, bits, packing, state, samples):
+        s = np.ascontiguousarray(samples)
+        kind = KIND_I16 if s.dtype == np.int16 else KIND_I32
+        gs, gb = G726_GROUP.get(bits, (1, 1))
+        out = np.empty(s.size // gs * gb, np.uint8)
+        self._ck(self.L.sk_g726_encode(self.h, bits, packing, _p(state), kind, _p(s), s.size, _p(out)))
+        return out
+
+    def g726_decode_batch_dev(self, bits, packing, d_in, in_stride, n_streams, nbytes, kind, d_out, out_stride, d_state=None):
+        self._ck(self.L.sk_g726_decode_batch_dev(self.h, bits, packing, _p(d_in), in_stride, n_streams, nbytes, kind, _p(d_out), out_stride,
+                                                 _p(d_state)))
+
+    def g726_encode_batch_dev(self, bits, packing, kind, d_in, in_stride, n_streams, n, d_out, out_stride, d_state=None):
+        self._ck(self.L.sk_g726_encode_batch_dev(self.h, bits, packing, kind, _p(d_in), in_stride, n_streams, n, _p(d_out), out_stride,
+                                                 _p(d_state)))
 
     # -- 48 kHz stereo normalizer (StreamingStereo48kNormalizer)
     def normalizer48k(self):

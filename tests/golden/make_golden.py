@@ -10,6 +10,8 @@ here and committed together with this script:
   * CAF / MOV PCM payloads (4 800 stereo frames each) with the LE-canonical SHA-256 the reference asserts
     (soundkit-audio-demux/src/caf.rs:777-842, soundkit-audio-demux/src/lib.rs:5568-5690)
   * short slices of the s32le / 24-bit WAV / f32 WAV speech fixtures as realistic conversion inputs
+  * G.726 fixtures for 16/24/32/40 kbit/s + the reference's golden decoded WAV payloads
+    (testdata/g726/*, golden/g726/*.decoded.wav; soundkit-g726/src/lib.rs:1113-1145)
 
 Only DATA is copied, no reference source.  MANIFEST.json records the SHA-256 of every file.
 """
@@ -101,6 +103,12 @@ def main():
     put("linear32.s32le", rd(f"testdata/linear32/{NAME}.s32le")[:64000])
     put("wav_24.s24le", wav_payload(os.path.join(REF, f"testdata/wav_24/{NAME}.wav"))[:48000])
     put("wav_32f.f32le", wav_payload(os.path.join(REF, f"testdata/wav_32f/{NAME}.wav"))[:64000])
+
+    # G.726 fixtures (ffmpeg-encoded, left-justified packing) + the reference's golden decodes for all four rates
+    # (soundkit-g726/src/lib.rs:1113-1145): pins the ADPCM decoder restatement bit for bit
+    for r in ("16", "24", "32", "40"):
+        put(f"g726_{r}.g726", rd(f"testdata/g726/{NAME}_{r}.g726"))
+        put(f"g726_{r}.decoded.s16le", wav_payload(os.path.join(REF, f"golden/g726/{NAME}_{r}.decoded.wav")))
 
     endian = {}
     for name, kind, bps, be in (("pcm-s16be.caf", "s16", 2, True), ("pcm-s24le.caf", "s24", 3, False),

@@ -462,3 +462,102 @@ def test_dvd_lpcm24_is_an_involution_free_permutation_at_full_size(ctx):
     out = ctx.dvd_lpcm_unpack(packed, 24, 2).reshape(n, 4, 3)
     g = packed.reshape(n, 12)
     assert np.array_equal(out[:, :, 2], g[:, 0:8:2]) and np.array_equal(out[:, :, 1], g[:, 1:8:2]) and np.array_equal(out[:, :, 0], g[:, 8:12])
+
+
+# ---------------------------------------------------------------------------------------------- 8(f) row 4: G.726 ADPCM
+G726_RATES = [("16", 2), ("24", 3), ("32", 4), ("40", 5)]
+
+
+@pytest.mark.parametrize("suffix,bits", G726_RATES)
+def test_g726_golden_fixture_decode(ctx, suffix, bits):
+    """the reference's own fixtures: testdata/g726/*.g726 -> golden/g726/*.decoded.wav, pushed in 127-byte chunks"""
+    fixture = np.frombuffer(golden(f"g726_{suffix}.g726"), np.uint8)
+    want = np.frombuffer(golden(f"g726_{suffix}.decoded.s16le"), "<i2")
+    gs, gb = capi.G726_GROUP[bits]
+    st, pending, out = ctx.g726_state(), np.zeros(0, np.uint8), []
+    for i in range(0, fixture.size, 127):
+        buf = np.concatenate([pending, fixture[i:i + 127]])
+        whole = buf.size // gb * gb
+        out.append(ctx.g726_decode(bits, capi.G726_LEFT, st, buf[:whole]))
+        pending = buf[whole:]
+    assert pending.size == 0
+    assert np.array_equal(np.concatenate(out), want)
+
+
+@pytest.mark.parametrize("suffix,bits", G726_RATES)
+@pytest.mark.parametrize("packing", [0, 1])
+def test_g726_encode_decode_match_oracle(ctx, oracle, suffix, bits, packing):
+    gs, gb = capi.G726_GROUP[bits]
+    speech = np.frombuffer(golden("linear16_8.s16le"), "<i2")
+    noise = RNG.integers(-32768, 32768, 8 * 1000).astype(np.int16)  # full-range noise drives the clamps and the transition detector
+    for x in (speech[: speech.size // 8 * 8], noise):
+        want_codes = oracle.G726(bits, packing).encode(x)
+        st = ctx.g726_state()
+        got_codes = ctx.g726_encode(bits, packing, st, x)
+        assert np.array_equal(got_codes, want_codes)
+        og = oracle.G726(bits, packing)
+        og.encode(x)
+        assert np.array_equal(st, og.state)  # the carried predictor state too
+        for kind, name in ((capi.KIND_I16, "i16"), (capi.KIND_I32, "i32"), (capi.KIND_F32, "f32")):
+            got = ctx.g726_decode(bits, packing, ctx.g726_state(), want_codes, kind)
+            ref = oracle.G726(bits, packing).decode(want_codes)
+            if name == "i32":
+                ref = ref.astype(np.int32) << 16
+            elif name == "f32":
+                ref = ref.astype(np.float32) / np.float32(32768.0)
+            assert np.array_equal(got.view(np.uint8), ref.view(np.uint8)), name
+    # random code streams (not produced by any encoder) exercise states an encoder never reaches
+    codes = RNG.integers(0, 256, gb * 4001, dtype=np.uint8)
+    assert np.array_equal(ctx.g726_decode(bits, packing, ctx.g726_state(), codes), oracle.G726(bits, packing).decode(codes))
+    # i32 input: (s >> 16) as i16
+    x32 = RNG.integers(-2 ** 31, 2 ** 31, gs * 500, dtype=np.int64).astype(np.int32)
+    assert np.array_equal(ctx.g726_encode(bits, packing, ctx.g726_state(), x32), oracle.G726(bits, packing).encode((x32 >> 16).astype(np.int16)))
+
+
+def test_g726_argument_errors(ctx):
+    st = ctx.g726_state()
+    with pytest.raises(capi.SoundkitError, match="whole number of 3-byte code groups"):
+        ctx.g726_decode(3, 0, st, np.zeros(4, np.uint8))
+    with pytest.raises(capi.SoundkitError, match="whole number of 8-sample code groups"):
+        ctx.g726_encode(5, 0, st, np.zeros(12, np.int16))
+    with pytest.raises(capi.SoundkitError, match="code size must be 2, 3, 4 or 5"):
+        ctx.g726_decode(6, 0, st, np.zeros(4, np.uint8))
+
+
+@pytest.mark.parametrize("suffix,bits", G726_RATES)
+def test_g726_batch_dev_streams_are_independent_and_chunkable(oracle, suffix, bits):
+    """device-resident batch: every stream equals the oracle on its own data; splitting the batch call in two with the
+    carried state equals the single call (chunk-boundary invariance, the property soundkit-g726's streaming tests pin)"""
+    import torch
+    c = capi.Context(0)
+    c.use_torch_stream()
+    gs, gb = capi.G726_GROUP[bits]
+    S, groups = 300, 257
+    nbytes, n = groups * gb, groups * gs
+    stride = (nbytes + 15) // 16 * 16 + 16
+    codes = RNG.integers(0, 256, (S, stride), dtype=np.uint8)
+    d_codes = torch.from_numpy(codes).cuda()
+    ostride = (n + 7) // 8 * 8
+    d_out = torch.zeros((S, ostride), dtype=torch.int16, device="cuda")
+    c.g726_decode_batch_dev(bits, 0, d_codes, stride, S, nbytes, capi.KIND_I16, d_out, ostride)
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy()
+    for s in (0, 1, 31, 32, 150, S - 1):
+        assert np.array_equal(out[s, :n], oracle.G726(bits).decode(codes[s, :nbytes])), s
+    # two calls with carried state == one call
+    d_state = torch.zeros((S, 24), dtype=torch.int32, device="cuda")
+    d_state[:] = torch.from_numpy(c.g726_state()).cuda()
+    half = (groups // 2) * gb
+    d_out2 = torch.zeros_like(d_out)
+    c.g726_decode_batch_dev(bits, 0, d_codes, stride, S, half, capi.KIND_I16, d_out2, ostride, d_state)
+    c.g726_decode_batch_dev(bits, 0, d_codes[:, half:], stride, S, nbytes - half, capi.KIND_I16, d_out2[:, half // gb * gs:], ostride, d_state)
+    torch.cuda.synchronize()
+    assert torch.equal(d_out2[:, :n], d_out[:, :n])
+    # encode batch: re-encode the decoded streams, compare with the oracle per stream
+    d_enc = torch.zeros((S, stride), dtype=torch.uint8, device="cuda")
+    c.g726_encode_batch_dev(bits, 0, capi.KIND_I16, d_out, ostride, S, n, d_enc, stride)
+    torch.cuda.synchronize()
+    enc = d_enc.cpu().numpy()
+    for s in (0, 7, 33, S - 1):
+        assert np.array_equal(enc[s, :nbytes], oracle.G726(bits).encode(out[s, :n])), s
+    c.close()

@@ -290,3 +290,61 @@ def test_packet_scalers_and_unpackers_known_answers(oracle):
     assert oracle.unpack_dvd_lpcm(np.zeros(36, np.uint8), 24, 3) is not None  # 3 channels: 36-byte blocks
     assert oracle.unpack_dvd_lpcm(np.zeros(24, np.uint8), 24, 3) is None
     assert oracle.unpack_dvd_lpcm(np.zeros(12, np.uint8), 20, 2) is None      # "20-bit DVD LPCM decoding is not implemented"
+
+
+# ---------------------------------------------------------------------------------------------- 8(f) row 4: G.726
+G726_RATES = [("16", 2), ("24", 3), ("32", 4), ("40", 5)]
+
+
+@pytest.mark.parametrize("suffix,bits", G726_RATES)
+def test_g726_decoder_reproduces_reference_golden_wavs(oracle, suffix, bits):
+    """testdata/g726/<name>_{16,24,32,40}.g726 -> golden/g726/<name>_*.decoded.wav (soundkit-g726/src/lib.rs:1113-1145),
+    fed in 127-byte pushes like the reference test (the partial group is carried the way G726Decoder.pending_bytes does)"""
+    fixture = np.frombuffer(golden(f"g726_{suffix}.g726"), np.uint8)
+    want = np.frombuffer(golden(f"g726_{suffix}.decoded.s16le"), "<i2")
+    gs, gb = oracle.G726_GROUP[bits]
+    dec, pending, out = oracle.G726(bits), np.zeros(0, np.uint8), []
+    for i in range(0, fixture.size, 127):
+        buf = np.concatenate([pending, fixture[i:i + 127]])
+        whole = buf.size // gb * gb
+        out.append(dec.decode(buf[:whole]))
+        pending = buf[whole:]
+    got = np.concatenate(out)
+    assert pending.size == 0 and got.size == fixture.size // gb * gs == want.size
+    assert np.array_equal(got, want)
+
+
+def _g726_test_samples():  # soundkit-g726/src/lib.rs:1031-1038
+    idx = np.arange(397, dtype=np.float32)
+    phase = idx / np.float32(80.0) * np.float32(2.0 * np.pi)
+    return (np.sin(phase).astype(np.float32) * np.float32(10000.0)).astype(np.int16)
+
+
+@pytest.mark.parametrize("suffix,bits", G726_RATES)
+def test_g726_streaming_matches_whole_and_right_packing_round_trips(oracle, suffix, bits):
+    """streaming_encoder_matches_padded_whole_encode / streaming_decoder_matches_whole_decode (lib.rs:1080-1140 of the
+    reference tests), restated on the core with caller-side pending buffers"""
+    x = _g726_test_samples()
+    gs, gb = oracle.G726_GROUP[bits]
+    padded = np.concatenate([x, np.zeros((-x.size) % gs, np.int16)])
+    whole = oracle.G726(bits).encode(padded)
+    enc, pend, parts = oracle.G726(bits), np.zeros(0, np.int16), []
+    for i in range(0, x.size, 37):
+        buf = np.concatenate([pend, x[i:i + 37]])
+        k = buf.size // gs * gs
+        parts.append(enc.encode(buf[:k]))
+        pend = buf[k:]
+    if pend.size:
+        parts.append(enc.encode(np.concatenate([pend, np.zeros(gs - pend.size, np.int16)])))  # flush_into pads with zeros (:653-668)
+    assert np.array_equal(np.concatenate(parts), whole)
+    dec_whole = oracle.G726(bits).decode(whole)
+    dec, pendb, outs = oracle.G726(bits), np.zeros(0, np.uint8), []
+    for i in range(whole.size):  # one byte at a time
+        buf = np.concatenate([pendb, whole[i:i + 1]])
+        k = buf.size // gb * gb
+        outs.append(dec.decode(buf[:k]))
+        pendb = buf[k:]
+    assert np.array_equal(np.concatenate(outs), dec_whole)
+    right = oracle.G726(bits, 1).encode(padded)
+    assert np.array_equal(oracle.G726(bits, 1).decode(right), dec_whole)  # same codes, other bit order
+    assert np.any(dec_whole != 0)
