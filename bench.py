@@ -219,6 +219,16 @@ def extras(ctx, torch, peaks, only=None):
             res[f"convert_{name}_stereo_to_planar_f32"] = hbm_entry(nb, t, S * frames * 2)
             del raw
         del out
+    if want("g726"):
+        # G.726-32 decode/encode, 65 536 telephony streams x 4 s (one thread per stream; latency bound)
+        S, n = 65536, 32000
+        codes = torch.randint(0, 256, (S, n // 2), dtype=torch.uint8, device="cuda")
+        pcm = torch.empty((S, n), dtype=torch.int16, device="cuda")
+        t = timed(lambda: ctx.g726_decode_batch_dev(4, 0, codes, n // 2, S, n // 2, capi.KIND_I16, pcm, n), reps=3)
+        res["g726_32k_decode_i16"] = {"Msamples/s": S * n / t / 1e6, "GB/s": S * n * 2.5 / t / 1e9, "streams": S}
+        t = timed(lambda: ctx.g726_encode_batch_dev(4, 0, capi.KIND_I16, pcm, n, S, n, codes, n // 2), reps=3)
+        res["g726_32k_encode_i16"] = {"Msamples/s": S * n / t / 1e6, "GB/s": S * n * 2.5 / t / 1e9, "streams": S}
+        del codes, pcm
     if want("norm48k"):
         # StreamingStereo48kNormalizer, 64 whole streams x 60 s s16le stereo 44.1 kHz -> f32 stereo 48 kHz
         S, frames, rate = 64, 2646000, 44100

@@ -164,6 +164,43 @@ PYBIND11_MODULE(_host, m) {
         .def("decode_f32", [](G711Decoder& d, const py::buffer& in, size_t out_len, bool fec) {
             auto b = to_bytes(in); std::vector<float> out(out_len); size_t n = d.decode_f32(b.data(), b.size(), out.data(), out.size(), fec); return py::make_tuple(n, arr(out)); });
 
+    // ---- soundkit_g726
+    {
+        auto g6 = m.def_submodule("g726");
+        using namespace soundkit_g726;
+        py::enum_<G726Rate>(g6, "G726Rate").value("Rate16000", G726Rate::Rate16000).value("Rate24000", G726Rate::Rate24000)
+            .value("Rate32000", G726Rate::Rate32000).value("Rate40000", G726Rate::Rate40000);
+        py::enum_<G726Packing>(g6, "G726Packing").value("Left", G726Packing::Left).value("Right", G726Packing::Right);
+        g6.def("samples_per_byte_group", &samples_per_byte_group);
+        g6.def("bytes_per_group", &bytes_per_group);
+        g6.def("from_bitrate", &rate_from_bitrate);
+        py::class_<G726Encoder>(g6, "G726Encoder")
+            .def(py::init<uint32_t, uint32_t, uint32_t, uint32_t, uint32_t>())
+            .def_static("try_new", &G726Encoder::try_new)
+            .def("rate", &G726Encoder::rate).def("packing", &G726Encoder::packing).def("reset", &G726Encoder::reset)
+            .def("encode_i16", [](G726Encoder& e, const std::vector<int16_t>& in, size_t cap) {
+                std::vector<uint8_t> out(cap); size_t n = e.encode_i16(in.data(), in.size(), out.data(), cap); out.resize(n);
+                return py::bytes((const char*)out.data(), out.size()); })
+            .def("encode_i32", [](G726Encoder& e, const std::vector<int32_t>& in, size_t cap) {
+                std::vector<uint8_t> out(cap); size_t n = e.encode_i32(in.data(), in.size(), out.data(), cap); out.resize(n);
+                return py::bytes((const char*)out.data(), out.size()); })
+            .def("encode_to_vec", [](G726Encoder& e, const std::vector<int16_t>& in) {
+                std::vector<uint8_t> out; e.encode_to_vec(in, out); return py::bytes((const char*)out.data(), out.size()); })
+            .def("flush_to_vec", [](G726Encoder& e) { std::vector<uint8_t> out; e.flush_to_vec(out); return py::bytes((const char*)out.data(), out.size()); })
+            .def("flush_into", [](G726Encoder& e, size_t cap) { std::vector<uint8_t> out(cap); size_t n = e.flush_into(out.data(), cap); out.resize(n);
+                return py::bytes((const char*)out.data(), out.size()); });
+        py::class_<G726Decoder>(g6, "G726Decoder")
+            .def_static("try_new", &G726Decoder::try_new)
+            .def_static("new_32k_left", &G726Decoder::new_32k_left).def_static("new_32k_right", &G726Decoder::new_32k_right)
+            .def("sample_rate", &G726Decoder::sample_rate).def("channels", &G726Decoder::channels).def("flush", &G726Decoder::flush)
+            .def("decode_i16", [](G726Decoder& d, const py::buffer& in, size_t cap, bool fec) {
+                auto b = to_bytes(in); std::vector<int16_t> out(cap); size_t n = d.decode_i16(b.data(), b.size(), out.data(), cap, fec); out.resize(n); return arr(out); })
+            .def("decode_i32", [](G726Decoder& d, const py::buffer& in, size_t cap, bool fec) {
+                auto b = to_bytes(in); std::vector<int32_t> out(cap); size_t n = d.decode_i32(b.data(), b.size(), out.data(), cap, fec); out.resize(n); return arr(out); })
+            .def("decode_f32", [](G726Decoder& d, const py::buffer& in, size_t cap, bool fec) {
+                auto b = to_bytes(in); std::vector<float> out(cap); size_t n = d.decode_f32(b.data(), b.size(), out.data(), cap, fec); out.resize(n); return arr(out); });
+    }
+
     // ---- soundkit_decoder output stage
     auto d = m.def_submodule("decoder");
     using namespace soundkit_decoder;

@@ -445,6 +445,127 @@ private:
 };
 }  // namespace soundkit_g711
 
+// ---- soundkit_g726 (soundkit-g726/src/lib.rs) — SURVEY.md 8(f) row 4 -----------------------------------------------
+namespace soundkit_g726 {
+using soundkit::Error;
+using soundkit::Gpu;
+constexpr uint32_t G726_SAMPLE_RATE = 8000;  // :7
+constexpr uint8_t G726_CHANNELS = 1;         // :8
+enum class G726Rate { Rate16000, Rate24000, Rate32000, Rate40000 };  // :62-72
+enum class G726Packing { Left = 0, Right = 1 };                      // :191-197
+inline G726Rate rate_from_bitrate(uint32_t b) {                      // :75-82
+    return b == 16000 ? G726Rate::Rate16000 : (b == 24000 ? G726Rate::Rate24000 : (b == 40000 ? G726Rate::Rate40000 : G726Rate::Rate32000));
+}
+inline size_t bits_per_sample(G726Rate r) { return 2 + (size_t)r; }   // :84-91
+inline uint32_t bit_rate(G726Rate r) { return 16000u + 8000u * (uint32_t)r; }
+inline size_t samples_per_byte_group(G726Rate r) { static const size_t t[4] = {4, 8, 2, 8}; return t[(int)r]; }  // :104-111
+inline size_t bytes_per_group(G726Rate r) { static const size_t t[4] = {1, 3, 1, 5}; return t[(int)r]; }         // :113-120
+
+class G726Encoder {  // :598-742, impl soundkit::audio_packet::Encoder; the partial group stays here (pending_samples)
+public:
+    static G726Encoder try_new(G726Rate rate, G726Packing packing) { return G726Encoder(rate, packing); }
+    static G726Encoder new_32k_left() { return try_new(G726Rate::Rate32000, G726Packing::Left); }
+    static G726Encoder new_32k_right() { return try_new(G726Rate::Rate32000, G726Packing::Right); }
+    static G726Encoder new_16k_left() { return try_new(G726Rate::Rate16000, G726Packing::Left); }
+    static G726Encoder new_24k_left() { return try_new(G726Rate::Rate24000, G726Packing::Left); }
+    static G726Encoder new_40k_left() { return try_new(G726Rate::Rate40000, G726Packing::Left); }
+    // Encoder::new(sample_rate, bits_per_sample, channels, frame_size, bitrate), :681-692
+    G726Encoder(uint32_t, uint32_t, uint32_t, uint32_t, uint32_t bitrate) : G726Encoder(rate_from_bitrate(bitrate), G726Packing::Left) {}
+    G726Rate rate() const { return rate_; }
+    G726Packing packing() const { return packing_; }
+    void init() {}
+    void reset() { sk_g726_state_init(core_); pending_.clear(); }  // :740-744
+    size_t encode_i16(const int16_t* input, size_t n, uint8_t* output, size_t cap) {  // :700-733
+        const size_t required = required_encode_bytes(n, false);
+        if (cap < required) throw Error("Output buffer too small for G.726 encode: need " + std::to_string(required) + ", have " + std::to_string(cap));
+        const size_t gs = samples_per_byte_group(rate_);
+        std::vector<int16_t> samples(pending_);
+        samples.insert(samples.end(), input, input + n);
+        const size_t complete = samples.size() / gs * gs;
+        size_t written = 0;
+        if (complete) written = encode_complete(samples.data(), complete, output);
+        pending_.assign(samples.begin() + complete, samples.end());
+        return written;
+    }
+    size_t encode_i32(const int32_t* input, size_t n, uint8_t* output, size_t cap) {  // :735-738
+        std::vector<int16_t> s(n);
+        for (size_t i = 0; i < n; i++) s[i] = (int16_t)(input[i] >> 16);
+        return encode_i16(s.data(), n, output, cap);
+    }
+    size_t encode_to_vec(const std::vector<int16_t>& input, std::vector<uint8_t>& output) {  // :635-642
+        const size_t start = output.size();
+        output.resize(start + required_encode_bytes(input.size(), false));
+        const size_t w = encode_i16(input.data(), input.size(), output.data() + start, output.size() - start);
+        output.resize(start + w);
+        return w;
+    }
+    size_t flush_into(uint8_t* output, size_t cap) {  // :644-662: zero-pads the pending samples to one group
+        const size_t required = required_encode_bytes(0, true);
+        if (cap < required) throw Error("Output buffer too small for G.726 flush: need " + std::to_string(required) + ", have " + std::to_string(cap));
+        if (pending_.empty()) return 0;
+        std::vector<int16_t> samples(pending_);
+        samples.resize(samples_per_byte_group(rate_), 0);
+        pending_.clear();
+        return encode_complete(samples.data(), samples.size(), output);
+    }
+    size_t flush_to_vec(std::vector<uint8_t>& output) {  // :664-671
+        const size_t start = output.size();
+        output.resize(start + required_encode_bytes(0, true));
+        const size_t w = flush_into(output.data() + start, output.size() - start);
+        output.resize(start + w);
+        return w;
+    }
+private:
+    G726Encoder(G726Rate r, G726Packing p) : rate_(r), packing_(p) { sk_g726_state_init(core_); }
+    size_t required_encode_bytes(size_t input_samples, bool flush) const {  // :681-690
+        const size_t gs = samples_per_byte_group(rate_), total = pending_.size() + input_samples;
+        return (flush ? (total + gs - 1) / gs : total / gs) * bytes_per_group(rate_);
+    }
+    size_t encode_complete(const int16_t* s, size_t n, uint8_t* out) {
+        Gpu::check(sk_g726_encode(Gpu::ctx(), (int)bits_per_sample(rate_), (int)packing_, core_, SK_KIND_I16, s, n, out));
+        return n / samples_per_byte_group(rate_) * bytes_per_group(rate_);
+    }
+    G726Rate rate_; G726Packing packing_;
+    int32_t core_[SK_G726_STATE_INTS];
+    std::vector<int16_t> pending_;
+};
+
+class G726Decoder {  // :746-951, impl soundkit::audio_packet::Decoder (fec ignored); pending_bytes stays here
+public:
+    static G726Decoder try_new(G726Rate rate, G726Packing packing) { return G726Decoder(rate, packing); }
+    static G726Decoder new_32k_left() { return try_new(G726Rate::Rate32000, G726Packing::Left); }
+    static G726Decoder new_32k_right() { return try_new(G726Rate::Rate32000, G726Packing::Right); }
+    static G726Decoder new_16k_left() { return try_new(G726Rate::Rate16000, G726Packing::Left); }
+    static G726Decoder new_24k_left() { return try_new(G726Rate::Rate24000, G726Packing::Left); }
+    static G726Decoder new_40k_left() { return try_new(G726Rate::Rate40000, G726Packing::Left); }
+    uint32_t sample_rate() const { return G726_SAMPLE_RATE; }
+    uint8_t channels() const { return G726_CHANNELS; }
+    G726Rate rate() const { return rate_; }
+    G726Packing packing() const { return packing_; }
+    void flush() const {  // :802-811
+        if (!pending_.empty()) throw Error("G.726 stream ended with " + std::to_string(pending_.size()) + " trailing partial-packet byte(s)");
+    }
+    size_t decode_i16(const uint8_t* in, size_t n, int16_t* out, size_t cap, bool) { return run(in, n, out, cap, SK_KIND_I16); }
+    size_t decode_i32(const uint8_t* in, size_t n, int32_t* out, size_t cap, bool) { return run(in, n, out, cap, SK_KIND_I32); }
+    size_t decode_f32(const uint8_t* in, size_t n, float* out, size_t cap, bool) { return run(in, n, out, cap, SK_KIND_F32); }
+private:
+    G726Decoder(G726Rate r, G726Packing p) : rate_(r), packing_(p) { sk_g726_state_init(core_); }
+    size_t run(const uint8_t* in, size_t n, void* out, size_t cap, int kind) {  // :821-860
+        const size_t gb = bytes_per_group(rate_), total = pending_.size() + n;
+        const size_t complete = total / gb * gb, required = complete / gb * samples_per_byte_group(rate_);
+        if (cap < required) throw Error("Output buffer too small for G.726 decode: need " + std::to_string(required) + ", have " + std::to_string(cap));
+        std::vector<uint8_t> bytes(pending_);
+        bytes.insert(bytes.end(), in, in + n);
+        if (complete) Gpu::check(sk_g726_decode(Gpu::ctx(), (int)bits_per_sample(rate_), (int)packing_, core_, bytes.data(), complete, kind, out));
+        pending_.assign(bytes.begin() + complete, bytes.end());
+        return required;
+    }
+    G726Rate rate_; G726Packing packing_;
+    int32_t core_[SK_G726_STATE_INTS];
+    std::vector<uint8_t> pending_;
+};
+}  // namespace soundkit_g726
+
 // ---- soundkit-decoder output-conversion stage (soundkit-decoder/src/lib.rs) ---------------------------------------
 namespace soundkit_decoder {
 using soundkit::AudioData;

@@ -426,3 +426,93 @@ def test_streaming_normalizer_error_strings():  # audio_pipeline.rs:288-309, 366
     assert (nz.source_sample_rate(), nz.source_channels(), nz.source_frames()) == (8000, 1, 1)
     tail = nz.finish()
     assert len(tail[0]) == 6 and nz.output_frames() == 6  # round(1 * 48000 / 8000)
+
+
+# ---------------------------------------------------------------------------------------------- GPU: soundkit_g726 (8f row 4)
+G6 = H.g726
+G726_RATES = [(G6.G726Rate.Rate16000, "16"), (G6.G726Rate.Rate24000, "24"), (G6.G726Rate.Rate32000, "32"), (G6.G726Rate.Rate40000, "40")]
+
+
+def g726_samples():  # soundkit-g726/src/lib.rs:1031-1038
+    idx = np.arange(397, dtype=np.float32)
+    return (np.sin(idx / np.float32(80.0) * np.float32(2.0 * math.pi)).astype(np.float32) * np.float32(10000.0)).astype(np.int16).tolist()
+
+
+def g726_encode_samples(x, rate, packing):  # encode_samples, lib.rs:1069-1077
+    enc = G6.G726Encoder.try_new(rate, packing)
+    out = b""
+    for i in range(0, len(x), 37):
+        out += enc.encode_to_vec(x[i:i + 37])
+    return out + enc.flush_to_vec()
+
+
+@pytest.mark.gpu
+def test_g726_streaming_encoder_matches_padded_whole_encode_for_all_rates():  # lib.rs:1079-1108
+    x = g726_samples()
+    for rate, _ in G726_RATES:
+        gs, gb = G6.samples_per_byte_group(rate), G6.bytes_per_group(rate)
+        padded = x + [0] * ((-len(x)) % gs)
+        whole = G6.G726Encoder.try_new(rate, G6.G726Packing.Left).encode_i16(padded, len(padded) // gs * gb)
+        enc = G6.G726Encoder.try_new(rate, G6.G726Packing.Left)
+        chunked = b""
+        for i in range(0, len(x), 37):
+            chunked += enc.encode_i16(x[i:i + 37], 64)
+        chunked += enc.flush_to_vec()
+        assert chunked == whole, rate
+
+
+@pytest.mark.gpu
+def test_g726_streaming_decoder_matches_whole_decode_for_all_rates():  # lib.rs:1110-1140
+    for rate, _ in G726_RATES:
+        gs, gb = G6.samples_per_byte_group(rate), G6.bytes_per_group(rate)
+        encoded = g726_encode_samples(g726_samples(), rate, G6.G726Packing.Left)
+        whole = G6.G726Decoder.try_new(rate, G6.G726Packing.Left).decode_i16(encoded, len(encoded) // gb * gs, False)
+        dec = G6.G726Decoder.try_new(rate, G6.G726Packing.Left)
+        chunked = []
+        for i in range(len(encoded)):
+            chunked += dec.decode_i16(encoded[i:i + 1], 64, False).tolist()
+        dec.flush()
+        assert chunked == whole.tolist(), rate
+
+
+@pytest.mark.gpu
+def test_g726_right_packing_round_trips_and_trait_outputs():  # lib.rs:1142-1190
+    encoded = g726_encode_samples(g726_samples(), G6.G726Rate.Rate32000, G6.G726Packing.Right)
+    decoded = G6.G726Decoder.new_32k_right().decode_i16(encoded, len(encoded) * 2, False)
+    assert len(decoded) == len(encoded) * 2 and np.any(decoded != 0)
+    encoded = g726_encode_samples(g726_samples(), G6.G726Rate.Rate32000, G6.G726Packing.Left)
+    n = len(encoded) * 2
+    i16 = G6.G726Decoder.new_32k_left().decode_i16(encoded, n, False)
+    i32 = G6.G726Decoder.new_32k_left().decode_i32(encoded, n, False)
+    f32 = G6.G726Decoder.new_32k_left().decode_f32(encoded, n, False)
+    assert len(i16) == len(i32) == len(f32) == n
+    assert np.array_equal(i32, i16.astype(np.int32) << 16)
+    assert np.all(np.abs(f32 - i16.astype(np.float32) / np.float32(32768.0)) < np.finfo(np.float32).eps)
+
+
+@pytest.mark.gpu
+def test_g726_decode_fixture_golden_and_error_strings():  # lib.rs:1113-1145 of the reference tests; error texts :644-668, :700-709, :802-833
+    for rate, suffix in G726_RATES:
+        gs, gb = G6.samples_per_byte_group(rate), G6.bytes_per_group(rate)
+        fixture = golden(f"g726_{suffix}.g726")
+        dec = G6.G726Decoder.try_new(rate, G6.G726Packing.Left)
+        decoded = []
+        for i in range(0, len(fixture), 127):
+            decoded.append(dec.decode_i16(fixture[i:i + 127], 512, False))
+        dec.flush()
+        decoded = np.concatenate(decoded)
+        assert len(decoded) == len(fixture) // gb * gs
+        assert decoded.astype("<i2").tobytes() == golden(f"g726_{suffix}.decoded.s16le")
+    with pytest.raises(H.SoundkitError, match=r"Output buffer too small for G.726 decode: need 8, have 7"):
+        G6.G726Decoder.try_new(G6.G726Rate.Rate24000, G6.G726Packing.Left).decode_i16(bytes(3), 7, False)
+    with pytest.raises(H.SoundkitError, match=r"Output buffer too small for G.726 encode: need 5, have 4"):
+        G6.G726Encoder.try_new(G6.G726Rate.Rate40000, G6.G726Packing.Left).encode_i16([0] * 8, 4)
+    d = G6.G726Decoder.try_new(G6.G726Rate.Rate40000, G6.G726Packing.Left)
+    assert len(d.decode_i16(bytes(7), 64, False)) == 8
+    with pytest.raises(H.SoundkitError, match=r"G.726 stream ended with 2 trailing partial-packet byte\(s\)"):
+        d.flush()
+    e = G6.G726Encoder.try_new(G6.G726Rate.Rate16000, G6.G726Packing.Left)
+    assert e.encode_i16([1, 2, 3], 8) == b""
+    with pytest.raises(H.SoundkitError, match=r"Output buffer too small for G.726 flush: need 1, have 0"):
+        e.flush_into(0)
+    assert G6.from_bitrate(24000) == G6.G726Rate.Rate24000 and G6.from_bitrate(12345) == G6.G726Rate.Rate32000
