@@ -268,10 +268,11 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from soundkit_b200 import shard
+    numa_node = shard.bind_to_gpu_numa_node(local) if world > 1 else None  # before any pinned allocation
     ctx = capi.Context(local)
     ctx.use_torch_stream()
 
-    from soundkit_b200 import shard
     # weak scaling: the job is a batch of streams_per_gpu x world streams; rank g owns the contiguous range
     # [g*S/G, (g+1)*S/G) of it and nothing crosses NVLink on the data path
     lo, hi = shard.stream_range(args.streams * world, world, rank)
@@ -359,7 +360,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (uniform random s24 samples, full range)",
             "config": config_dict(args, frames, n_out), "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": S * frames * CHANNELS * 3,
-                    "d2h_bytes_per_step": S * n_out * 4, "steps": e2e_steps, "api": "sk_normalize_batch (host pointers, pinned)",
+                    "d2h_bytes_per_step": S * n_out * 4, "steps": e2e_steps, "api": "sk_normalize_batch (host pointers, pinned)", "numa_node": numa_node,
                     "matches_device_path": same},
             "gpu_launches": launches, "roofline": roofline}
     if world == 1 and not args.no_cpu:

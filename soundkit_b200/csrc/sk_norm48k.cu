@@ -114,6 +114,176 @@ norm48k_kernel(const __grid_constant__ N48Src src, unsigned long long o_start, u
     }
 }
 
+// Tiled form (the fast path): a CTA owns kN48Tile consecutive outputs of one stream at a time.  The source bytes those
+// outputs touch are one contiguous run, copied into shared memory with coalesced 128-bit loads (the gathers of the
+// direct kernel above become shared-memory reads).  Positions AND the byte offsets of the frames they select are
+// computed once per thread and reused for every stream of the CTA's grid.y slice, and the sample format is a template
+// parameter, so the per-stream work of an output is 4 shared-memory loads, 4 conversions and the lerp.
+constexpr int kN48Tile = kN48Threads * 4;
+
+// W sample bytes at shared-memory address p (2- / 4-byte aligned for W = 2 / 4, any alignment for W = 3)
+template <int W>
+__device__ __forceinline__ uint32_t n48_lds(const uint8_t* p) {
+    if (W == 2) return *reinterpret_cast<const uint16_t*>(p);
+    if (W == 4) return *reinterpret_cast<const uint32_t*>(p);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>((uintptr_t)p & ~(uintptr_t)3);
+    return __funnelshift_r(q[0], q[1], 8 * (int)((uintptr_t)p & 3));  // staged run has 16 spare bytes behind it
+}
+template <int W, bool BE, bool FLT>
+__device__ __forceinline__ float n48_cvt(uint32_t u) {  // pcm_sample_to_f32 (:176-227) + finite_pcm
+    if (W == 2) {
+        if (BE) u = __byte_perm(u, 0, 0x3201);
+        return __fmul_rn((float)(int16_t)(u & 0xffffu), 1.0f / 32768.0f);  // always finite, |x| <= 1
+    }
+    if (W == 3) {
+        const uint32_t v = BE ? __byte_perm(u, 0, 0x0124) : __byte_perm(u, 0, 0x2104);  // sample in bytes 1..3
+        return __fmul_rn((float)(((int32_t)v) >> 8), 1.0f / 8388608.0f);
+    }
+    if (BE) u = bswap32(u);
+    if (FLT) return n48_finite_pcm(__uint_as_float(u));
+    return __fmul_rn(__int2float_rn((int32_t)u), 4.656612873077393e-10f);
+}
+
+// one frame (left, right) at shared-memory address p.  ST = the stream has >= 2 channels (else right = left).
+template <int W, bool BE, bool FLT, bool ST>
+__device__ __forceinline__ void n48_frame(const uint8_t* p, float& l, float& r) {
+    if (W == 2) {
+        if (ST) {  // both channels in one aligned 32-bit word when the frame is 4 bytes; two halfword loads otherwise
+            const uint32_t lo = *reinterpret_cast<const uint16_t*>(p), hi = *reinterpret_cast<const uint16_t*>(p + 2);
+            l = n48_cvt<2, BE, FLT>(lo); r = n48_cvt<2, BE, FLT>(hi);
+        } else { l = r = n48_cvt<2, BE, FLT>(*reinterpret_cast<const uint16_t*>(p)); }
+    } else {
+        l = n48_cvt<W, BE, FLT>(n48_lds<W>(p));
+        r = ST ? n48_cvt<W, BE, FLT>(n48_lds<W>(p + W)) : l;
+    }
+}
+__device__ __forceinline__ float n48_clamp1(float x) { return fminf(fmaxf(x, -1.0f), 1.0f); }  // finite_pcm of a finite value
+
+constexpr int kN48MaxVec = 4;  // 128-bit vectors of one staged run a thread may hold in registers (prefetch of the next stream)
+
+// Outputs of a tile are dealt to threads round-robin (thread t owns outputs t, t + 256, t + 512, t + 768 of the tile):
+// consecutive lanes read consecutive source frames (conflict-free shared-memory reads) and write consecutive floats
+// (one 128-byte line per warp store).  The staged run is double buffered: the global loads of the NEXT stream are in
+// flight while the current stream is interpolated, and there is one barrier per stream.
+template <int W, bool BE, bool FLT, bool ST>
+__global__ void __launch_bounds__(kN48Threads)
+norm48k_tile_kernel(const __grid_constant__ N48Src src, unsigned long long o_start, unsigned long long n_lerp, unsigned long long n_total,
+                    unsigned rate, float prev_l, float prev_r, float* __restrict__ out_l, float* __restrict__ out_r, long long out_stride,
+                    unsigned n_streams, float* __restrict__ final_lr, int buf_bytes) {
+    extern __shared__ __align__(16) uint8_t n48_raw[];
+    const unsigned long long t0 = (unsigned long long)blockIdx.x * kN48Tile;   // first output of the tile
+    const bool writes_final = final_lr != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    const bool passthrough = rate == 48000u;
+    auto lower_of = [&](unsigned long long o, float* frac) -> long long {
+        if (passthrough) { if (frac) *frac = 0.0f; return (long long)(o - src.start_frame); }
+        const double pos = __ddiv_rn(__dmul_rn((double)o, (double)rate), 48000.0);
+        const double fl = floor(pos);
+        if (frac) *frac = __double2float_rn(__dsub_rn(pos, fl));
+        return (long long)((unsigned long long)fl - src.start_frame);
+    };
+    // source frames of the tile's interpolated outputs: [f_lo, f_hi] (local indices, clipped to the buffer)
+    const unsigned long long t_last = min(n_lerp, t0 + kN48Tile);  // one past the tile's last interpolated output
+    long long f_lo = 0, f_hi = -1, first_lower = 0;
+    if (t_last > t0) {
+        first_lower = lower_of(o_start + t0, nullptr);
+        f_lo = max(0ll, first_lower);
+        f_hi = min((long long)src.frames - 1, lower_of(o_start + t_last - 1, nullptr) + (passthrough ? 0 : 1));
+    }
+    // the common tile: every output interpolated from frames inside this buffer -> no per-output special cases
+    const bool plain = t0 + kN48Tile <= n_lerp && first_lower >= 0 && !writes_final && t0 + kN48Tile <= n_total;
+    const int fb = src.channels * src.width;
+    int off[4];   // byte offset of the output's lower frame from frame f_lo; -1: the carried previous frame; -2: tail output
+    float fr[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const unsigned long long i = t0 + (unsigned)(k * kN48Threads) + threadIdx.x;
+        const long long f = lower_of(o_start + i, &fr[k]);
+        off[k] = (i >= n_lerp) ? -2 : (f < 0 ? -1 : (int)(f - f_lo) * fb);
+    }
+    bool need_last = writes_final;
+#pragma unroll
+    for (int k = 0; k < 4; k++) need_last |= off[k] == -2 && t0 + (unsigned)(k * kN48Threads) + threadIdx.x < n_total;
+
+    // ---- staging helpers: the run [f_lo, f_hi] of stream s as 16-byte vectors around it
+    uint4 pre[kN48MaxVec];
+    auto run_of = [&](unsigned s, const uint8_t*& a0, int& nvec, long long& run, int& skew) {
+        const uint8_t* sbase = src.base + (long long)s * src.stream_stride;
+        const uint8_t* g0 = sbase + f_lo * fb;
+        a0 = reinterpret_cast<const uint8_t*>((uintptr_t)g0 & ~(uintptr_t)15);
+        skew = (int)(g0 - a0);
+        run = f_hi >= f_lo ? (sbase + (f_hi + 1) * fb) - a0 : 0;
+        const long long safe = (sbase + (long long)src.frames * fb) - a0;  // never read past the caller's buffer
+        nvec = (int)(min((run + 15) >> 4, safe >> 4));
+    };
+    auto prefetch = [&](unsigned s) {
+        const uint8_t* a0; int nvec, skew; long long run;
+        run_of(s, a0, nvec, run, skew);
+#pragma unroll
+        for (int j = 0; j < kN48MaxVec; j++) {
+            const int v = threadIdx.x + j * kN48Threads;
+            if (v < nvec) pre[j] = ld_stream_v4_nv(reinterpret_cast<const uint4*>(a0) + v);
+        }
+    };
+    auto commit = [&](unsigned s, uint8_t* buf) {  // registers -> shared memory, plus the bytes after the last whole vector
+        const uint8_t* a0; int nvec, skew; long long run;
+        run_of(s, a0, nvec, run, skew);
+#pragma unroll
+        for (int j = 0; j < kN48MaxVec; j++) {
+            const int v = threadIdx.x + j * kN48Threads;
+            if (v < nvec) reinterpret_cast<uint4*>(buf)[v] = pre[j];
+        }
+        for (long long b = (long long)nvec * 16 + threadIdx.x; b < run; b += kN48Threads) buf[b] = a0[b];
+        return skew;
+    };
+
+    unsigned s = blockIdx.y;
+    if (s < n_streams) prefetch(s);
+    int cur = 0;
+    for (; s < n_streams; s += gridDim.y, cur ^= 1) {
+        uint8_t* buf = n48_raw + cur * buf_bytes;
+        const int skew = commit(s, buf);
+        __syncthreads();  // buf complete; the other buffer (read two streams ago) is free for the next commit
+        if (s + gridDim.y < n_streams) prefetch(s + gridDim.y);
+        const uint8_t* sm = buf + skew;  // frame f_lo
+        float* pl = out_l + (long long)s * out_stride + t0 + threadIdx.x;
+        float* pr = out_r + (long long)s * out_stride + t0 + threadIdx.x;
+        if (plain) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float ll, rl, lu, ru;
+                n48_frame<W, BE, FLT, ST>(sm + off[k], ll, rl);
+                if (passthrough) { pl[k * kN48Threads] = ll; pr[k * kN48Threads] = rl; continue; }
+                n48_frame<W, BE, FLT, ST>(sm + off[k] + fb, lu, ru);
+                pl[k * kN48Threads] = n48_clamp1(__fadd_rn(ll, __fmul_rn(__fsub_rn(lu, ll), fr[k])));
+                pr[k * kN48Threads] = n48_clamp1(__fadd_rn(rl, __fmul_rn(__fsub_rn(ru, rl), fr[k])));
+            }
+        } else {
+            const uint8_t* sbase = src.base + (long long)s * src.stream_stride;
+            float last_l = prev_l, last_r = prev_r;
+            if (need_last && src.frames) { last_l = n48_sample(sbase, src, src.frames - 1, 0); last_r = n48_sample(sbase, src, src.frames - 1, src.channels > 1 ? 1 : 0); }
+            if (writes_final) { final_lr[2 * s] = last_l; final_lr[2 * s + 1] = last_r; }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned long long i = t0 + (unsigned)(k * kN48Threads) + threadIdx.x;
+                if (i >= n_total) continue;
+                float o_l, o_r;
+                if (off[k] == -2) { o_l = last_l; o_r = last_r; }  // finish(): vec![previous; remaining]
+                else {
+                    float ll = prev_l, rl = prev_r, lu, ru;
+                    if (off[k] >= 0) n48_frame<W, BE, FLT, ST>(sm + off[k], ll, rl);
+                    if (passthrough) { o_l = ll; o_r = rl; }
+                    else {
+                        n48_frame<W, BE, FLT, ST>(off[k] < 0 ? sm : sm + off[k] + fb, lu, ru);  // upper = lower + 1 (frame 0 after the carried one)
+                        o_l = n48_clamp1(__fadd_rn(ll, __fmul_rn(__fsub_rn(lu, ll), fr[k])));
+                        o_r = n48_clamp1(__fadd_rn(rl, __fmul_rn(__fsub_rn(ru, rl), fr[k])));
+                    }
+                }
+                pl[k * kN48Threads] = o_l; pr[k * kN48Threads] = o_r;
+            }
+        }
+    }
+}
+
 // ---- host arithmetic of the block / stream lengths (exact integer forms of the reference's f64 expressions) ----
 // outputs a push may emit once `end` source frames are known: every o with floor(o*rate/48000) + 1 < end, i.e.
 // o * rate < (end - 1) * 48000  ->  o < ceil((end - 1) * 48000 / rate).  (o * rate is exact in f64 below 2^53 and the
@@ -153,6 +323,11 @@ static int n48_fill_src(sk_ctx* ctx, N48Src* s, const void* in, size_t in_stride
 static int n48_launch(sk_ctx* ctx, const N48Src& src, unsigned long long o_start, unsigned long long n_lerp, unsigned long long n_total,
                       unsigned rate, float prev_l, float prev_r, float* out_l, float* out_r, long long out_stride, size_t n_streams,
                       float* final_lr) {
+    // source bytes one tile of outputs can touch (+ alignment slack); the staged kernel needs them in shared memory
+    const unsigned long long span_frames = ((unsigned long long)kN48Tile * rate + 47999) / 48000 + 3;
+    const unsigned long long span_bytes = span_frames * (unsigned long long)(src.width * src.channels) + 48;
+    const bool tiled = span_bytes + 32 <= (unsigned long long)kN48MaxVec * kN48Threads * 16 &&
+                       (((uintptr_t)src.base | (uintptr_t)src.stream_stride) & 15) == 0;
     const unsigned long long groups = (n_total + 3) / 4;
     unsigned long long gx = (groups + kN48Threads - 1) / kN48Threads;
     if (gx < 1) gx = 1;
@@ -162,8 +337,28 @@ static int n48_launch(sk_ctx* ctx, const N48Src& src, unsigned long long o_start
     const unsigned long long want = (unsigned long long)ctx->num_sms * 16;
     if (gx < want) gy = (unsigned)std::min<unsigned long long>(n_streams, (want + gx - 1) / gx);
     if (gy > 65535u) gy = 65535u;
-    norm48k_kernel<<<dim3((unsigned)gx, gy), kN48Threads, 0, ctx->stream>>>(src, o_start, n_lerp, n_total, rate, prev_l, prev_r, out_l, out_r,
-                                                                           out_stride, (unsigned)n_streams, final_lr);
+    if (tiled) {
+        const dim3 grid((unsigned)gx, gy);
+        const int buf_bytes = (int)sk_round_up((size_t)span_bytes + 32, 16);
+        const size_t smem = 2 * (size_t)buf_bytes;
+#define N48_LAUNCH(W_, BE_, FLT_, ST_)                                                                                                        \
+        do {                                                                                                                                  \
+            SK_CUDA(ctx, cudaFuncSetAttribute(norm48k_tile_kernel<W_, BE_, FLT_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+            norm48k_tile_kernel<W_, BE_, FLT_, ST_><<<grid, kN48Threads, smem, ctx->stream>>>(src, o_start, n_lerp, n_total, rate, prev_l, prev_r, \
+                                                                                              out_l, out_r, out_stride, (unsigned)n_streams, final_lr, buf_bytes); \
+        } while (0)
+#define N48_LAUNCH_ST(W_, BE_, FLT_) do { if (src.channels > 1) N48_LAUNCH(W_, BE_, FLT_, true); else N48_LAUNCH(W_, BE_, FLT_, false); } while (0)
+        const bool be = src.big_endian != 0;
+        if (src.width == 2) { if (be) N48_LAUNCH_ST(2, true, false); else N48_LAUNCH_ST(2, false, false); }
+        else if (src.width == 3) { if (be) N48_LAUNCH_ST(3, true, false); else N48_LAUNCH_ST(3, false, false); }
+        else if (src.is_float) { if (be) N48_LAUNCH_ST(4, true, true); else N48_LAUNCH_ST(4, false, true); }
+        else { if (be) N48_LAUNCH_ST(4, true, false); else N48_LAUNCH_ST(4, false, false); }
+#undef N48_LAUNCH_ST
+#undef N48_LAUNCH
+    } else {
+        norm48k_kernel<<<dim3((unsigned)gx, gy), kN48Threads, 0, ctx->stream>>>(src, o_start, n_lerp, n_total, rate, prev_l, prev_r, out_l, out_r,
+                                                                               out_stride, (unsigned)n_streams, final_lr);
+    }
     SK_LAUNCH_CHECK(ctx);
     return SK_OK;
 }

@@ -36,3 +36,28 @@ def gather_counts(count, dist=None, device="cpu"):
     out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
     dist.all_gather(out, t)
     return [int(x.item()) for x in out]
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process (and the pinned host buffers it allocates afterwards, by first touch) to the NUMA node the GPU
+    hangs off, so that N ranks staging host buffers do not all pull from one socket's memory.  Best effort: returns
+    the node number, or None when the topology cannot be read (then nothing is changed)."""
+    import os
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(device_index)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
