@@ -37,7 +37,12 @@ pub enum sk_flat_op {
     S24BE_TO_I16 = 6, S32LE_TO_I32 = 7, S32BE_TO_I32 = 8, S32LE_TO_S24 = 9, S32BE_TO_S24 = 10, S32LE_TO_F32 = 11,
     S32BE_TO_F32 = 12, S32LE_TO_I16 = 13, S32BE_TO_I16 = 14, F32LE_TO_I16 = 15, F32BE_TO_I16 = 16, F32LE_TO_I32 = 17,
     F32LE_TO_S24 = 18,
+    // packet scalers of soundkit/src/audio_packet.rs and container-PCM unpackers
+    PKT_S16LE_TO_F32 = 19, PKT_S24LE_TO_F32 = 20, PKT_S32LE_TO_I16 = 21, PKT_F32LE_TO_I16 = 22, U8_TO_S16 = 23,
 }
+
+#[repr(C)] pub struct sk_norm48k { _private: [u8; 0] }
+pub const SK_G726_STATE_INTS: usize = 24;
 
 #[repr(C)] #[derive(Clone, Copy, Debug)]
 pub struct sk_resample_params {
@@ -103,4 +108,35 @@ extern "C" {
     pub fn sk_normalize_stream(ctx: *mut sk_ctx, input: *const u8, bytes: usize, bits: c_int, fmt: c_int, big_endian: c_int, channels: c_int,
                                scale_mode: c_int, in_rate: u32, out_rate: u32, semantics: c_int, mix_mode: c_int, out: *mut c_float,
                                out_cap_per_plane: usize, n_out: *mut usize) -> c_int;
+
+    // unpack_dvd_lpcm (soundkit-decoder/src/lib.rs:750-804)
+    pub fn sk_dvd_lpcm_unpack(ctx: *mut sk_ctx, packed: *const u8, bytes: usize, bits: c_int, channels: c_int, out: *mut u8) -> c_int;
+    pub fn sk_dvd_lpcm_unpack_dev(ctx: *mut sk_ctx, packed: *const u8, bytes: usize, bits: c_int, channels: c_int, out: *mut u8) -> c_int;
+
+    // G.726 ADPCM (soundkit-g726/src/lib.rs): whole code groups, explicit G726Core state
+    pub fn sk_g726_state_init(state: *mut i32);
+    pub fn sk_g726_decode(ctx: *mut sk_ctx, bits: c_int, packing: c_int, state: *mut i32, input: *const u8, bytes: usize, out_kind: c_int,
+                          out: *mut c_void) -> c_int;
+    pub fn sk_g726_encode(ctx: *mut sk_ctx, bits: c_int, packing: c_int, state: *mut i32, in_kind: c_int, input: *const c_void, n: usize,
+                          out: *mut u8) -> c_int;
+    pub fn sk_g726_decode_batch_dev(ctx: *mut sk_ctx, bits: c_int, packing: c_int, input: *const u8, in_stride: usize, n_streams: usize,
+                                    bytes: usize, out_kind: c_int, out: *mut c_void, out_stride: usize, state: *mut i32) -> c_int;
+    pub fn sk_g726_encode_batch_dev(ctx: *mut sk_ctx, bits: c_int, packing: c_int, in_kind: c_int, input: *const c_void, in_stride: usize,
+                                    n_streams: usize, n: usize, out: *mut u8, out_stride: usize, state: *mut i32) -> c_int;
+
+    // StreamingStereo48kNormalizer (soundkit/src/audio_pipeline.rs:256-394)
+    pub fn sk_norm48k_create(ctx: *mut sk_ctx, out: *mut *mut sk_norm48k) -> c_int;
+    pub fn sk_norm48k_destroy(n: *mut sk_norm48k);
+    pub fn sk_norm48k_push(n: *mut sk_norm48k, data: *const u8, bytes: usize, bits: c_int, fmt: c_int, big_endian: c_int, channels: c_int,
+                           rate: u32, left: *mut c_float, right: *mut c_float, cap: usize, n_out: *mut usize) -> c_int;
+    pub fn sk_norm48k_finish(n: *mut sk_norm48k, left: *mut c_float, right: *mut c_float, cap: usize, n_out: *mut usize) -> c_int;
+    pub fn sk_norm48k_source_frames(n: *const sk_norm48k) -> u64;
+    pub fn sk_norm48k_output_frames(n: *const sk_norm48k) -> u64;
+    pub fn sk_norm48k_source_sample_rate(n: *const sk_norm48k) -> u32;
+    pub fn sk_norm48k_source_channels(n: *const sk_norm48k) -> c_int;
+    pub fn sk_norm48k_max_output(frames: usize, rate: u32) -> usize;
+    pub fn sk_normalize48k_out_frames(frames: usize, rate: u32) -> usize;
+    pub fn sk_normalize48k_batch_dev(ctx: *mut sk_ctx, input: *const c_void, in_stride: usize, n_streams: usize, frames: usize, bits: c_int,
+                                     fmt: c_int, big_endian: c_int, channels: c_int, rate: u32, out: *mut c_float, out_stride: usize,
+                                     out_stride_ch: usize, n_out: *mut usize) -> c_int;
 }

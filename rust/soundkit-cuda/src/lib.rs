@@ -10,6 +10,7 @@ use std::ffi::CStr;
 pub mod audio_bytes;
 pub mod audio_pipeline;
 pub mod g711;
+pub mod g726;
 
 /// One `sk_ctx` per thread: the reference runs one worker thread per `DecodePipeline`
 /// (soundkit-decoder/src/lib.rs:2764) and contexts are thread-confined.
