@@ -114,6 +114,8 @@ struct sk_plan {
     int32_t* d_i0 = nullptr; uint8_t* d_s0 = nullptr; float* d_frac = nullptr;
     int period = 8;          // outputs per phase period used for the phase-major tile mapping
     int max_window = 0;      // largest input window (frames) any tile of 32*period outputs needs
+    int period2 = 0;         // resample_gen2_kernel: outputs per period (a multiple of L), 0 = kernel not applicable
+    int max_window2 = 0;     // largest input window of a 64-period tile
 };
 
 static uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
@@ -136,6 +138,7 @@ void sk_resample_free_ctx(sk_ctx* ctx) {
 }
 
 static const int kGenMaxWindow = 14400;  // frames of shared memory window the general kernel may use (57.6 KB)
+static const int kGen2MaxWindow = 46000;  // resample_gen2_kernel: up to 184 KB of window + 32 KB of staged table rows
 
 // finish a general plan from recorded walk arrays: choose the tile period and upload
 static int finalize_general_plan(sk_ctx* ctx, sk_plan* p, uint32_t in_rate, uint32_t out_rate, const WalkOut& w) {
@@ -158,6 +161,24 @@ static int finalize_general_plan(sk_ctx* ctx, sk_plan* p, uint32_t in_rate, uint
         if (mw <= kGenMaxWindow) p->period = (int)L;
     }
     p->max_window = window_for(p->period);
+    // gen2 mapping: 64 periods per tile, period = the smallest multiple of L that is >= 32 outputs (phases repeat every L
+    // outputs, so any multiple keeps "same position in the period -> same table rows" true)
+    {
+        const uint32_t per = L * ((31 + L) / L);
+        auto window2_for = [&](size_t period) {
+            int mw = 0;
+            const size_t tile = period * 64;
+            for (size_t n0 = 0; n0 < p->n_out; n0 += tile) {
+                size_t n1 = std::min(p->n_out, n0 + tile) - 1;
+                mw = std::max(mw, w.i0[n1] - w.i0[n0] + SINC_LEN + 2);
+            }
+            return mw;
+        };
+        if (per <= 1024 && p->n_out >= (size_t)per * 64) {
+            const int mw = window2_for(per);
+            if (mw <= kGen2MaxWindow) { p->period2 = (int)per; p->max_window2 = mw; }
+        }
+    }
     if (p->n_out) {
         SK_CUDA(ctx, cudaMalloc((void**)&p->d_i0, p->n_out * sizeof(int32_t)));
         SK_CUDA(ctx, cudaMalloc((void**)&p->d_s0, p->n_out));
@@ -786,6 +807,162 @@ resample_gen_kernel(const __grid_constant__ SrcDesc src, const __grid_constant__
 }
 
 // ================================================================================================
+// general kernel v2: register tile of 2 adjacent phases x 2 periods per thread
+// ================================================================================================
+// The v1 kernel computes one output per thread at a time: every 8 taps cost 9 shared-memory loads and 4 table
+// loads for 16 FMAs, so the load/store unit, not the FMA pipe, sets the pace (13 % of the FP32 peak).  Here a thread
+// owns a 2 x 2 tile: two ADJACENT outputs (phases p, p+1: their input windows differ by DELTA = 0 or 1 samples, so
+// one register window serves both) of two PERIODS (k and k + 32: same phases, hence the same four table rows).
+// Per 8 taps: 16 + 2*DELTA shared-memory loads and 8 table loads feed 64 FMAs (0.39 loads per FMA instead of 0.81).
+// Each of the 8 dot products keeps rubato's 8 lane accumulators and reduction tree, and `p0 + frac * (p1 - p0)` uses the
+// output's own frac, so results stay bit-identical to v1 and to the oracle.
+// The tile mapping needs warp-uniform rows: all lanes of a warp sit at the same position inside the phase period, which
+// fixes (subindex, DELTA) except where the f64 walk lands within rounding of an integer; such warps (and ragged tile
+// ends, and subindex 255 whose second product starts one sample later) take the v1 arithmetic per output.
+constexpr int kGen2Threads = 256;
+constexpr int kGen2Periods = 64;
+
+__device__ __forceinline__ float gen_single(const float* x, const float* __restrict__ h0, const float* __restrict__ h1, int d, float frac) {
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, c[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+    for (int k = 0; k < SINC_LEN; k += 8) {
+        float xs[9];
+#pragma unroll
+        for (int l = 0; l < 9; l++) xs[l] = x[k + l];
+        const float4 ha = __ldg(reinterpret_cast<const float4*>(h0 + k)), hb = __ldg(reinterpret_cast<const float4*>(h0 + k + 4));
+        const float4 hc = __ldg(reinterpret_cast<const float4*>(h1 + k)), hd = __ldg(reinterpret_cast<const float4*>(h1 + k + 4));
+        const float g0[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+        const float g1[8] = {hc.x, hc.y, hc.z, hc.w, hd.x, hd.y, hd.z, hd.w};
+#pragma unroll
+        for (int l = 0; l < 8; l++) {
+            a[l] = __fmaf_rn(xs[l], g0[l], a[l]);
+            c[l] = __fmaf_rn(d ? xs[l + 1] : xs[l], g1[l], c[l]);
+        }
+    }
+    const float p0 = reduce8(a), p1 = reduce8(c);
+    return __fadd_rn(p0, __fmul_rn(frac, __fsub_rn(p1, p0)));  // interp_lin
+}
+
+// y[phase][period] for the 2 x 2 tile; x0 / x1: windows of the two periods at phase 0's first tap; hs: the warp's four
+// table rows (subindex s_a, s_a + 1, s_b, s_b + 1) staged in shared memory, so the loop's coefficient reads are
+// broadcast LDS.128 with shared-memory latency instead of L1/L2 round trips
+template <int DELTA>
+__device__ __forceinline__ void gen2_tile(const float* x0, const float* x1, const float* hs, const float (&frac)[2][2], float (&y)[2][2]) {
+    float acc[2][2][2][8];  // [phase][period][product][lane]
+#pragma unroll
+    for (int i = 0; i < 64; i++) (&acc[0][0][0][0])[i] = 0.0f;
+    // 4 taps per step (lanes 0-3, then 4-7 of rubato's accumulators): 4 broadcast LDS.128 + 8 (+2) LDS.32 feed 32 FMAs
+    // with only 26 operand registers live, which keeps the kernel at 2 CTAs per SM
+#pragma unroll 1
+    for (int k = 0; k < SINC_LEN; k += 8) {
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int kk = k + 4 * half;
+            // lanes are periods: consecutive lanes read words M apart (M odd for the common ratios) -> conflict-free LDS.32.
+            // (An even/odd double copy of the window read with LDS.64 was measured slower: 64-bit bank conflicts.)
+            float xs[2][4 + DELTA];
+#pragma unroll
+            for (int l = 0; l < 4 + DELTA; l++) { xs[0][l] = x0[kk + l]; xs[1][l] = x1[kk + l]; }
+            float4 g[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) g[r] = *reinterpret_cast<const float4*>(hs + r * SINC_LEN + kk);
+#pragma unroll
+            for (int l = 0; l < 4; l++) {
+                const int ln = 4 * half + l;
+                const float c0 = l == 0 ? g[0].x : (l == 1 ? g[0].y : (l == 2 ? g[0].z : g[0].w));
+                const float c1 = l == 0 ? g[1].x : (l == 1 ? g[1].y : (l == 2 ? g[1].z : g[1].w));
+                const float c2 = l == 0 ? g[2].x : (l == 1 ? g[2].y : (l == 2 ? g[2].z : g[2].w));
+                const float c3 = l == 0 ? g[3].x : (l == 1 ? g[3].y : (l == 2 ? g[3].z : g[3].w));
+#pragma unroll
+                for (int b = 0; b < 2; b++) {
+                    acc[0][b][0][ln] = __fmaf_rn(xs[b][l], c0, acc[0][b][0][ln]);
+                    acc[0][b][1][ln] = __fmaf_rn(xs[b][l], c1, acc[0][b][1][ln]);
+                    acc[1][b][0][ln] = __fmaf_rn(xs[b][l + DELTA], c2, acc[1][b][0][ln]);
+                    acc[1][b][1][ln] = __fmaf_rn(xs[b][l + DELTA], c3, acc[1][b][1][ln]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            const float p0 = reduce8(acc[a][b][0]), p1 = reduce8(acc[a][b][1]);
+            y[a][b] = __fadd_rn(p0, __fmul_rn(frac[a][b], __fsub_rn(p1, p0)));  // interp_lin
+        }
+}
+
+__global__ void __launch_bounds__(kGen2Threads, 2)
+resample_gen2_kernel(const __grid_constant__ SrcDesc src, const __grid_constant__ OutDesc dst, const int32_t* __restrict__ pi0,
+                     const uint8_t* __restrict__ ps0, const float* __restrict__ pfrac, const float* __restrict__ table, int period,
+                     int lanes_per_stream) {
+    extern __shared__ __align__(16) float win_all[];
+    float* rows_smem = win_all;                                   // [8 warps][4 rows][256]
+    float* win = win_all + (kGen2Threads / 32) * 4 * SINC_LEN;
+    const long long stream = blockIdx.y / lanes_per_stream;
+    const int lane_ch = blockIdx.y % lanes_per_stream;
+    const long long tile = (long long)period * kGen2Periods;
+    const long long n0 = (long long)blockIdx.x * tile;
+    const long long n1 = min(dst.n_out, n0 + tile) - 1;  // last output of this tile
+    const int w0 = pi0[n0];
+    const int count = pi0[n1] - w0 + SINC_LEN + 2;
+    stage_window<kGen2Threads>(src, stream, lane_ch, false, (long long)w0, count, win, nullptr);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, q = threadIdx.x & 31;
+    float* op = dst.base + stream * dst.stream_stride + (long long)lane_ch * dst.lane_stride;
+    for (int phase = 2 * warp; phase < period; phase += 2 * (kGen2Threads / 32)) {
+        // the tile's four outputs of this lane: n[a][b] = n0 + (q + 32 b) * period + phase + a
+        long long n[2][2]; int i0[2][2], s0[2][2]; float frac[2][2]; bool ok[2][2];
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                n[a][b] = n0 + (long long)(q + 32 * b) * period + phase + a;
+                ok[a][b] = phase + a < period && n[a][b] <= n1;
+                i0[a][b] = ok[a][b] ? pi0[n[a][b]] : w0;
+                s0[a][b] = ok[a][b] ? (int)ps0[n[a][b]] : 0;
+                frac[a][b] = ok[a][b] ? pfrac[n[a][b]] : 0.0f;
+            }
+        // warp-uniform rows and window offset?  (reference values: lane 0, period 0)
+        const int sa = __shfl_sync(0xffffffffu, s0[0][0], 0), sb = __shfl_sync(0xffffffffu, s0[1][0], 0);
+        const int dl = __shfl_sync(0xffffffffu, i0[1][0] - i0[0][0], 0);
+        const bool all4 = ok[0][0] && ok[0][1] && ok[1][0] && ok[1][1];
+        const bool none = !(ok[0][0] || ok[0][1] || ok[1][0] || ok[1][1]);
+        const bool fits = all4 && s0[0][0] == sa && s0[0][1] == sa && s0[1][0] == sb && s0[1][1] == sb && sa < OVERSAMPLING - 1 &&
+                          sb < OVERSAMPLING - 1 && i0[1][0] - i0[0][0] == dl && i0[1][1] - i0[0][1] == dl && (dl == 0 || dl == 1);
+        const bool lane0_ok = __shfl_sync(0xffffffffu, (int)all4, 0) != 0;
+        if (lane0_ok && __all_sync(0xffffffffu, fits || none)) {
+            float y[2][2];
+            const float* x0 = win + (i0[0][0] - w0);
+            const float* x1 = win + (i0[0][1] - w0);
+            // stage the four rows for this warp: rows sa, sa + 1 are contiguous in the table, so are sb, sb + 1
+            float* hs = rows_smem + warp * 4 * SINC_LEN;
+            __syncwarp();  // the previous work item's reads of hs are done
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                reinterpret_cast<float4*>(hs)[q + 32 * j] = __ldg(reinterpret_cast<const float4*>(table + sa * SINC_LEN) + q + 32 * j);
+                reinterpret_cast<float4*>(hs + 2 * SINC_LEN)[q + 32 * j] = __ldg(reinterpret_cast<const float4*>(table + sb * SINC_LEN) + q + 32 * j);
+            }
+            __syncwarp();
+            if (dl == 0) gen2_tile<0>(x0, x1, hs, frac, y);
+            else gen2_tile<1>(x0, x1, hs, frac, y);
+            if (all4) { op[n[0][0]] = y[0][0]; op[n[1][0]] = y[1][0]; op[n[0][1]] = y[0][1]; op[n[1][1]] = y[1][1]; }
+        } else {
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int b = 0; b < 2; b++) {
+                    if (!ok[a][b]) continue;
+                    int s1 = s0[a][b] + 1, d = 0;
+                    if (s1 >= OVERSAMPLING) { s1 -= OVERSAMPLING; d = 1; }  // get_nearest_times_2
+                    op[n[a][b]] = gen_single(win + (i0[a][b] - w0), table + s0[a][b] * SINC_LEN, table + s1 * SINC_LEN, d, frac[a][b]);
+                }
+        }
+    }
+}
+
+// ================================================================================================
 // host: launch helpers
 // ================================================================================================
 static int src_desc_for(sk_ctx* ctx, SrcDesc* s, const void* in, size_t in_stride, int bits, int fmt, int big_endian, int channels, int scale_mode,
@@ -857,6 +1034,27 @@ static int launch_int(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const
     return SK_OK;
 }
 
+static int launch_gen2(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, const float* d_table, size_t n_streams,
+                       int lanes_per_stream) {
+    const int smem = (plan->max_window2 + 8 + (kGen2Threads / 32) * 4 * SINC_LEN) * (int)sizeof(float);
+    SK_CUDA(ctx, cudaFuncSetAttribute(resample_gen2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const size_t tile = (size_t)plan->period2 * kGen2Periods;
+    const size_t tiles = (plan->n_out + tile - 1) / tile;
+    const size_t lanes = (size_t)lanes_per_stream * n_streams;
+    const size_t slab = (size_t)lanes_per_stream * (65535 / lanes_per_stream);
+    for (size_t l0 = 0; l0 < lanes; l0 += slab) {
+        const size_t nl = std::min<size_t>(slab, lanes - l0);
+        SrcDesc s2 = src; OutDesc d2 = dst;
+        const size_t stream0 = l0 / lanes_per_stream;
+        s2.base += (long long)stream0 * src.stream_stride;
+        d2.base += (long long)stream0 * dst.stream_stride;
+        dim3 grid((unsigned)tiles, (unsigned)nl);
+        resample_gen2_kernel<<<grid, kGen2Threads, smem, ctx->stream>>>(s2, d2, plan->d_i0, plan->d_s0, plan->d_frac, d_table, plan->period2, lanes_per_stream);
+        SK_LAUNCH_CHECK(ctx);
+    }
+    return SK_OK;
+}
+
 static int launch_gen(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, const float* d_table, size_t n_streams,
                       int lanes_per_stream) {
     const int smem = (plan->max_window + 8) * (int)sizeof(float);
@@ -896,6 +1094,7 @@ static int run_plan(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const s
         SK_FAIL(ctx, SK_E_STATE, "internal: no kernel for integer step %d", plan->step);
     }
     if (dst.mix != SK_MIX_NONE) SK_FAIL(ctx, SK_E_STATE, "internal: general kernel does not mix");
+    if (plan->period2 > 0) return launch_gen2(ctx, src, dst, plan, d_table, n_streams, lanes_per_stream);
     return launch_gen(ctx, src, dst, plan, d_table, n_streams, lanes_per_stream);
 }
 

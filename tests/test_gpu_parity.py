@@ -561,3 +561,27 @@ def test_g726_batch_dev_streams_are_independent_and_chunkable(oracle, suffix, bi
     for s in (0, 7, 33, S - 1):
         assert np.array_equal(enc[s, :nbytes], oracle.G726(bits).encode(out[s, :n])), s
     c.close()
+
+
+# ---------------------------------------------------------------------------------------------- general-ratio kernel v2 (2 x 2 register tile)
+@pytest.mark.parametrize("rates", [(44100, 48000), (44100, 16000), (48000, 44100), (32000, 48000), (8000, 44100), (22050, 16000)])
+@pytest.mark.parametrize("semantics", ["oneshot", "streaming"])
+def test_general_ratio_long_streams_bit_exact(ctx, oracle, rates, semantics):
+    """streams long enough (>= 64 phase periods of outputs) to run resample_gen2_kernel, including its ragged last tile
+    and the warps that fall back to per-output arithmetic; white noise plus a near-Nyquist tone (exposes index drift)"""
+    i, o = rates
+    frames = int(i * 1.7) + 173
+    rng = np.random.default_rng(i + o)
+    t = np.arange(frames)
+    x = np.stack([rng.uniform(-0.5, 0.5, frames), 0.8 * np.sin(2 * np.pi * 0.41 * min(i, o) * t / i)], axis=1).astype(np.float32)
+    data = x.reshape(-1).view(np.uint8)
+    if semantics == "oneshot":
+        want = oracle.downsample_audio(data, 32, 1, 2, i, o)
+        got = ctx.normalize_stream(data, 32, capi.FMT_FLOAT, False, 2, capi.MODE_A, i, o, capi.SEM_ONESHOT, capi.MIX_NONE)
+    else:
+        st = oracle.Stream(i, o, 2)
+        want = np.concatenate([st.process(np.ascontiguousarray(x.T)), st.flush()], axis=1)
+        got = ctx.normalize_stream(data, 32, capi.FMT_FLOAT, False, 2, capi.MODE_B, i, o, capi.SEM_STREAMING, capi.MIX_NONE)
+    assert got.shape == want.shape and got.shape[1] > 64 * 33
+    for c in range(2):
+        assert_resample_close(want[c], got[c])
