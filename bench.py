@@ -348,20 +348,21 @@ def run_ours(args):
     kernels_per_step = max(1, launches // max(1, args.steps))
     ach = FLOPS_PER_FRAME * S * n_out / (launch_ms * 1e-3) / 1e12
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch, same workload only)
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
         w = tr["workload"]
         if (w["streams_per_gpu"], w["frames_per_stream"], w["bits"], w["channels"]) == (S, frames, BITS, CHANNELS):
-            traffic = {"bytes_per_launch": tr["dram_bytes_read"] + tr["dram_bytes_write"], "algorithmic_bytes_per_launch": BYTES_PER_FRAME * S * n_out,
-                       "source": tr["source"]}
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]  # bytes per launch; algorithmic: BYTES_PER_FRAME * S * n_out
+            traffic_src = tr["source"]
     except Exception:
         pass
     roofline = {"bound": "fp32", "kernel": "resample_int_tma_kernel<3, 3> (fused s24->f32 + 256-tap FIR x2ch + downmix)",
                 "achieved": ach, "peak": ffma_peak, "unit": "TFLOP/s", "frac": ach / ffma_peak,
                 "peak_source": "FFMA microbenchmark measured in this run (sk_ctx_measure_ffma_peak); nominal 148 SM x 128 x 2 x 1.965 GHz = 74.4",
                 "algorithmic_flops_per_launch": FLOPS_PER_FRAME * S * n_out, "launch_ms": launch_ms,
-                "kernels_per_step": kernels_per_step, "traffic": traffic,
+                "kernels_per_step": kernels_per_step, "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": BYTES_PER_FRAME * S * n_out,
                 "hbm": {"achieved_GBs": BYTES_PER_FRAME * S * n_out / (launch_ms * 1e-3) / 1e9, "peak_GBs": hbm_peak,
                         "frac": BYTES_PER_FRAME * S * n_out / (launch_ms * 1e-3) / 1e9 / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"}}
