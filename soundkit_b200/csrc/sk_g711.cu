@@ -61,59 +61,65 @@ __device__ __forceinline__ uint32_t g711_dec_word(int law, int kind, uint32_t co
 }
 
 // ---- decode ------------------------------------------------------------------------------------
-// Work split: a CTA iteration covers kDecThreads * CPT * kDecUnroll codes; in sub-iteration u thread t owns the
-// CPT consecutive codes at ((u * kDecThreads) + t) * CPT, CPT = 16 B / output width.  Every warp-wide load is one
-// contiguous 256 B (128 B) run and every warp-wide store one contiguous 512 B run: whole sectors in both directions
-// (the first version gave each thread 16 codes and two 16 B stores 32 B apart - half-written sectors, 0.70 of HBM).
-// All kDecUnroll loads are issued before the first lookup so each thread keeps 4 independent requests in flight.
+// Every global access is a full-width, contiguous warp access: per step a warp loads 512 codes as one 512-byte run
+// (16 B per lane) and stores the 1024 / 2048 output bytes as 2 / 4 runs of 512 bytes (16 B per lane).  The lane that
+// loaded codes [16t, 16t+16) is not the lane that stores their samples, so the codes cross lanes through 512 bytes of
+// warp-private shared memory (one STS.128, then one LDS.64 / LDS.32 per store).  Narrower per-lane accesses (8 B loads,
+// the previous version) ran at 0.85 of HBM, two half-sector stores per lane (the first version) at 0.70.
 constexpr int kDecThreads = 512;
-constexpr int kDecUnroll = 4;
+constexpr int kDecUnroll = 2;  // warp steps whose loads are issued together
 
 template <int KIND>
 __global__ void __launch_bounds__(kDecThreads) g711_decode_kernel(const uint8_t* __restrict__ in, void* __restrict__ outv,
                                                                    size_t n, int law) {
     __shared__ uint32_t lut[256 * 32];  // [code][bank]
+    __shared__ __align__(16) uint8_t xch[kDecThreads / 32][kDecUnroll][512];
     for (int i = threadIdx.x; i < 256 * 32; i += kDecThreads) lut[i] = g711_dec_word(law, KIND, (uint32_t)i >> 5);
     __syncthreads();
-    const uint32_t* my = lut + (threadIdx.x & 31);
-    constexpr int CPT = KIND == SK_KIND_I16 ? 8 : 4;   // codes per thread per sub-iteration (one 16 B store)
-    constexpr int NW = CPT / 4;                         // 32-bit words of codes per thread
-    const size_t nvec = n / CPT;
-    const uint32_t* inw = reinterpret_cast<const uint32_t*>(in);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t* my = lut + lane;
+    constexpr int OB = KIND == SK_KIND_I16 ? 2 : 4;
+    constexpr int EPL = 16 / OB;        // elements per lane per store (8 or 4)
+    constexpr int NST = 512 / (32 * EPL);  // stores per step (2 or 4)
+    const size_t nsteps = n / 512;
+    const uint4* in4 = reinterpret_cast<const uint4*>(in);
     uint4* out4 = reinterpret_cast<uint4*>(outv);
-    const size_t tile = (size_t)kDecThreads * kDecUnroll;
-    for (size_t base = (size_t)blockIdx.x * tile; base < nvec; base += (size_t)gridDim.x * tile) {
-        uint32_t w[kDecUnroll][NW];
+    const size_t wstride = (size_t)gridDim.x * (kDecThreads / 32) * kDecUnroll;
+    for (size_t s0 = ((size_t)blockIdx.x * (kDecThreads / 32) + warp) * kDecUnroll; s0 < nsteps; s0 += wstride) {
+        uint4 c[kDecUnroll];
+#pragma unroll
+        for (int u = 0; u < kDecUnroll; u++)
+            if (s0 + u < nsteps) c[u] = ld_stream_v4_nv(in4 + (s0 + u) * 32 + lane);
+        __syncwarp();  // the previous iteration's reads of xch are done
+#pragma unroll
+        for (int u = 0; u < kDecUnroll; u++)
+            if (s0 + u < nsteps) reinterpret_cast<uint4*>(xch[warp][u])[lane] = c[u];
+        __syncwarp();
 #pragma unroll
         for (int u = 0; u < kDecUnroll; u++) {
-            size_t v = base + (size_t)u * kDecThreads + threadIdx.x;
-            if (v < nvec) {
-                if (NW == 2) { uint2 c = ld_stream_v2(inw + v * 2); w[u][0] = c.x; w[u][NW - 1] = c.y; }
-                else w[u][0] = ld_stream_u32(inw + v);
+            if (s0 + u >= nsteps) break;
+#pragma unroll
+            for (int i = 0; i < NST; i++) {
+                uint32_t w[2];
+                if (EPL == 8) { const uint2 t = reinterpret_cast<const uint2*>(xch[warp][u])[i * 32 + lane]; w[0] = t.x; w[1] = t.y; }
+                else { w[0] = reinterpret_cast<const uint32_t*>(xch[warp][u])[i * 32 + lane]; w[1] = 0; }
+                uint32_t o[EPL];
+#pragma unroll
+                for (int k = 0; k < EPL; k++) o[k] = my[((w[k >> 2] >> (8 * (k & 3))) & 0xff) << 5];
+                uint4 r;
+                if (KIND == SK_KIND_I16) {
+                    r.x = __byte_perm(o[0], o[1], 0x5410); r.y = __byte_perm(o[2], o[3], 0x5410);
+                    r.z = __byte_perm(o[4 % EPL], o[5 % EPL], 0x5410); r.w = __byte_perm(o[6 % EPL], o[7 % EPL], 0x5410);
+                } else {
+                    r = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                st_stream_v4(out4 + ((s0 + u) * NST + i) * 32 + lane, r);
             }
-        }
-#pragma unroll
-        for (int u = 0; u < kDecUnroll; u++) {
-            size_t v = base + (size_t)u * kDecThreads + threadIdx.x;
-            if (v >= nvec) break;
-            uint32_t o[CPT];
-#pragma unroll
-            for (int q = 0; q < NW; q++)
-#pragma unroll
-                for (int k = 0; k < 4; k++) o[q * 4 + k] = my[((w[u][q] >> (8 * k)) & 0xff) << 5];
-            uint4 r;
-            if (KIND == SK_KIND_I16) {
-                r.x = __byte_perm(o[0], o[1], 0x5410); r.y = __byte_perm(o[2], o[3], 0x5410);
-                r.z = __byte_perm(o[4 % CPT], o[5 % CPT], 0x5410); r.w = __byte_perm(o[6 % CPT], o[7 % CPT], 0x5410);
-            } else {
-                r = make_uint4(o[0], o[1], o[2], o[3]);
-            }
-            st_stream_v4(out4 + v, r);
         }
     }
-    // tail (< CPT codes): one thread per sample
+    // tail (< 512 codes): one thread per sample
     if (blockIdx.x == 0) {
-        for (size_t i = nvec * CPT + threadIdx.x; i < n; i += kDecThreads) {
+        for (size_t i = nsteps * 512 + threadIdx.x; i < n; i += kDecThreads) {
             uint32_t wv = my[(uint32_t)in[i] << 5];
             if (KIND == SK_KIND_I16) reinterpret_cast<uint16_t*>(outv)[i] = (uint16_t)wv;
             else reinterpret_cast<uint32_t*>(outv)[i] = wv;
@@ -144,7 +150,6 @@ __global__ void g711_decode_scalar_kernel(const uint8_t* __restrict__ in, void* 
 // same function ran at 0.51 of HBM (random 16-bit indices: ~3.5-way bank conflicts); this form is 7 issue slots
 // per sample and streams.
 constexpr int kEncThreads = 256;
-constexpr int kEncUnroll = 4;
 
 template <int LAW>
 __device__ __forceinline__ uint32_t g711_enc_fast(float f) {  // f = (float)sample; returns enc + 16 (mu) / enc (A), in [0, 0x8f]
@@ -181,33 +186,37 @@ __device__ __forceinline__ uint32_t g711_enc4(uint32_t a, uint32_t b, uint32_t c
     return packed ^ (signs & 0x80808080u);
 }
 
-template <int LAW, int KIND>  // SK_KIND_I16: 8 samples / 16 B; SK_KIND_I32: 4 samples / 16 B, (s >> 16) as i16 (:133-135)
+// Same access discipline as the decoder: per step a warp loads 512 samples as 2 (i16) or 4 (i32) contiguous 512-byte
+// runs and stores their 512 codes as one 512-byte run (16 B per lane); the codes cross lanes through warp-private
+// shared memory.  KIND i32: (s >> 16) as i16 (:133-135).
+template <int LAW, int KIND>
 __global__ void __launch_bounds__(kEncThreads) g711_encode_kernel(const void* __restrict__ inv, uint8_t* __restrict__ out, size_t n) {
-    constexpr int SPV = KIND == SK_KIND_I16 ? 8 : 4;  // samples per 128-bit load
-    const size_t nvec = n / SPV;
+    __shared__ __align__(16) uint8_t xch[kEncThreads / 32][512];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NLD = KIND == SK_KIND_I16 ? 2 : 4;  // 128-bit loads per lane per step
+    const size_t nsteps = n / 512;
     const uint4* in4 = reinterpret_cast<const uint4*>(inv);
-    const size_t tile = (size_t)kEncThreads * kEncUnroll;
-    for (size_t base = (size_t)blockIdx.x * tile; base < nvec; base += (size_t)gridDim.x * tile) {
-        uint4 c[kEncUnroll];
+    uint4* out4 = reinterpret_cast<uint4*>(out);
+    const size_t wstride = (size_t)gridDim.x * (kEncThreads / 32);
+    for (size_t s0 = (size_t)blockIdx.x * (kEncThreads / 32) + warp; s0 < nsteps; s0 += wstride) {
+        uint4 c[NLD];
 #pragma unroll
-        for (int u = 0; u < kEncUnroll; u++) {
-            size_t v = base + (size_t)u * kEncThreads + threadIdx.x;
-            if (v < nvec) c[u] = ld_stream_v4_nv(in4 + v);
-        }
+        for (int i = 0; i < NLD; i++) c[i] = ld_stream_v4_nv(in4 + (s0 * NLD + i) * 32 + lane);
+        __syncwarp();  // the previous step's read of xch is done
 #pragma unroll
-        for (int u = 0; u < kEncUnroll; u++) {
-            size_t v = base + (size_t)u * kEncThreads + threadIdx.x;
-            if (v >= nvec) break;
+        for (int i = 0; i < NLD; i++) {
             if (KIND == SK_KIND_I16) {
-                uint32_t lo = g711_enc4<LAW, KIND>(c[u].x, c[u].y, 0, 0), hi = g711_enc4<LAW, KIND>(c[u].z, c[u].w, 0, 0);
-                st_stream_v2(reinterpret_cast<uint2*>(out) + v, make_uint2(lo, hi));
+                const uint32_t lo = g711_enc4<LAW, KIND>(c[i].x, c[i].y, 0, 0), hi = g711_enc4<LAW, KIND>(c[i].z, c[i].w, 0, 0);
+                reinterpret_cast<uint2*>(xch[warp])[i * 32 + lane] = make_uint2(lo, hi);
             } else {
-                st_stream_u32(reinterpret_cast<uint32_t*>(out) + v, g711_enc4<LAW, KIND>(c[u].x, c[u].y, c[u].z, c[u].w));
+                reinterpret_cast<uint32_t*>(xch[warp])[i * 32 + lane] = g711_enc4<LAW, KIND>(c[i].x, c[i].y, c[i].z, c[i].w);
             }
         }
+        __syncwarp();
+        st_stream_v4(out4 + s0 * 32 + lane, reinterpret_cast<const uint4*>(xch[warp])[lane]);
     }
     if (blockIdx.x == 0) {
-        for (size_t i = nvec * SPV + threadIdx.x; i < n; i += kEncThreads) {
+        for (size_t i = nsteps * 512 + threadIdx.x; i < n; i += kEncThreads) {
             int s = KIND == SK_KIND_I16 ? (int)reinterpret_cast<const int16_t*>(inv)[i]
                                         : (int)(int16_t)(reinterpret_cast<const uint32_t*>(inv)[i] >> 16);
             out[i] = (uint8_t)(LAW == SK_LAW_MULAW ? g711_enc_mulaw(s) : g711_enc_alaw(s));
@@ -245,8 +254,7 @@ extern "C" int sk_g711_decode_dev(sk_ctx* ctx, int law, const uint8_t* in, size_
         SK_LAUNCH_CHECK(ctx);
         return SK_OK;
     }
-    const size_t nvec = n / (out_kind == SK_KIND_I16 ? 8 : 4);
-    int grid = grid_for(ctx, (nvec + kDecUnroll - 1) / kDecUnroll, kDecThreads, 4);
+    int grid = grid_for(ctx, (n / 512 + kDecUnroll - 1) / kDecUnroll * 32, kDecThreads, 4);
     if (out_kind == SK_KIND_I16) g711_decode_kernel<SK_KIND_I16><<<grid, kDecThreads, 0, ctx->stream>>>(in, out, n, law);
     else if (out_kind == SK_KIND_I32) g711_decode_kernel<SK_KIND_I32><<<grid, kDecThreads, 0, ctx->stream>>>(in, out, n, law);
     else g711_decode_kernel<SK_KIND_F32><<<grid, kDecThreads, 0, ctx->stream>>>(in, out, n, law);
@@ -266,8 +274,7 @@ extern "C" int sk_g711_encode_dev(sk_ctx* ctx, int law, int in_kind, const void*
         SK_LAUNCH_CHECK(ctx);
         return SK_OK;
     }
-    const size_t nvec = n / (in_kind == SK_KIND_I16 ? 8 : 4);
-    int grid = grid_for(ctx, (nvec + kEncUnroll - 1) / kEncUnroll, kEncThreads, 8);
+    int grid = grid_for(ctx, n / 512 * 32, kEncThreads, 8);
     if (law == SK_LAW_MULAW) {
         if (in_kind == SK_KIND_I16) g711_encode_kernel<SK_LAW_MULAW, SK_KIND_I16><<<grid, kEncThreads, 0, ctx->stream>>>(in, out, n);
         else g711_encode_kernel<SK_LAW_MULAW, SK_KIND_I32><<<grid, kEncThreads, 0, ctx->stream>>>(in, out, n);

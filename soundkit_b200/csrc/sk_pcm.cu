@@ -12,6 +12,8 @@
 //     the file is built with -fmad=false and uses explicit _rn intrinsics where order matters.
 // A scalar kernel (one thread per sample, byte loads) covers channel counts > 2, unaligned caller
 // pointers and the < G-frame tail; it is correctness-only.
+#include <algorithm>
+
 #include "sk_common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -365,6 +367,43 @@ __global__ void __launch_bounds__(kPcmThreads) deint_kernel(const uint8_t* __res
     }
 }
 
+// Packed 24-bit stereo (BASELINE configs[1], s24le): a thread's natural unit (8 frames = 48 B in, 2 x 32 B out) makes
+// every 128-bit access a strided, partially used sector.  Here a WARP owns 256 consecutive frames: three coalesced
+// 512-byte loads land in warp-private shared memory, each lane then reads the 24 bytes of 4 frames (LDS.64 x 3, stride
+// 24 B: conflict-free) and writes one 128-bit vector per channel, so every global access is a whole contiguous line.
+template <bool BE, int CONV>
+__global__ void __launch_bounds__(kPcmThreads) deint_s24_stereo_kernel(const uint8_t* __restrict__ in, size_t in_stride, uint8_t* __restrict__ out,
+                                                                        size_t out_stride_bytes, size_t frames, size_t ntiles, float scale) {
+    __shared__ __align__(16) uint8_t stage[kPcmThreads / 32][1536];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint8_t* sin = in + (size_t)blockIdx.y * in_stride;
+    uint8_t* sout = out + (size_t)blockIdx.y * out_stride_bytes;
+    const size_t wstride = (size_t)gridDim.x * (kPcmThreads / 32);
+    for (size_t t = (size_t)blockIdx.x * (kPcmThreads / 32) + warp; t < ntiles; t += wstride) {
+        const uint4* p = reinterpret_cast<const uint4*>(sin + t * 1536);
+        uint4 v0 = ld_stream_v4_nv(p + lane), v1 = ld_stream_v4_nv(p + 32 + lane), v2 = ld_stream_v4_nv(p + 64 + lane);
+        __syncwarp();  // previous tile's reads of the staging buffer are done
+        uint4* st = reinterpret_cast<uint4*>(stage[warp]);
+        st[lane] = v0; st[32 + lane] = v1; st[64 + lane] = v2;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const uint2* q = reinterpret_cast<const uint2*>(stage[warp] + (i * 32 + lane) * 24);
+            const uint2 a = q[0], b = q[1], c = q[2];
+            const uint32_t w[7] = {a.x, a.y, b.x, b.y, c.x, c.y, 0u};
+            uint32_t l[4], r[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                l[k] = planar_apply<CONV>(get_sample<3, BE>(w, 2 * k), scale);
+                r[k] = planar_apply<CONV>(get_sample<3, BE>(w, 2 * k + 1), scale);
+            }
+            const size_t f0 = t * 256 + (size_t)(i * 32 + lane) * 4;
+            st_stream_v4(sout + f0 * 4, make_uint4(l[0], l[1], l[2], l[3]));
+            st_stream_v4(sout + (frames + f0) * 4, make_uint4(r[0], r[1], r[2], r[3]));
+        }
+    }
+}
+
 // any channel count / alignment / tail frames: one thread per sample
 __global__ void deint_scalar_kernel(const uint8_t* __restrict__ in, size_t in_stride, uint8_t* __restrict__ out, size_t out_stride_bytes,
                                     size_t frames, size_t first_frame, int B, int CH, int be, int conv, float scale) {
@@ -396,6 +435,13 @@ static size_t launch_deint_vec(sk_ctx* ctx, const uint8_t* in, size_t in_stride,
                                size_t n_streams, float scale) {
     constexpr int OB = CONV == CONV_RAW_I16 ? 2 : 4;
     constexpr int G = (OB == 2) ? 8 : ((B == 3) ? 8 * (CH == 1 ? 2 : 1) : (B == 2 && CH == 1 ? 8 : 4));
+    if (B == 3 && CH == 2 && OB == 4 && frames >= 256) {  // warp-tiled path for packed 24-bit stereo
+        const size_t ntiles = frames / 256;
+        const size_t ctas = (ntiles + kPcmThreads / 32 - 1) / (kPcmThreads / 32);
+        dim3 grid((unsigned)std::max<size_t>(1, n_streams > 1 ? (ctas + 7) / 8 : std::min<size_t>(ctas, (size_t)ctx->num_sms * 8)), (unsigned)n_streams);
+        deint_s24_stereo_kernel<BE, CONV><<<grid, kPcmThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride_bytes, frames, ntiles, scale);
+        return ntiles * 256;
+    }
     size_t ngroups = frames / G;
     if (!ngroups) return 0;
     dim3 grid(grid_for(ctx, ngroups, kPcmThreads), (unsigned)n_streams);

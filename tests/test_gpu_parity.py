@@ -147,7 +147,7 @@ def test_endian_swap_matches_reference_hashes(ctx):
 @pytest.mark.parametrize("mode", [capi.MODE_A, capi.MODE_B])
 @pytest.mark.parametrize("be", [False, True])
 def test_pcm_to_planar_f32(ctx, oracle, bits, fmt, channels, mode, be):
-    for frames in (0, 1, 7, 64, 4099):
+    for frames in (0, 1, 7, 64, 4099, 4100, 66000):  # 4100 / 66000: vector kernels (frames % 4 == 0) + scalar tail
         if fmt == 1:
             data = _flat_input("f32be" if be else "f32le", frames * channels)
         else:
