@@ -219,6 +219,20 @@ def extras(ctx, torch, peaks, only=None):
             res[f"convert_{name}_stereo_to_planar_f32"] = hbm_entry(nb, t, S * frames * 2)
             del raw
         del out
+    if want("flat"):
+        # a few of the remaining R1 entry points (soundkit/src/audio_bytes.rs flat functions, f32_channels_to_bytes)
+        n = 1 << 28
+        raw = torch.randint(0, 256, (n * 4,), dtype=torch.uint8, device="cuda")
+        o = torch.empty((n * 4,), dtype=torch.uint8, device="cuda")
+        for name, ib, ob in (("s24le_to_i32", 3, 4), ("s16be_to_i16", 2, 2), ("s32le_to_f32", 4, 4), ("f32le_to_i16", 4, 2)):
+            t = timed(lambda: ctx.flat_convert_dev(name, raw, n * ib, o))
+            res[f"flat_{name}"] = hbm_entry(n * (ib + ob), t, n)
+        frames = n // 2
+        planar = torch.rand((2, frames), device="cuda") * 2 - 1
+        for bits, fmt, nm in ((16, 0, "s16"), (24, 0, "s24"), (32, 1, "f32")):
+            t = timed(lambda: ctx.planar_f32_to_pcm_dev(planar, frames, 2, bits, fmt, o))
+            res[f"planar_f32_stereo_to_{nm}_bytes"] = hbm_entry(2 * frames * (4 + bits // 8), t, 2 * frames)
+        del raw, o, planar
     if want("g726"):
         # G.726-32 decode/encode, 65 536 telephony streams x 4 s (one thread per stream; latency bound)
         S, n = 65536, 32000

@@ -308,6 +308,9 @@ class Context:
         self._ck(self.L.sk_planar_f32_to_pcm(self.h, _p(p), p.shape[1], p.shape[0], bits, fmt, _p(out)))
         return out
 
+    def planar_f32_to_pcm_dev(self, d_planar, frames, channels, bits, fmt, d_out):
+        self._ck(self.L.sk_planar_f32_to_pcm_dev(self.h, _p(d_planar), frames, channels, bits, fmt, _p(d_out)))
+
     def pcm_narrow_i16(self, data, bits, big_endian):
         d = _u8(data)
         out = np.empty(d.size // (bits // 8) * 2, np.uint8)

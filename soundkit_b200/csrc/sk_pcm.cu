@@ -126,23 +126,54 @@ __device__ __forceinline__ uint32_t flat_apply(int32_t raw) {
 }
 
 constexpr int kPcmThreads = 256;
+constexpr int kPcmWarps = kPcmThreads / 32;
 
-// G samples per thread: input G*B bytes = NV_IN 16-byte vectors, output G*OB bytes
+// Warp-tiled global I/O.  A lane's natural unit is a contiguous span of NV 16-byte vectors (its group of samples); issued
+// directly, each warp-wide access would touch every NV-th vector of a 512*NV-byte run (partially used sectors, 0.67-0.86
+// of HBM).  Instead the warp moves the run with NV fully contiguous 512-byte accesses and the vectors change lanes through
+// NV*512 bytes of warp-private shared memory.  NV == 1 needs no exchange.
+template <int NV>
+__device__ __forceinline__ void warp_load_spans(uint4* xch, const uint4* __restrict__ gsrc, uint32_t* w, int lane) {
+    if (NV <= 2) {  // measured: up to two vectors per lane, direct L1-allocating loads of the lane's own span are as fast or faster
+#pragma unroll
+        for (int v = 0; v < NV; v++) { const uint4 q = __ldg(gsrc + lane * NV + v); w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w; }
+        return;
+    }
+    uint4 r[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) r[v] = ld_stream_v4_nv(gsrc + v * 32 + lane);
+    __syncwarp();
+#pragma unroll
+    for (int v = 0; v < NV; v++) xch[v * 32 + lane] = r[v];
+    __syncwarp();
+#pragma unroll
+    for (int v = 0; v < NV; v++) { const uint4 q = xch[lane * NV + v]; w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w; }
+}
+template <int NV>
+__device__ __forceinline__ void warp_store_spans(uint4* xch, uint4* __restrict__ gdst, const uint32_t* o, int lane) {
+    if (NV == 1) { st_stream_v4(gdst + lane, make_uint4(o[0], o[1], o[2], o[3])); return; }
+    __syncwarp();
+#pragma unroll
+    for (int v = 0; v < NV; v++) xch[lane * NV + v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int v = 0; v < NV; v++) st_stream_v4(gdst + v * 32 + lane, xch[v * 32 + lane]);
+}
+
+// G samples per lane: input G*B bytes = NV_IN 16-byte vectors, output G*OB bytes = NV_OUT vectors; a warp owns 32 groups
 template <int OP>
-__global__ void __launch_bounds__(kPcmThreads) flat_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t ngroups) {
+__global__ void __launch_bounds__(kPcmThreads) flat_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t ntiles) {
     constexpr FlatOpInfo I = flat_info(OP);
     constexpr int B = I.in_b, OB = I.out_b;
     constexpr int G = B == 1 ? 16 : (B == 2 ? 8 : (B == 3 ? 16 : (OB == 2 ? 8 : 4)));
-    constexpr int NV_IN = G * B / 16, NW_OUT = G * OB / 4;
-    const size_t stride = (size_t)gridDim.x * kPcmThreads;
-    for (size_t g = (size_t)blockIdx.x * kPcmThreads + threadIdx.x; g < ngroups; g += stride) {
+    constexpr int NV_IN = G * B / 16, NW_OUT = G * OB / 4, NV_OUT = NW_OUT / 4;
+    constexpr int NVX = NV_IN > NV_OUT ? NV_IN : NV_OUT;
+    __shared__ uint4 xch_all[kPcmWarps][NVX * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint4* xch = xch_all[warp];
+    for (size_t t = (size_t)blockIdx.x * kPcmWarps + warp; t < ntiles; t += (size_t)gridDim.x * kPcmWarps) {
         uint32_t w[NV_IN * 4];
-        const uint4* p = reinterpret_cast<const uint4*>(in + g * (size_t)(G * B));
-#pragma unroll
-        for (int v = 0; v < NV_IN; v++) {
-            uint4 q = __ldg(p + v);
-            w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
-        }
+        warp_load_spans<NV_IN>(xch, reinterpret_cast<const uint4*>(in + t * (size_t)(32 * G * B)), w, lane);
         uint32_t o[NW_OUT];
 #pragma unroll
         for (int k = 0; k < G; k++) {
@@ -151,9 +182,7 @@ __global__ void __launch_bounds__(kPcmThreads) flat_kernel(const uint8_t* __rest
             else if (k & 1) o[k >> 1] |= r << 16;
             else o[k >> 1] = r;
         }
-        uint4* q = reinterpret_cast<uint4*>(out + g * (size_t)(G * OB));
-#pragma unroll
-        for (int v = 0; v < NW_OUT / 4; v++) st_stream_v4(q + v, make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]));
+        warp_store_spans<NV_OUT>(xch, reinterpret_cast<uint4*>(out + t * (size_t)(32 * G * OB)), o, lane);
     }
 }
 
@@ -184,13 +213,13 @@ template <int OP>
 static int launch_flat(sk_ctx* ctx, const uint8_t* in, size_t n, uint8_t* out) {
     constexpr FlatOpInfo I = flat_info(OP);
     constexpr int G = I.in_b == 1 ? 16 : (I.in_b == 2 ? 8 : (I.in_b == 3 ? 16 : (I.out_b == 2 ? 8 : 4)));
-    size_t ngroups = (aligned16(in) && aligned16(out)) ? n / G : 0;
-    if (ngroups) {
-        flat_kernel<OP><<<grid_for(ctx, ngroups, kPcmThreads), kPcmThreads, 0, ctx->stream>>>(in, out, ngroups);
+    const size_t ntiles = (aligned16(in) && aligned16(out)) ? n / (32 * (size_t)G) : 0;  // warp tiles of 32 groups
+    if (ntiles) {
+        flat_kernel<OP><<<grid_for(ctx, ntiles * 32, kPcmThreads), kPcmThreads, 0, ctx->stream>>>(in, out, ntiles);
         SK_LAUNCH_CHECK(ctx);
     }
-    if (ngroups * G < n) {
-        flat_scalar_kernel<OP><<<grid_for(ctx, n - ngroups * G, 256), 256, 0, ctx->stream>>>(in, out, ngroups * G, n);
+    if (ntiles * 32 * G < n) {
+        flat_scalar_kernel<OP><<<grid_for(ctx, n - ntiles * 32 * G, 256), 256, 0, ctx->stream>>>(in, out, ntiles * 32 * G, n);
         SK_LAUNCH_CHECK(ctx);
     }
     return SK_OK;
@@ -582,24 +611,22 @@ __device__ __forceinline__ uint32_t quantize(float x) {
     return (uint32_t)f32_to_i32_dev(x);
 }
 
-// thread = G frames x CH channels; output span G*CH*(BITS/8) bytes is whole 16-byte vectors
+// lane = G frames x CH channels; output span G*CH*(BITS/8) bytes is whole 16-byte vectors; a warp owns 32 groups
 template <int BITS, int CH, bool ISFLOAT>
 __global__ void __launch_bounds__(kPcmThreads) interleave_kernel(const float* __restrict__ planar, size_t frames, uint8_t* __restrict__ out,
-                                                                  size_t ngroups) {
+                                                                  size_t ntiles) {
     constexpr int OB = BITS / 8;
     constexpr int G = (OB == 3) ? (CH == 1 ? 16 : 8) : (OB == 2 ? (CH == 1 ? 8 : 4) : 4);
-    constexpr int NW = G * CH * OB / 4;
+    constexpr int NW = G * CH * OB / 4, NV_OUT = NW / 4, NV_IN = G / 4;
+    constexpr int NVX = NV_IN > NV_OUT ? NV_IN : NV_OUT;
     static_assert((G * CH * OB) % 16 == 0 && G % 4 == 0, "vector group");
-    const size_t stride = (size_t)gridDim.x * kPcmThreads;
-    for (size_t g = (size_t)blockIdx.x * kPcmThreads + threadIdx.x; g < ngroups; g += stride) {
-        float x[CH][G];
+    __shared__ uint4 xch_all[kPcmWarps][NVX * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint4* xch = xch_all[warp];
+    for (size_t t = (size_t)blockIdx.x * kPcmWarps + warp; t < ntiles; t += (size_t)gridDim.x * kPcmWarps) {
+        uint32_t xb[CH][G];
 #pragma unroll
-        for (int c = 0; c < CH; c++)
-#pragma unroll
-            for (int v = 0; v < G / 4; v++) {
-                float4 q = __ldg(reinterpret_cast<const float4*>(planar + (size_t)c * frames + g * G) + v);
-                x[c][4 * v] = q.x; x[c][4 * v + 1] = q.y; x[c][4 * v + 2] = q.z; x[c][4 * v + 3] = q.w;
-            }
+        for (int c = 0; c < CH; c++) warp_load_spans<NV_IN>(xch, reinterpret_cast<const uint4*>(planar + (size_t)c * frames + t * (size_t)(32 * G)), xb[c], lane);
         uint32_t o[NW];
 #pragma unroll
         for (int i = 0; i < NW; i++) o[i] = 0;
@@ -607,14 +634,12 @@ __global__ void __launch_bounds__(kPcmThreads) interleave_kernel(const float* __
         for (int k = 0; k < G; k++)
 #pragma unroll
             for (int c = 0; c < CH; c++) {
-                const uint32_t r = quantize<BITS, ISFLOAT>(x[c][k]);
+                const uint32_t r = quantize<BITS, ISFLOAT>(__uint_as_float(xb[c][k]));
                 const int byte = (k * CH + c) * OB, wi = byte >> 2, sh = (byte & 3) * 8;
                 o[wi] |= r << sh;
                 if (sh + OB * 8 > 32) o[wi + 1] |= r >> (32 - sh);
             }
-        uint4* q = reinterpret_cast<uint4*>(out + g * (size_t)(G * CH * OB));
-#pragma unroll
-        for (int v = 0; v < NW / 4; v++) st_stream_v4(q + v, make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]));
+        warp_store_spans<NV_OUT>(xch, reinterpret_cast<uint4*>(out + t * (size_t)(32 * G * CH * OB)), o, lane);
     }
 }
 
@@ -635,10 +660,10 @@ template <int BITS, int CH, bool ISFLOAT>
 static size_t launch_interleave_vec(sk_ctx* ctx, const float* planar, size_t frames, uint8_t* out) {
     constexpr int OB = BITS / 8;
     constexpr int G = (OB == 3) ? (CH == 1 ? 16 : 8) : (OB == 2 ? (CH == 1 ? 8 : 4) : 4);
-    size_t ngroups = frames / G;
-    if (!ngroups) return 0;
-    interleave_kernel<BITS, CH, ISFLOAT><<<grid_for(ctx, ngroups, kPcmThreads), kPcmThreads, 0, ctx->stream>>>(planar, frames, out, ngroups);
-    return ngroups * G;
+    const size_t ntiles = frames / (32 * (size_t)G);
+    if (!ntiles) return 0;
+    interleave_kernel<BITS, CH, ISFLOAT><<<grid_for(ctx, ntiles * 32, kPcmThreads), kPcmThreads, 0, ctx->stream>>>(planar, frames, out, ntiles);
+    return ntiles * 32 * G;
 }
 
 extern "C" int sk_planar_f32_to_pcm_dev(sk_ctx* ctx, const float* planar, size_t frames, int channels, int bits, int fmt, uint8_t* out) {
