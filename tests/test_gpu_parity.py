@@ -585,3 +585,83 @@ def test_general_ratio_long_streams_bit_exact(ctx, oracle, rates, semantics):
     assert got.shape == want.shape and got.shape[1] > 64 * 33
     for c in range(2):
         assert_resample_close(want[c], got[c])
+
+
+# ---------------------------------------------------------------------------------------------- guard bands
+def test_device_entry_points_do_not_write_outside_their_buffers():
+    """compute-sanitizer is closed on this pool, so out-of-bounds WRITES are checked the blunt way: every device-pointer
+    entry point writes into the middle of a canary-filled arena at ragged sizes; the canaries must survive."""
+    import torch
+    c = capi.Context(0)
+    c.use_torch_stream()
+    GUARD = 4096
+
+    def arena(nbytes):
+        buf = torch.full((GUARD + nbytes + GUARD + 64,), 0xA5, dtype=torch.uint8, device="cuda")
+        return buf, buf[GUARD:GUARD + nbytes]
+
+    def intact(buf, nbytes):
+        torch.cuda.synchronize()
+        return bool((buf[:GUARD] == 0xA5).all()) and bool((buf[GUARD + nbytes:] == 0xA5).all())
+
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    rnd = lambda n: torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda", generator=g)
+    for n in (1, 511, 512, 513, 70001):
+        src = rnd(n)
+        for kind, ob in ((capi.KIND_I16, 2), (capi.KIND_F32, 4)):
+            buf, out = arena(n * ob)
+            c.g711_decode_dev(capi.LAW_ALAW, src, n, kind, out)
+            assert intact(buf, n * ob), ("g711 decode", n, kind)
+        pcm = rnd(2 * n)
+        buf, out = arena(n)
+        c.g711_encode_dev(capi.LAW_MULAW, capi.KIND_I16, pcm, n, out)
+        assert intact(buf, n), ("g711 encode", n)
+    for name in ("s24le_to_i32", "f32le_to_i16", "u8_to_s16", "pkt_s16le_to_f32"):
+        iw, ow = c.flat_widths(capi.FLAT_OP[name])
+        for n in (1, 31 * 16, 32 * 16 + 5, 50001):
+            src = rnd(n * iw)
+            buf, out = arena(n * ow)
+            c.flat_convert_dev(name, src, n * iw, out)
+            assert intact(buf, n * ow), (name, n)
+    for bits, fmt in ((16, 0), (24, 0), (32, 1)):
+        for frames in (4, 252, 256, 260, 8196):
+            S, fb = 3, (bits // 8) * 2
+            stride = (frames * fb + 15) // 16 * 16
+            src = rnd(S * stride)
+            buf, out = arena(S * 2 * frames * 4)
+            c.pcm_to_planar_f32_dev(src, stride, S, frames, bits, fmt, False, 2, capi.MODE_B, out, 2 * frames)
+            assert intact(buf, S * 2 * frames * 4), ("planar", bits, frames)
+            planar = torch.rand((2, frames), device="cuda") * 2 - 1
+            buf, out = arena(frames * fb)
+            c.planar_f32_to_pcm_dev(planar, frames, 2, bits, fmt, out)
+            assert intact(buf, frames * fb), ("interleave", bits, frames)
+    for rate in (44100, 48000, 96000):
+        S, frames = 3, 5003
+        src = rnd(S * frames * 4 + 16)
+        n_out = c.normalize48k_out_frames(frames, rate)
+        plane = (n_out + 3) // 4 * 4
+        buf, out = arena(S * 2 * plane * 4)
+        c.normalize48k_batch_dev(src, (frames * 4 + 15) // 16 * 16, S, frames, 16, 0, False, 2, rate, out.view(torch.float32), 2 * plane, plane)
+        assert intact(buf, S * 2 * plane * 4), ("norm48k", rate)
+    for i_rate, o_rate in ((48000, 16000), (44100, 48000)):
+        S, frames = 2, 30011
+        stride = (frames * 6 + 15) // 16 * 16
+        src = rnd(S * stride)
+        n_out = c.batch_plan(i_rate, o_rate, frames, capi.SEM_STREAMING)
+        plane = (n_out + 3) // 4 * 4
+        buf, out = arena(S * 2 * plane * 4)
+        d = capi.BatchDesc(src.data_ptr(), stride, S, frames, 24, capi.FMT_SIGNED, 0, 2, capi.MODE_B, i_rate, o_rate, capi.SEM_STREAMING,
+                           capi.MIX_NONE, out.data_ptr(), 2 * plane, plane)
+        c.normalize_batch_dev(d)
+        assert intact(buf, S * 2 * plane * 4), ("normalize", i_rate, o_rate)
+    for bits in (2, 3, 4, 5):
+        gs, gb = capi.G726_GROUP[bits]
+        S, groups = 70, 333
+        src = rnd(S * groups * gb)
+        buf, out = arena(S * groups * gs * 2)
+        c.g726_decode_batch_dev(bits, 0, src, groups * gb, S, groups * gb, capi.KIND_I16, out, groups * gs)
+        assert intact(buf, S * groups * gs * 2), ("g726 decode", bits)
+        buf2, enc = arena(S * groups * gb)
+        c.g726_encode_batch_dev(bits, 0, capi.KIND_I16, out, groups * gs, S, groups * gs, enc, groups * gb)
+        assert intact(buf2, S * groups * gb), ("g726 encode", bits)
+    c.close()
