@@ -26,6 +26,7 @@ struct sk_ctx {
     void* h_stage = nullptr; size_t h_cap = 0;
     void* d_in = nullptr;    size_t d_in_cap = 0;
     void* d_out = nullptr;   size_t d_out_cap = 0;
+    void* batch_pipe = nullptr;                       // sk_resample.cu: slab pipeline of sk_normalize_batch (streams, events, device slabs)
     bool g726_tables_ready = false;                   // sk_g726.cu: __constant__ tables uploaded on this device
     // sinc tables per ratio, built lazily
     std::map<uint64_t, float*> sinc_tables;          // key = (in_rate << 32) | out_rate -> device [256][256]

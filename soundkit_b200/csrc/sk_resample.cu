@@ -1206,12 +1206,11 @@ struct BatchPipe {
     void* d_in[2] = {nullptr, nullptr}; size_t in_cap = 0;
     float* d_out[2] = {nullptr, nullptr}; size_t out_cap = 0;
 };
-static std::map<sk_ctx*, BatchPipe> g_pipes;  // one per context (contexts are thread-confined)
-
+// one per context, owned by the context (contexts are thread-confined; no process-wide state, so pipelines on different
+// threads never meet)
 void sk_resample_free_pipe(sk_ctx* ctx) {
-    auto it = g_pipes.find(ctx);
-    if (it == g_pipes.end()) return;
-    BatchPipe& p = it->second;
+    if (!ctx->batch_pipe) return;
+    BatchPipe& p = *static_cast<BatchPipe*>(ctx->batch_pipe);
     for (int b = 0; b < 2; b++) {
         if (p.d_in[b]) cudaFree(p.d_in[b]);
         if (p.d_out[b]) cudaFree(p.d_out[b]);
@@ -1221,7 +1220,8 @@ void sk_resample_free_pipe(sk_ctx* ctx) {
     }
     if (p.s_in) cudaStreamDestroy(p.s_in);
     if (p.s_out) cudaStreamDestroy(p.s_out);
-    g_pipes.erase(it);
+    delete static_cast<BatchPipe*>(ctx->batch_pipe);
+    ctx->batch_pipe = nullptr;
 }
 
 extern "C" int sk_normalize_batch(sk_ctx* ctx, const sk_batch_desc* d) {
@@ -1243,7 +1243,8 @@ extern "C" int sk_normalize_batch(sk_ctx* ctx, const sk_batch_desc* d) {
     // slab: as many streams as fit ~256 MiB of input (at least one)
     size_t slab = std::max<size_t>(1, ((size_t)256 << 20) / std::max<size_t>(1, in_bytes));
     slab = std::min(slab, d->n_streams);
-    BatchPipe& p = g_pipes[ctx];
+    if (!ctx->batch_pipe) ctx->batch_pipe = new BatchPipe();
+    BatchPipe& p = *static_cast<BatchPipe*>(ctx->batch_pipe);
     if (!p.s_in) {
         SK_CUDA(ctx, cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking));
         SK_CUDA(ctx, cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking));

@@ -665,3 +665,40 @@ def test_device_entry_points_do_not_write_outside_their_buffers():
         c.g726_encode_batch_dev(bits, 0, capi.KIND_I16, out, groups * gs, S, groups * gs, enc, groups * gb)
         assert intact(buf2, S * groups * gb), ("g726 encode", bits)
     c.close()
+
+
+# ---------------------------------------------------------------------------------------------- threads
+def test_contexts_on_concurrent_threads_do_not_interfere(oracle):
+    """the reference runs one worker thread per DecodePipeline and many pipelines at once (soundkit-decoder/src/lib.rs:
+    2764): one sk_ctx per thread, calls overlapping in time (ctypes releases the GIL), every result equal to the oracle"""
+    import threading
+    errors = []
+
+    def worker(seed):
+        try:
+            rng = np.random.default_rng(seed)
+            c = capi.Context(0)
+            for it in range(6):
+                codes = rng.integers(0, 256, 20000 + seed, dtype=np.uint8)
+                law = (seed + it) & 1
+                assert np.array_equal(c.g711_decode(law, codes), oracle.g711_decode(law, codes))
+                frames = 6000 + 7 * seed
+                v = rng.integers(-(1 << 23), 1 << 23, frames * 2, dtype=np.int64)
+                raw = np.stack([v & 0xff, (v >> 8) & 0xff, (v >> 16) & 0xff], axis=1).astype(np.uint8).reshape(-1)
+                got = c.normalize_stream(raw, 24, capi.FMT_SIGNED, False, 2, capi.MODE_B, 48000, 16000, capi.SEM_STREAMING,
+                                         capi.MIX_SCALE_THEN_SUM)[0]
+                want = oracle.normalize_chain_mono(raw, 24, oracle.SIGNED, False, 2, 48000, 16000)
+                assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+                st = c.g726_state()
+                g = c.g726_decode(4, 0, st, codes[:8000])
+                assert np.array_equal(g, oracle.G726(4).decode(codes[:8000]))
+            c.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append((seed, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(1, 7)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
