@@ -254,16 +254,19 @@ def extras(ctx, torch, peaks, only=None):
         res["normalizer48k_s16le_stereo_44k1"] = hbm_entry(S * (frames * 4 + n_out * 8), t, S * n_out * 2)
         del raw, o
     if want("resample"):
-        # non-integer ratio 44.1k -> 48k stereo f32 (BASELINE configs[3] wave), one-shot semantics
-        S, frames = 16, 2646000
-        n_out = ctx.batch_plan(44100, 48000, frames, capi.SEM_ONESHOT)
-        x = (torch.rand((S, frames * 2), device="cuda") - 0.5)
-        o = torch.empty((S, 2, n_out), dtype=torch.float32, device="cuda")
-        d = capi.BatchDesc(x.data_ptr(), x.stride(0) * 4, S, frames, 32, 1, 0, 2, capi.MODE_A, 44100, 48000, capi.SEM_ONESHOT,
-                           capi.MIX_NONE, o.data_ptr(), 2 * n_out, n_out)
-        t = timed(lambda: ctx.normalize_batch_dev(d), reps=3)
-        fl = 1027.0 * S * 2 * n_out
-        res["resample_44k1_to_48k_stereo_f32"] = {"TFLOP/s": fl / t / 1e12, "Msamples/s": S * 2 * n_out / t / 1e6}
+        # non-integer ratios, stereo f32, one-shot semantics (BASELINE configs[3] wave: 44.1k -> 48k; plus the common
+        # downsampling case 44.1k -> 16k).  P = 2: both interpolation products, 1027 flop per output sample.
+        for in_rate, out_rate in ((44100, 48000), (44100, 16000)):
+            S, frames = 16, 2646000
+            n_out = ctx.batch_plan(in_rate, out_rate, frames, capi.SEM_ONESHOT)
+            x = (torch.rand((S, frames * 2), device="cuda") - 0.5)
+            o = torch.empty((S, 2, n_out), dtype=torch.float32, device="cuda")
+            d = capi.BatchDesc(x.data_ptr(), x.stride(0) * 4, S, frames, 32, 1, 0, 2, capi.MODE_A, in_rate, out_rate, capi.SEM_ONESHOT,
+                               capi.MIX_NONE, o.data_ptr(), 2 * n_out, n_out)
+            t = timed(lambda: ctx.normalize_batch_dev(d), reps=3)
+            fl = 1027.0 * S * 2 * n_out
+            res[f"resample_{in_rate}_to_{out_rate}_stereo_f32"] = {"TFLOP/s": fl / t / 1e12, "Msamples/s": S * 2 * n_out / t / 1e6}
+            del x, o
     return res
 
 

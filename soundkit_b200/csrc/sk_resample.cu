@@ -138,7 +138,7 @@ void sk_resample_free_ctx(sk_ctx* ctx) {
 }
 
 static const int kGenMaxWindow = 14400;  // frames of shared memory window the general kernel may use (57.6 KB)
-static const int kGen2MaxWindow = 46000;  // resample_gen2_kernel: up to 184 KB of window + 32 KB of staged table rows
+static const int kGen2MaxWindow = 40000;  // resample_gen2_kernel: up to 160 KB of window + 64 KB of staged table rows (512-thread form)
 
 // finish a general plan from recorded walk arrays: choose the tile period and upload
 static int finalize_general_plan(sk_ctx* ctx, sk_plan* p, uint32_t in_rate, uint32_t out_rate, const WalkOut& w) {
@@ -819,8 +819,8 @@ resample_gen_kernel(const __grid_constant__ SrcDesc src, const __grid_constant__
 // The tile mapping needs warp-uniform rows: all lanes of a warp sit at the same position inside the phase period, which
 // fixes (subindex, DELTA) except where the f64 walk lands within rounding of an integer; such warps (and ragged tile
 // ends, and subindex 255 whose second product starts one sample later) take the v1 arithmetic per output.
-constexpr int kGen2Threads = 256;
 constexpr int kGen2Periods = 64;
+constexpr int kGen2MaxDelta = 6;  // largest window offset between the two adjacent outputs of a tile
 
 __device__ __forceinline__ float gen_single(const float* x, const float* __restrict__ h0, const float* __restrict__ h1, int d, float frac) {
     float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, c[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -892,13 +892,14 @@ __device__ __forceinline__ void gen2_tile(const float* x0, const float* x1, cons
         }
 }
 
-__global__ void __launch_bounds__(kGen2Threads, 2)
+template <int NT>  // 256 threads x 2 CTAs/SM when two windows fit an SM, else 512 threads x 1 CTA (same 16 warps per SM)
+__global__ void __launch_bounds__(NT, 512 / NT)
 resample_gen2_kernel(const __grid_constant__ SrcDesc src, const __grid_constant__ OutDesc dst, const int32_t* __restrict__ pi0,
                      const uint8_t* __restrict__ ps0, const float* __restrict__ pfrac, const float* __restrict__ table, int period,
                      int lanes_per_stream) {
     extern __shared__ __align__(16) float win_all[];
     float* rows_smem = win_all;                                   // [8 warps][4 rows][256]
-    float* win = win_all + (kGen2Threads / 32) * 4 * SINC_LEN;
+    float* win = win_all + (NT / 32) * 4 * SINC_LEN;
     const long long stream = blockIdx.y / lanes_per_stream;
     const int lane_ch = blockIdx.y % lanes_per_stream;
     const long long tile = (long long)period * kGen2Periods;
@@ -906,12 +907,12 @@ resample_gen2_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
     const long long n1 = min(dst.n_out, n0 + tile) - 1;  // last output of this tile
     const int w0 = pi0[n0];
     const int count = pi0[n1] - w0 + SINC_LEN + 2;
-    stage_window<kGen2Threads>(src, stream, lane_ch, false, (long long)w0, count, win, nullptr);
+    stage_window<NT>(src, stream, lane_ch, false, (long long)w0, count, win, nullptr);
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, q = threadIdx.x & 31;
     float* op = dst.base + stream * dst.stream_stride + (long long)lane_ch * dst.lane_stride;
-    for (int phase = 2 * warp; phase < period; phase += 2 * (kGen2Threads / 32)) {
+    for (int phase = 2 * warp; phase < period; phase += 2 * (NT / 32)) {
         // the tile's four outputs of this lane: n[a][b] = n0 + (q + 32 b) * period + phase + a
         long long n[2][2]; int i0[2][2], s0[2][2]; float frac[2][2]; bool ok[2][2];
 #pragma unroll
@@ -930,7 +931,7 @@ resample_gen2_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
         const bool all4 = ok[0][0] && ok[0][1] && ok[1][0] && ok[1][1];
         const bool none = !(ok[0][0] || ok[0][1] || ok[1][0] || ok[1][1]);
         const bool fits = all4 && s0[0][0] == sa && s0[0][1] == sa && s0[1][0] == sb && s0[1][1] == sb && sa < OVERSAMPLING - 1 &&
-                          sb < OVERSAMPLING - 1 && i0[1][0] - i0[0][0] == dl && i0[1][1] - i0[0][1] == dl && (dl == 0 || dl == 1);
+                          sb < OVERSAMPLING - 1 && i0[1][0] - i0[0][0] == dl && i0[1][1] - i0[0][1] == dl && dl >= 0 && dl <= kGen2MaxDelta;
         const bool lane0_ok = __shfl_sync(0xffffffffu, (int)all4, 0) != 0;
         if (lane0_ok && __all_sync(0xffffffffu, fits || none)) {
             float y[2][2];
@@ -945,8 +946,15 @@ resample_gen2_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
                 reinterpret_cast<float4*>(hs + 2 * SINC_LEN)[q + 32 * j] = __ldg(reinterpret_cast<const float4*>(table + sb * SINC_LEN) + q + 32 * j);
             }
             __syncwarp();
-            if (dl == 0) gen2_tile<0>(x0, x1, hs, frac, y);
-            else gen2_tile<1>(x0, x1, hs, frac, y);
+            switch (dl) {  // adjacent outputs are floor/ceil(t_ratio) input samples apart: 0-1 when upsampling, up to 6 for 44.1 -> 8 kHz
+                case 0: gen2_tile<0>(x0, x1, hs, frac, y); break;
+                case 1: gen2_tile<1>(x0, x1, hs, frac, y); break;
+                case 2: gen2_tile<2>(x0, x1, hs, frac, y); break;
+                case 3: gen2_tile<3>(x0, x1, hs, frac, y); break;
+                case 4: gen2_tile<4>(x0, x1, hs, frac, y); break;
+                case 5: gen2_tile<5>(x0, x1, hs, frac, y); break;
+                default: gen2_tile<6>(x0, x1, hs, frac, y); break;
+            }
             if (all4) { op[n[0][0]] = y[0][0]; op[n[1][0]] = y[1][0]; op[n[0][1]] = y[0][1]; op[n[1][1]] = y[1][1]; }
         } else {
 #pragma unroll
@@ -1036,8 +1044,12 @@ static int launch_int(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const
 
 static int launch_gen2(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, const float* d_table, size_t n_streams,
                        int lanes_per_stream) {
-    const int smem = (plan->max_window2 + 8 + (kGen2Threads / 32) * 4 * SINC_LEN) * (int)sizeof(float);
-    SK_CUDA(ctx, cudaFuncSetAttribute(resample_gen2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int smem256 = (plan->max_window2 + 8 + (256 / 32) * 4 * SINC_LEN) * (int)sizeof(float);
+    const bool two_ctas = 2 * (smem256 + 1024) <= 227 * 1024;
+    const int nt = two_ctas ? 256 : 512;
+    const int smem = (plan->max_window2 + 8 + (nt / 32) * 4 * SINC_LEN) * (int)sizeof(float);
+    if (two_ctas) SK_CUDA(ctx, cudaFuncSetAttribute(resample_gen2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    else SK_CUDA(ctx, cudaFuncSetAttribute(resample_gen2_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const size_t tile = (size_t)plan->period2 * kGen2Periods;
     const size_t tiles = (plan->n_out + tile - 1) / tile;
     const size_t lanes = (size_t)lanes_per_stream * n_streams;
@@ -1049,7 +1061,8 @@ static int launch_gen2(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, cons
         s2.base += (long long)stream0 * src.stream_stride;
         d2.base += (long long)stream0 * dst.stream_stride;
         dim3 grid((unsigned)tiles, (unsigned)nl);
-        resample_gen2_kernel<<<grid, kGen2Threads, smem, ctx->stream>>>(s2, d2, plan->d_i0, plan->d_s0, plan->d_frac, d_table, plan->period2, lanes_per_stream);
+        if (two_ctas) resample_gen2_kernel<256><<<grid, 256, smem, ctx->stream>>>(s2, d2, plan->d_i0, plan->d_s0, plan->d_frac, d_table, plan->period2, lanes_per_stream);
+        else resample_gen2_kernel<512><<<grid, 512, smem, ctx->stream>>>(s2, d2, plan->d_i0, plan->d_s0, plan->d_frac, d_table, plan->period2, lanes_per_stream);
         SK_LAUNCH_CHECK(ctx);
     }
     return SK_OK;
