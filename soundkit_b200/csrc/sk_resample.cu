@@ -577,9 +577,11 @@ template <int STEP, int SRCW> __host__ __device__ constexpr int tma_smem_bytes()
 }
 
 // 4 interleaved stereo frames (FB words in memory order) -> 4 L and 4 R f32 samples.  Everything about
-// the format is a template parameter: no per-sample branches.  Scale is an exact power of two.
+// the format is a template parameter: no per-sample branches.  Integer samples are staged UNSCALED (as the integer
+// value): the exact power-of-two scale is folded into the taps on the host instead
+// (fma(x * 2^-k, h, a) == fma(x, h * 2^-k, a) bit for bit), which removes one FMUL per sample from the staging pass.
 template <int SRCW, bool BE, bool ISFLOAT, bool SCRUB>
-__device__ __forceinline__ void convert4(const uint32_t* w, float scale, float* l, float* r) {
+__device__ __forceinline__ void convert4(const uint32_t* w, float* l, float* r) {
 #pragma unroll
     for (int k = 0; k < 4; k++) {
 #pragma unroll
@@ -588,19 +590,19 @@ __device__ __forceinline__ void convert4(const uint32_t* w, float scale, float* 
             if (SRCW == 2) {
                 uint32_t h = c == 0 ? (w[k] & 0xffffu) : (w[k] >> 16);
                 if (BE) h = __byte_perm(h, 0, 0x3201) & 0xffffu;
-                f = __fmul_rn((float)(int16_t)h, scale);
+                f = (float)(int16_t)h;
             } else if (SRCW == 3) {
                 const int o = 3 * (2 * k + c), wi = o >> 2, sh = o & 3;
                 const uint32_t lo = w[wi], hi = (sh >= 2) ? w[wi + 1] : 0u;
                 // sample bytes -> result bytes 1..3 (most significant byte on top), then arithmetic >> 8 sign-extends
                 const uint32_t sel = !BE ? ((uint32_t)(sh + 2) << 12) | ((uint32_t)(sh + 1) << 8) | ((uint32_t)sh << 4)
                                          : ((uint32_t)sh << 12) | ((uint32_t)(sh + 1) << 8) | ((uint32_t)(sh + 2) << 4);
-                f = __fmul_rn(__int2float_rn(((int32_t)__byte_perm(lo, hi, sel)) >> 8), scale);
+                f = __int2float_rn(((int32_t)__byte_perm(lo, hi, sel)) >> 8);
             } else {
                 uint32_t u = w[2 * k + c];
                 if (BE) u = bswap32(u);
                 if (ISFLOAT) f = (SCRUB && (u & 0x7f800000u) == 0x7f800000u) ? 0.0f : __uint_as_float(u);
-                else f = __fmul_rn(__int2float_rn((int32_t)u), scale);
+                else f = __int2float_rn((int32_t)u);
             }
             if (c == 0) l[k] = f; else r[k] = f;
         }
@@ -632,7 +634,7 @@ __device__ __forceinline__ bool convert_window(const uint8_t* __restrict__ rb, f
                     w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
                 }
             }
-            convert4<SRCW, BE, ISFLOAT, SCRUB>(w, src.scale, l, r);
+            convert4<SRCW, BE, ISFLOAT, SCRUB>(w, l, r);
         } else {
 #pragma unroll
             for (int q = 0; q < 4; q++) {
@@ -1001,7 +1003,16 @@ static int launch_int_tma(sk_ctx* ctx, const Taps& taps, const SrcDesc& src, con
     const long long total = tiles_per_stream * (long long)n_streams;
     const int per_sm = std::max(1, std::min(SK_TMA_CTAS_PER_SM, (220 * 1024) / smem));
     const long long grid = std::min<long long>(total, (long long)ctx->num_sms * per_sm);
-    resample_int_tma_kernel<STEP, SRCW><<<(unsigned)grid, kIntThreads, smem, ctx->stream>>>(taps, src, dst, plan->i0_first, (unsigned)tiles_per_stream,
+    // integer sources are staged unscaled (see convert4): fold the exact power-of-two scale into the taps and let the
+    // per-frame edge path (decode_sample_bits) stage the same unscaled values
+    SrcDesc s2 = src;
+    Taps t2 = taps;
+    if (!src.is_float) {
+        for (int i = 0; i < SINC_LEN; i++) t2.he[i] *= src.scale;
+        for (int i = 0; i < SINC_LEN + 8; i++) t2.ho[i] *= src.scale;
+        s2.scale = 1.0f;
+    }
+    resample_int_tma_kernel<STEP, SRCW><<<(unsigned)grid, kIntThreads, smem, ctx->stream>>>(t2, s2, dst, plan->i0_first, (unsigned)tiles_per_stream,
                                                                                           (unsigned)total, d_table + SINC_LEN);
     SK_LAUNCH_CHECK(ctx);
     return SK_OK;
