@@ -159,13 +159,40 @@ __device__ __forceinline__ void n48_frame(const uint8_t* p, float& l, float& r) 
 }
 __device__ __forceinline__ float n48_clamp1(float x) { return fminf(fmaxf(x, -1.0f), 1.0f); }  // finite_pcm of a finite value
 
+// Integer formats, fast loop: the frame as UNSCALED floats (the integer value).  The exact power-of-two scale commutes with
+// every rounding of `lo + ((up - lo) * frac)`, so it is applied once to the result instead of to the four inputs, and the
+// result of interpolating between values in [-1, 1] needs no clamp.  fb4: the frame is one aligned 32-bit word (s16 stereo).
+template <int W, bool BE, bool ST>
+__device__ __forceinline__ void n48_frame_raw(const uint8_t* p, bool fb4, float& l, float& r) {
+    if (W == 2) {
+        uint32_t u;
+        if (ST && fb4) u = *reinterpret_cast<const uint32_t*>(p);
+        else u = *reinterpret_cast<const uint16_t*>(p) | (ST ? (uint32_t)*reinterpret_cast<const uint16_t*>(p + 2) << 16 : 0u);
+        if (BE) u = __byte_perm(u, 0, 0x2301);
+        l = (float)(int16_t)(u & 0xffffu);
+        r = ST ? (float)(int16_t)(u >> 16) : l;
+    } else if (W == 3) {
+        const uint32_t a = n48_lds<3>(p);
+        l = (float)(((int32_t)(BE ? __byte_perm(a, 0, 0x0124) : __byte_perm(a, 0, 0x2104))) >> 8);
+        if (ST) { const uint32_t b = n48_lds<3>(p + 3); r = (float)(((int32_t)(BE ? __byte_perm(b, 0, 0x0124) : __byte_perm(b, 0, 0x2104))) >> 8); }
+        else r = l;
+    } else {
+        uint32_t a = *reinterpret_cast<const uint32_t*>(p);
+        if (BE) a = bswap32(a);
+        l = __int2float_rn((int32_t)a);
+        if (ST) { uint32_t b = *reinterpret_cast<const uint32_t*>(p + 4); if (BE) b = bswap32(b); r = __int2float_rn((int32_t)b); }
+        else r = l;
+    }
+}
+template <int W> __device__ __forceinline__ float n48_scale() { return W == 2 ? 1.0f / 32768.0f : (W == 3 ? 1.0f / 8388608.0f : 4.656612873077393e-10f); }
+
 constexpr int kN48MaxVec = 4;  // 128-bit vectors of one staged run a thread may hold in registers (prefetch of the next stream)
 
 // Outputs of a tile are dealt to threads round-robin (thread t owns outputs t, t + 256, t + 512, t + 768 of the tile):
 // consecutive lanes read consecutive source frames (conflict-free shared-memory reads) and write consecutive floats
 // (one 128-byte line per warp store).  The staged run is double buffered: the global loads of the NEXT stream are in
 // flight while the current stream is interpolated, and there is one barrier per stream.
-template <int W, bool BE, bool FLT, bool ST>
+template <int W, bool BE, bool FLT, bool ST, bool FB4>  // FB4: a frame is exactly one aligned 32-bit word (16-bit stereo)
 __global__ void __launch_bounds__(kN48Threads)
 norm48k_tile_kernel(const __grid_constant__ N48Src src, unsigned long long o_start, unsigned long long n_lerp, unsigned long long n_total,
                     unsigned rate, float prev_l, float prev_r, float* __restrict__ out_l, float* __restrict__ out_r, long long out_stride,
@@ -204,36 +231,33 @@ norm48k_tile_kernel(const __grid_constant__ N48Src src, unsigned long long o_sta
 #pragma unroll
     for (int k = 0; k < 4; k++) need_last |= off[k] == -2 && t0 + (unsigned)(k * kN48Threads) + threadIdx.x < n_total;
 
-    // ---- staging helpers: the run [f_lo, f_hi] of stream s as 16-byte vectors around it
+    // ---- staging: the run [f_lo, f_hi] of a stream as 16-byte vectors around it.  Base and stride are 16-byte aligned on
+    // this path, so the run's offset inside a stream, its length and its skew are the same for every stream.
+    const long long g_off = f_lo * fb;                        // byte offset of frame f_lo inside a stream
+    const long long a_off = g_off & ~15ll;                    // ... rounded down to a vector
+    const int skew = (int)(g_off - a_off);
+    const int run = f_hi >= f_lo ? (int)((f_hi + 1) * fb - a_off) : 0;
+    const long long safe = (long long)src.frames * fb - a_off;  // never read past the caller's buffer
+    const int nvec = (int)min((long long)((run + 15) >> 4), safe >> 4);
     uint4 pre[kN48MaxVec];
-    auto run_of = [&](unsigned s, const uint8_t*& a0, int& nvec, long long& run, int& skew) {
-        const uint8_t* sbase = src.base + (long long)s * src.stream_stride;
-        const uint8_t* g0 = sbase + f_lo * fb;
-        a0 = reinterpret_cast<const uint8_t*>((uintptr_t)g0 & ~(uintptr_t)15);
-        skew = (int)(g0 - a0);
-        run = f_hi >= f_lo ? (sbase + (f_hi + 1) * fb) - a0 : 0;
-        const long long safe = (sbase + (long long)src.frames * fb) - a0;  // never read past the caller's buffer
-        nvec = (int)(min((run + 15) >> 4, safe >> 4));
-    };
     auto prefetch = [&](unsigned s) {
-        const uint8_t* a0; int nvec, skew; long long run;
-        run_of(s, a0, nvec, run, skew);
+        const uint4* a0 = reinterpret_cast<const uint4*>(src.base + (long long)s * src.stream_stride + a_off);
 #pragma unroll
         for (int j = 0; j < kN48MaxVec; j++) {
             const int v = threadIdx.x + j * kN48Threads;
-            if (v < nvec) pre[j] = ld_stream_v4_nv(reinterpret_cast<const uint4*>(a0) + v);
+            if (v < nvec) pre[j] = ld_stream_v4_nv(a0 + v);
         }
     };
     auto commit = [&](unsigned s, uint8_t* buf) {  // registers -> shared memory, plus the bytes after the last whole vector
-        const uint8_t* a0; int nvec, skew; long long run;
-        run_of(s, a0, nvec, run, skew);
 #pragma unroll
         for (int j = 0; j < kN48MaxVec; j++) {
             const int v = threadIdx.x + j * kN48Threads;
             if (v < nvec) reinterpret_cast<uint4*>(buf)[v] = pre[j];
         }
-        for (long long b = (long long)nvec * 16 + threadIdx.x; b < run; b += kN48Threads) buf[b] = a0[b];
-        return skew;
+        if (nvec * 16 < run) {
+            const uint8_t* a0 = src.base + (long long)s * src.stream_stride + a_off;
+            for (int b = nvec * 16 + threadIdx.x; b < run; b += kN48Threads) buf[b] = a0[b];
+        }
     };
 
     unsigned s = blockIdx.y;
@@ -241,13 +265,24 @@ norm48k_tile_kernel(const __grid_constant__ N48Src src, unsigned long long o_sta
     int cur = 0;
     for (; s < n_streams; s += gridDim.y, cur ^= 1) {
         uint8_t* buf = n48_raw + cur * buf_bytes;
-        const int skew = commit(s, buf);
+        commit(s, buf);
         __syncthreads();  // buf complete; the other buffer (read two streams ago) is free for the next commit
         if (s + gridDim.y < n_streams) prefetch(s + gridDim.y);
         const uint8_t* sm = buf + skew;  // frame f_lo
         float* pl = out_l + (long long)s * out_stride + t0 + threadIdx.x;
         float* pr = out_r + (long long)s * out_stride + t0 + threadIdx.x;
-        if (plain) {
+        if (plain && !FLT) {
+            constexpr bool fb4 = FB4;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float ll, rl, lu, ru;
+                n48_frame_raw<W, BE, ST>(sm + off[k], fb4, ll, rl);
+                if (passthrough) { pl[k * kN48Threads] = __fmul_rn(ll, n48_scale<W>()); pr[k * kN48Threads] = __fmul_rn(rl, n48_scale<W>()); continue; }
+                n48_frame_raw<W, BE, ST>(sm + off[k] + fb, fb4, lu, ru);
+                pl[k * kN48Threads] = __fmul_rn(__fadd_rn(ll, __fmul_rn(__fsub_rn(lu, ll), fr[k])), n48_scale<W>());
+                pr[k * kN48Threads] = __fmul_rn(__fadd_rn(rl, __fmul_rn(__fsub_rn(ru, rl), fr[k])), n48_scale<W>());
+            }
+        } else if (plain) {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 float ll, rl, lu, ru;
@@ -341,13 +376,18 @@ static int n48_launch(sk_ctx* ctx, const N48Src& src, unsigned long long o_start
         const dim3 grid((unsigned)gx, gy);
         const int buf_bytes = (int)sk_round_up((size_t)span_bytes + 32, 16);
         const size_t smem = 2 * (size_t)buf_bytes;
-#define N48_LAUNCH(W_, BE_, FLT_, ST_)                                                                                                        \
+#define N48_LAUNCH(W_, BE_, FLT_, ST_, FB4_)                                                                                                        \
         do {                                                                                                                                  \
-            SK_CUDA(ctx, cudaFuncSetAttribute(norm48k_tile_kernel<W_, BE_, FLT_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-            norm48k_tile_kernel<W_, BE_, FLT_, ST_><<<grid, kN48Threads, smem, ctx->stream>>>(src, o_start, n_lerp, n_total, rate, prev_l, prev_r, \
+            SK_CUDA(ctx, cudaFuncSetAttribute(norm48k_tile_kernel<W_, BE_, FLT_, ST_, FB4_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+            norm48k_tile_kernel<W_, BE_, FLT_, ST_, FB4_><<<grid, kN48Threads, smem, ctx->stream>>>(src, o_start, n_lerp, n_total, rate, prev_l, prev_r, \
                                                                                               out_l, out_r, out_stride, (unsigned)n_streams, final_lr, buf_bytes); \
         } while (0)
-#define N48_LAUNCH_ST(W_, BE_, FLT_) do { if (src.channels > 1) N48_LAUNCH(W_, BE_, FLT_, true); else N48_LAUNCH(W_, BE_, FLT_, false); } while (0)
+#define N48_LAUNCH_ST(W_, BE_, FLT_)                                                                  \
+        do {                                                                                          \
+            if (W_ == 2 && src.channels == 2) N48_LAUNCH(W_, BE_, FLT_, true, (W_ == 2));             \
+            else if (src.channels > 1) N48_LAUNCH(W_, BE_, FLT_, true, false);                        \
+            else N48_LAUNCH(W_, BE_, FLT_, false, false);                                             \
+        } while (0)
         const bool be = src.big_endian != 0;
         if (src.width == 2) { if (be) N48_LAUNCH_ST(2, true, false); else N48_LAUNCH_ST(2, false, false); }
         else if (src.width == 3) { if (be) N48_LAUNCH_ST(3, true, false); else N48_LAUNCH_ST(3, false, false); }
