@@ -252,6 +252,8 @@ struct SrcDesc {
     int width;                // 0 = planar f32, 2/3/4 = interleaved sample bytes
     int channels;             // channels per stream
     int big_endian, is_float, scrub;
+    int pair_ok;              // base and stride are 8-byte aligned: a stereo frame may be fetched with one 4 / 8-byte load
+    int byte_loads;           // base or stride not aligned to the sample width: assemble 16 / 32-bit samples from bytes
     float scale;              // exact power of two for integer sources
     long long origin;         // frame index i lives at element i + origin
     long long valid_lo, valid_hi;  // frames outside [lo, hi) read as 0.0 (initial history / flush padding)
@@ -273,6 +275,11 @@ __device__ __forceinline__ float decode_sample_bits(uint32_t u, const SrcDesc& s
 __device__ __forceinline__ uint32_t load_sample_bits(const uint8_t* sbase, long long f, int ch, const SrcDesc& s) {
     const uint8_t* p = sbase + ((f + s.origin) * s.channels + ch) * (long long)s.width;
     uint32_t u;
+    if (s.byte_loads) {  // a caller's slice may start at any byte
+        u = 0;
+        for (int b = 0; b < s.width; b++) u |= (uint32_t)p[b] << (8 * (s.big_endian ? s.width - 1 - b : b));
+        return u;
+    }
     if (s.width == 2) { u = *reinterpret_cast<const uint16_t*>(p); if (s.big_endian) u = ((u & 0xff) << 8) | (u >> 8); }
     else if (s.width == 3) {
         uint32_t b0 = p[0], b1 = p[1], b2 = p[2];
@@ -302,7 +309,7 @@ __device__ __forceinline__ bool stage_window(const SrcDesc& s, long long stream,
         }
     } else {
         const uint8_t* sbase = s.base + stream * s.stream_stride;
-        const bool stereo_pair = (s.channels == 2) && lane1_valid && lane0 == 0;
+        const bool stereo_pair = (s.channels == 2) && lane1_valid && lane0 == 0 && s.pair_ok;
         for (int i = threadIdx.x; i < count; i += NTHREADS) {
             const long long f = w0 + i;
             float a = 0.0f, b = 0.0f;
@@ -985,6 +992,8 @@ static int src_desc_for(sk_ctx* ctx, SrcDesc* s, const void* in, size_t in_strid
     if (bits != 16 && bits != 24 && bits != 32) SK_FAIL(ctx, SK_E_ARG, "Unsupported bits_per_sample: %d", bits);
     if (fmt == SK_FMT_FLOAT && bits != 32) SK_FAIL(ctx, SK_E_ARG, "floating-point PCM must contain 32-bit samples");
     s->width = bits / 8;
+    s->pair_ok = (((uintptr_t)in | (uintptr_t)in_stride) & 7) == 0;
+    s->byte_loads = s->width != 3 && (((uintptr_t)in | (uintptr_t)in_stride) & (uintptr_t)(s->width - 1)) != 0;
     s->big_endian = scale_mode == SK_MODE_B ? (big_endian != 0) : 0;  // mode A is always little-endian
     s->is_float = fmt == SK_FMT_FLOAT;
     s->scrub = scale_mode == SK_MODE_B;

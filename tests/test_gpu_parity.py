@@ -702,3 +702,76 @@ def test_contexts_on_concurrent_threads_do_not_interfere(oracle):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+# ---------------------------------------------------------------------------------------------- unaligned device buffers
+def test_device_entry_points_with_unaligned_pointers_match_oracle(oracle):
+    """callers may hand in device pointers at any offset (a Rust slice into a larger buffer): the vector / TMA kernels
+    need 16-byte alignment, everything else must take the scalar kernels and still be exact"""
+    import torch
+    c = capi.Context(0)
+    c.use_torch_stream()
+    rng = np.random.default_rng(99)
+
+    def dev(a, off):  # device copy of `a` placed `off` bytes into an allocation
+        raw = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+        buf = torch.zeros(raw.size + off + 64, dtype=torch.uint8, device="cuda")
+        buf[off:off + raw.size] = torch.from_numpy(raw).cuda()
+        return buf, buf[off:off + raw.size]
+
+    for off_in, off_out in ((1, 0), (0, 2), (3, 6), (16, 16)):
+        n = 5003
+        codes = rng.integers(0, 256, n, dtype=np.uint8)
+        _, d_in = dev(codes, off_in)
+        obuf, d_out = dev(np.zeros(n, np.int16), off_out & ~1)
+        c.g711_decode_dev(capi.LAW_MULAW, d_in, n, capi.KIND_I16, d_out)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy().view(np.int16), oracle.g711_decode(0, codes))
+        pcm = rng.integers(-32768, 32768, n).astype(np.int16)
+        _, d_pcm = dev(pcm, off_in & ~1)
+        _, d_codes = dev(np.zeros(n, np.uint8), off_out + 1)
+        c.g711_encode_dev(capi.LAW_ALAW, capi.KIND_I16, d_pcm, n, d_codes)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_codes.cpu().numpy(), oracle.g711_encode(1, pcm))
+        s24 = rng.integers(0, 256, 3 * n, dtype=np.uint8)
+        _, d_s24 = dev(s24, off_in)
+        _, d_i32 = dev(np.zeros(n, np.int32), off_out & ~3)
+        c.flat_convert_dev("s24le_to_i32", d_s24, 3 * n, d_i32)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_i32.cpu().numpy().view(np.int32), oracle.flat("s24le_to_i32", s24))
+    # fused chain and 48 kHz normalizer from a stream that starts 2 bytes into an allocation (no TMA / no staged path)
+    frames = 20011
+    v = rng.integers(-(1 << 15), 1 << 15, frames * 2).astype(np.int16)
+    _, d_v = dev(v, 2)
+    n_out = c.batch_plan(48000, 16000, frames, capi.SEM_STREAMING)
+    out = torch.zeros(n_out + 8, dtype=torch.float32, device="cuda")
+    d = capi.BatchDesc(d_v.data_ptr(), frames * 4, 1, frames, 16, capi.FMT_SIGNED, 0, 2, capi.MODE_B, 48000, 16000, capi.SEM_STREAMING,
+                       capi.MIX_SCALE_THEN_SUM, out.data_ptr(), n_out, 0)
+    c.normalize_batch_dev(d)
+    torch.cuda.synchronize()
+    want = oracle.normalize_chain_mono(v.view(np.uint8), 16, oracle.SIGNED, False, 2, 48000, 16000)
+    assert np.array_equal(out[:n_out].cpu().numpy().view(np.uint32), want.view(np.uint32))
+    # other widths at offsets that break the paired loads (4) and the sample alignment itself (1, 2)
+    for bits, fmt, off in ((16, 0, 1), (24, 0, 1), (32, 0, 4), (32, 1, 2), (32, 1, 1)):
+        fr2 = 9001
+        raw = rng.integers(0, 256, fr2 * 2 * (bits // 8), dtype=np.uint8)
+        if fmt == 1:
+            raw = rng.uniform(-1, 1, fr2 * 2).astype(np.float32).view(np.uint8)
+        _, d_raw = dev(raw, off)
+        for (ir, orr) in ((48000, 16000), (44100, 48000)):
+            n2 = c.batch_plan(ir, orr, fr2, capi.SEM_ONESHOT)
+            o2 = torch.zeros((2, n2), dtype=torch.float32, device="cuda")
+            dd = capi.BatchDesc(d_raw.data_ptr(), raw.size, 1, fr2, bits, fmt, 0, 2, capi.MODE_A, ir, orr, capi.SEM_ONESHOT, capi.MIX_NONE,
+                                o2.data_ptr(), 2 * n2, n2)
+            c.normalize_batch_dev(dd)
+            torch.cuda.synchronize()
+            w2 = oracle.downsample_audio(raw, bits, fmt, 2, ir, orr)
+            assert np.array_equal(o2.cpu().numpy().view(np.uint32), w2.view(np.uint32)), (bits, fmt, off, ir)
+    n48 = c.normalize48k_out_frames(frames, 44100)
+    o48 = torch.zeros((2, n48 + 3), dtype=torch.float32, device="cuda")
+    c.normalize48k_batch_dev(d_v, frames * 4, 1, frames, 16, 0, False, 2, 44100, o48[:, 1:], 2 * (n48 + 3), n48 + 3)  # output 4 bytes off alignment too
+    torch.cuda.synchronize()
+    wl, wr = oracle.normalize48k([(v.view(np.uint8), 16, 0, False, 2, 44100)])
+    got = o48.cpu().numpy()
+    assert np.array_equal(got[0, 1:1 + n48].view(np.uint32), wl.view(np.uint32)) and np.array_equal(got[1, 1:1 + n48].view(np.uint32), wr.view(np.uint32))
+    c.close()
