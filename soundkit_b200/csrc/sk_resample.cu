@@ -200,6 +200,10 @@ static bool integer_step_of(uint32_t in_rate, uint32_t out_rate, int* step) {
 
 // whole-stream plan for the batch entry points
 static int build_stream_plan(sk_ctx* ctx, uint32_t in_rate, uint32_t out_rate, size_t frames, int semantics, sk_plan** out) {
+    // frame and output indices travel as int32 inside the kernels (12.4 hours at 48 kHz): refuse longer streams loudly
+    if (frames > 0x7fff0000ull || (double)frames * (double)out_rate / (double)in_rate > 2.0e9)
+        SK_FAIL(ctx, SK_E_ARG, "stream of %zu frames is too long for one call (limit 2^31 frames in and out); split it", frames);
+    if (semantics != SK_SEM_ONESHOT && semantics != SK_SEM_STREAMING) SK_FAIL(ctx, SK_E_ARG, "unknown resample semantics %d", semantics);
     char key[96];
     snprintf(key, sizeof(key), "%u:%u:%zu:%d", in_rate, out_rate, frames, semantics);
     auto it = ctx->plans.find(key);
