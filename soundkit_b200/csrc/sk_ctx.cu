@@ -217,34 +217,6 @@ extern "C" int sk_ctx_measure_ffma_peaks(sk_ctx* ctx, double* scalar_tflops, dou
     return SK_OK;
 }
 
-static int measure_ffma_peak_unused(sk_ctx* ctx, double* tflops) {
-    if (!ctx || !tflops) return SK_E_ARG;
-    SK_CUDA(ctx, cudaSetDevice(ctx->device));
-    int rc = sk_ensure_dev_out(ctx, 256);
-    if (rc) return rc;
-    const int iters = 4096, blocks = ctx->num_sms * 8, threads = 256;
-    cudaEvent_t e0, e1;
-    SK_CUDA(ctx, cudaEventCreate(&e0));
-    SK_CUDA(ctx, cudaEventCreate(&e1));
-    double best = 0.0;
-    for (int rep = 0; rep < 5; rep++) {
-        cudaEventRecord(e0, ctx->stream);
-        ffma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((float*)ctx->d_out, 0.999f, 0.001f, iters);
-        cudaEventRecord(e1, ctx->stream);
-        SK_LAUNCH_CHECK(ctx);
-        SK_CUDA(ctx, cudaEventSynchronize(e1));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, e0, e1);
-        double flops = 2.0 * (double)blocks * threads * (double)iters * 8.0 * 16.0;
-        double t = flops / (ms * 1e-3) / 1e12;
-        if (rep > 0 && t > best) best = t;
-    }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    *tflops = best;
-    return SK_OK;
-}
-
 // FP32 FMA peak of this device: the better of the scalar (FFMA) and packed (FFMA2) microbenchmarks
 extern "C" int sk_ctx_measure_ffma_peak(sk_ctx* ctx, double* tflops) {
     if (!ctx || !tflops) return SK_E_ARG;

@@ -134,30 +134,33 @@ constexpr int kPcmWarps = kPcmThreads / 32;
 // NV*512 bytes of warp-private shared memory.  NV == 1 needs no exchange.
 template <int NV>
 __device__ __forceinline__ void warp_load_spans(uint4* xch, const uint4* __restrict__ gsrc, uint32_t* w, int lane) {
-    if (NV <= 2) {  // measured: up to two vectors per lane, direct L1-allocating loads of the lane's own span are as fast or faster
+    if constexpr (NV <= 2) {  // measured: up to two vectors per lane, direct L1-allocating loads of the lane's own span are as fast or faster
 #pragma unroll
         for (int v = 0; v < NV; v++) { const uint4 q = __ldg(gsrc + lane * NV + v); w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w; }
-        return;
+    } else {
+        uint4 r[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) r[v] = ld_stream_v4_nv(gsrc + v * 32 + lane);
+        __syncwarp();
+#pragma unroll
+        for (int v = 0; v < NV; v++) xch[v * 32 + lane] = r[v];
+        __syncwarp();
+#pragma unroll
+        for (int v = 0; v < NV; v++) { const uint4 q = xch[lane * NV + v]; w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w; }
     }
-    uint4 r[NV];
-#pragma unroll
-    for (int v = 0; v < NV; v++) r[v] = ld_stream_v4_nv(gsrc + v * 32 + lane);
-    __syncwarp();
-#pragma unroll
-    for (int v = 0; v < NV; v++) xch[v * 32 + lane] = r[v];
-    __syncwarp();
-#pragma unroll
-    for (int v = 0; v < NV; v++) { const uint4 q = xch[lane * NV + v]; w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w; }
 }
 template <int NV>
 __device__ __forceinline__ void warp_store_spans(uint4* xch, uint4* __restrict__ gdst, const uint32_t* o, int lane) {
-    if (NV == 1) { st_stream_v4(gdst + lane, make_uint4(o[0], o[1], o[2], o[3])); return; }
-    __syncwarp();
+    if constexpr (NV == 1) {
+        st_stream_v4(gdst + lane, make_uint4(o[0], o[1], o[2], o[3]));
+    } else {
+        __syncwarp();
 #pragma unroll
-    for (int v = 0; v < NV; v++) xch[lane * NV + v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
-    __syncwarp();
+        for (int v = 0; v < NV; v++) xch[lane * NV + v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+        __syncwarp();
 #pragma unroll
-    for (int v = 0; v < NV; v++) st_stream_v4(gdst + v * 32 + lane, xch[v * 32 + lane]);
+        for (int v = 0; v < NV; v++) st_stream_v4(gdst + v * 32 + lane, xch[v * 32 + lane]);
+    }
 }
 
 // G samples per lane: input G*B bytes = NV_IN 16-byte vectors, output G*OB bytes = NV_OUT vectors; a warp owns 32 groups
