@@ -828,7 +828,7 @@ resample_gen_kernel(const __grid_constant__ SrcDesc src, const __grid_constant__
 // one register window serves both) of two PERIODS (k and k + 32: same phases, hence the same four table rows).
 // Per 8 taps: 16 + 2*DELTA shared-memory loads and 8 table loads feed 64 FMAs (0.39 loads per FMA instead of 0.81).
 // Each of the 8 dot products keeps rubato's 8 lane accumulators and reduction tree, and `p0 + frac * (p1 - p0)` uses the
-// output's own frac, so results stay bit-identical to v1 and to the oracle.
+// output's own frac, so results stay bit-identical to v1 (and to the CPU restatement the tests compare against).
 // The tile mapping needs warp-uniform rows: all lanes of a warp sit at the same position inside the phase period, which
 // fixes (subindex, DELTA) except where the f64 walk lands within rounding of an integer; such warps (and ragged tile
 // ends, and subindex 255 whose second product starts one sample later) take the v1 arithmetic per output.
