@@ -775,3 +775,37 @@ def test_device_entry_points_with_unaligned_pointers_match_oracle(oracle):
     got = o48.cpu().numpy()
     assert np.array_equal(got[0, 1:1 + n48].view(np.uint32), wl.view(np.uint32)) and np.array_equal(got[1, 1:1 + n48].view(np.uint32), wr.view(np.uint32))
     c.close()
+
+
+# ---------------------------------------------------------------------------------------------- full-size properties
+def test_f32_deinterleave_interleave_round_trip_at_config_size():
+    """BASELINE configs[1] wave (64 streams x 60 s f32le stereo 48 kHz, 1.5 GB): deinterleave_vecs_f32 followed by
+    interleave_vecs_f32 (f32_channels_to_bytes, PCMFloat) is the identity on the BYTES, NaN payloads and -0.0 included;
+    s16 -> planar f32 -> float_sample_to_i16 is checked the same way through its closed form."""
+    import torch
+    c = capi.Context(0)
+    c.use_torch_stream()
+    S, frames = 64, 2880000
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    raw = torch.randint(0, 256, (S, frames * 8), dtype=torch.uint8, device="cuda", generator=g)  # arbitrary bit patterns incl. NaNs
+    planar = torch.empty((S, 2, frames), dtype=torch.float32, device="cuda")
+    c.pcm_to_planar_f32_dev(raw, raw.stride(0), S, frames, 32, capi.FMT_FLOAT, False, 2, capi.MODE_A, planar, 2 * frames)
+    back = torch.empty((frames * 8,), dtype=torch.uint8, device="cuda")
+    for s in (0, 17, S - 1):
+        c.planar_f32_to_pcm_dev(planar[s], frames, 2, 32, capi.FMT_FLOAT, back)
+        torch.cuda.synchronize()
+        assert torch.equal(back, raw[s]), s
+    del planar, back
+    # s16: x / 32768 then float_sample_to_i16: negative values scale back by 32768 (identity), positive by 32767:
+    # round(v * 32767 / 32768) = round(v - v / 32768) = v - (1 if v > 16384 else 0) for v >= 0 (v = 16384 is the one tie:
+    # 16383.5 rounds half away from zero, back to 16384)
+    raw16 = torch.randint(-32768, 32768, (frames * 2,), dtype=torch.int16, device="cuda", generator=g)
+    p16 = torch.empty((2, frames), dtype=torch.float32, device="cuda")
+    c.pcm_to_planar_f32_dev(raw16, frames * 4, 1, frames, 16, capi.FMT_SIGNED, False, 2, capi.MODE_B, p16, 2 * frames)
+    b16 = torch.empty((frames * 2,), dtype=torch.int16, device="cuda")
+    c.planar_f32_to_pcm_dev(p16, frames, 2, 16, capi.FMT_SIGNED, b16)
+    torch.cuda.synchronize()
+    want = raw16.to(torch.int32)
+    want = torch.where(want > 16384, want - 1, want).to(torch.int16)
+    assert torch.equal(b16, want)
+    c.close()
