@@ -219,6 +219,19 @@ def extras(ctx, torch, peaks, only=None):
             res[f"convert_{name}_stereo_to_planar_f32"] = hbm_entry(nb, t, S * frames * 2)
             del raw
         del out
+    if want("bytes"):
+        # the headline chain with the byte epilogue: s24le stereo 48 kHz -> s16le mono 16 kHz (apply_output_options for ASR), 8 streams x 600 s
+        S, frames = 8, 28800000
+        n_out = ctx.batch_plan(48000, 16000, frames, capi.SEM_STREAMING)
+        stride = (frames * 6 + 15) // 16 * 16
+        raw = torch.randint(0, 256, (S, stride), dtype=torch.uint8, device="cuda")
+        ostride = (n_out * 2 + 15) // 16 * 16
+        o = torch.empty((S, ostride), dtype=torch.uint8, device="cuda")
+        d = capi.BatchDesc(raw.data_ptr(), stride, S, frames, 24, capi.FMT_SIGNED, 0, 2, capi.MODE_B, 48000, 16000, capi.SEM_STREAMING,
+                           capi.MIX_SCALE_THEN_SUM, 0, 0, 0)
+        t = timed(lambda: ctx.normalize_batch_pcm_dev(d, 16, 0, o, ostride), reps=3)
+        res["chain_s24_stereo_48k_to_s16_mono_16k_bytes"] = {"Msamples/s": S * n_out / t / 1e6, "TFLOP/s": 1024.0 * S * n_out / t / 1e12}
+        del raw, o
     if want("flat"):
         # a few of the remaining R1 entry points (soundkit/src/audio_bytes.rs flat functions, f32_channels_to_bytes)
         n = 1 << 28

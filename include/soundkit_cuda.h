@@ -229,6 +229,14 @@ typedef struct {
 int sk_normalize_batch_plan(sk_ctx*, uint32_t in_rate, uint32_t out_rate, size_t frames, int semantics,
                             size_t* n_out);
 int sk_normalize_batch_dev(sk_ctx*, const sk_batch_desc* desc);
+/* The same chain with BYTES out: apply_output_options' rate-changing arm down to one channel (soundkit-decoder/src/lib.rs:
+ * 3324-3456), i.e. convert -> resample -> downmix -> f32_channels_to_bytes (:3619-3683) for a device-resident batch.
+ * desc->out / out_stride / out_stride_ch are ignored; the result must be mono (channels == 1 or mix_mode != NONE).
+ * out[s] = n_out samples of out_bits / 8 little-endian bytes, out_stride_bytes between streams; out_fmt FLOAT needs
+ * out_bits 32 (the reference only emits PCMFloat when the INPUT was float — that choice stays with the caller, :3377-3382).
+ * Two-channel integer-ratio sources (48 -> 16 kHz ...) are quantised inside the fused kernel; other combinations take an
+ * f32 scratch and one more pass. */
+int sk_normalize_batch_pcm_dev(sk_ctx*, const sk_batch_desc* desc, int out_bits, int out_fmt, void* out, size_t out_stride_bytes);
 /* host-pointer form of the batch call: desc->in / desc->out are HOST pointers (pinned memory gives
  * full PCIe rate).  Streams are processed in slabs; the H2D copy of the next slab and the D2H copy of
  * the previous one overlap the kernel of the current one.  Returns when every result is in `out`. */

@@ -105,6 +105,8 @@ extern "C" {
     pub fn sk_normalize_batch_plan(ctx: *mut sk_ctx, in_rate: u32, out_rate: u32, frames: usize, semantics: c_int, n_out: *mut usize) -> c_int;
     pub fn sk_normalize_batch_dev(ctx: *mut sk_ctx, desc: *const sk_batch_desc) -> c_int;
     pub fn sk_normalize_batch(ctx: *mut sk_ctx, desc: *const sk_batch_desc) -> c_int;
+    pub fn sk_normalize_batch_pcm_dev(ctx: *mut sk_ctx, desc: *const sk_batch_desc, out_bits: c_int, out_fmt: c_int, out: *mut c_void,
+                                      out_stride_bytes: usize) -> c_int;
     pub fn sk_normalize_stream(ctx: *mut sk_ctx, input: *const u8, bytes: usize, bits: c_int, fmt: c_int, big_endian: c_int, channels: c_int,
                                scale_mode: c_int, in_rate: u32, out_rate: u32, semantics: c_int, mix_mode: c_int, out: *mut c_float,
                                out_cap_per_plane: usize, n_out: *mut usize) -> c_int;

@@ -39,7 +39,7 @@ EXPORTS = (
     "sk_planar_f32_to_pcm_dev", "sk_pcm_narrow_i16", "sk_mixdown_mono", "sk_mixdown_mono_dev", "sk_downmix_stereo",
     "sk_resampler_create", "sk_resampler_destroy", "sk_resampler_out_max", "sk_resampler_last_index",
     "sk_resampler_process", "sk_resampler_process_partial", "sk_resampler_copy_table",
-    "sk_normalize_batch_plan", "sk_normalize_batch_dev", "sk_normalize_batch", "sk_normalize_stream",
+    "sk_normalize_batch_plan", "sk_normalize_batch_dev", "sk_normalize_batch_pcm_dev", "sk_normalize_batch", "sk_normalize_stream",
     "sk_norm48k_create", "sk_norm48k_destroy", "sk_norm48k_push", "sk_norm48k_finish", "sk_norm48k_source_frames",
     "sk_norm48k_output_frames", "sk_norm48k_source_sample_rate", "sk_norm48k_source_channels", "sk_norm48k_max_output",
     "sk_normalize48k_out_frames", "sk_normalize48k_batch_dev",
@@ -120,6 +120,7 @@ def load():
         "sk_normalize_batch_plan": (i, [vp, u32, u32, sz, i, psz]),
         "sk_normalize_batch_dev": (i, [vp, C.POINTER(BatchDesc)]),
         "sk_normalize_batch": (i, [vp, C.POINTER(BatchDesc)]),
+        "sk_normalize_batch_pcm_dev": (i, [vp, C.POINTER(BatchDesc), i, i, vp, sz]),
         "sk_normalize_stream": (i, [vp, vp, sz, i, i, i, i, i, u32, u32, i, i, vp, sz, psz]),
         "sk_norm48k_create": (i, [vp, C.POINTER(vp)]),
         "sk_norm48k_destroy": (None, [vp]),
@@ -337,6 +338,9 @@ class Context:
 
     def normalize_batch_dev(self, desc):
         self._ck(self.L.sk_normalize_batch_dev(self.h, C.byref(desc)))
+
+    def normalize_batch_pcm_dev(self, desc, out_bits, out_fmt, d_out, out_stride_bytes):
+        self._ck(self.L.sk_normalize_batch_pcm_dev(self.h, C.byref(desc), out_bits, out_fmt, _p(d_out), out_stride_bytes))
 
     def normalize_batch_host(self, desc):
         self._ck(self.L.sk_normalize_batch(self.h, C.byref(desc)))

@@ -26,6 +26,7 @@ struct sk_ctx {
     void* h_stage = nullptr; size_t h_cap = 0;
     void* d_in = nullptr;    size_t d_in_cap = 0;
     void* d_out = nullptr;   size_t d_out_cap = 0;
+    void* d_tmp = nullptr;   size_t d_tmp_cap = 0;     // scratch of sk_normalize_batch_pcm_dev (mono f32 before quantisation)
     void* batch_pipe = nullptr;                       // sk_resample.cu: slab pipeline of sk_normalize_batch (streams, events, device slabs)
     bool g726_tables_ready = false;                   // sk_g726.cu: __constant__ tables uploaded on this device
     // sinc tables per ratio, built lazily
@@ -100,4 +101,25 @@ __device__ __forceinline__ void st_stream_v2(void* p, uint2 v) {
     asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// ---- float -> integer sample quantisers shared by sk_pcm.cu (f32_channels_to_bytes) and the fused chain's byte epilogue
+// Rust f32::clamp(-1.0, 1.0): NaN stays NaN
+__device__ __forceinline__ float clamp1(float x) { return x < -1.0f ? -1.0f : (x > 1.0f ? 1.0f : x); }
+__device__ __forceinline__ bool finite_f(float x) { return (__float_as_uint(x) & 0x7f800000u) != 0x7f800000u; }
+
+// float_sample_to_i16, soundkit-decoder/src/lib.rs:1815-1827 (f64 scale, round half away from zero)
+__device__ __forceinline__ int32_t float_sample_to_i16_dev(float s) {
+    float f = finite_f(s) ? clamp1(s) : 0.0f;
+    double scaled = f < 0.0f ? __dmul_rn((double)f, 32768.0) : __dmul_rn((double)f, 32767.0);
+    int32_t r = __double2int_rz(round(scaled));
+    return max(-32768, min(32767, r));
+}
+// audio_bytes.rs:205-220 / decoder lib.rs:3653-3659
+__device__ __forceinline__ int32_t f32_to_s24_dev(float x) {
+    float c = clamp1(x);
+    return c >= 0.0f ? __float2int_rz(__fmul_rn(c, 8388607.0f)) : __float2int_rz(__fmul_rn(c, 8388608.0f));
+}
+// audio_bytes.rs:189-203 / decoder lib.rs:3667-3673: both multipliers are 2^31 in f32, `as` saturates
+__device__ __forceinline__ int32_t f32_to_i32_dev(float x) { return __float2int_rz(__fmul_rn(clamp1(x), 2147483648.0f)); }
+__device__ __forceinline__ int32_t f32_to_i16_trunc_dev(float x) { return __float2int_rz(__fmul_rn(clamp1(x), 32767.0f)); }
 #endif

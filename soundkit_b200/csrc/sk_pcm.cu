@@ -45,26 +45,6 @@ __device__ __forceinline__ int32_t get_sample(const uint32_t* w, int k) {  // k 
     }
 }
 
-// Rust f32::clamp(-1.0, 1.0): NaN stays NaN
-__device__ __forceinline__ float clamp1(float x) { return x < -1.0f ? -1.0f : (x > 1.0f ? 1.0f : x); }
-__device__ __forceinline__ bool finite_f(float x) { return (__float_as_uint(x) & 0x7f800000u) != 0x7f800000u; }
-
-// float_sample_to_i16, soundkit-decoder/src/lib.rs:1815-1827 (f64 scale, round half away from zero)
-__device__ __forceinline__ int32_t float_sample_to_i16_dev(float s) {
-    float f = finite_f(s) ? clamp1(s) : 0.0f;
-    double scaled = f < 0.0f ? __dmul_rn((double)f, 32768.0) : __dmul_rn((double)f, 32767.0);
-    int32_t r = __double2int_rz(round(scaled));
-    return max(-32768, min(32767, r));
-}
-// audio_bytes.rs:205-220 / decoder lib.rs:3653-3659
-__device__ __forceinline__ int32_t f32_to_s24_dev(float x) {
-    float c = clamp1(x);
-    return c >= 0.0f ? __float2int_rz(__fmul_rn(c, 8388607.0f)) : __float2int_rz(__fmul_rn(c, 8388608.0f));
-}
-// audio_bytes.rs:189-203 / decoder lib.rs:3667-3673: both multipliers are 2^31 in f32, `as` saturates
-__device__ __forceinline__ int32_t f32_to_i32_dev(float x) { return __float2int_rz(__fmul_rn(clamp1(x), 2147483648.0f)); }
-__device__ __forceinline__ int32_t f32_to_i16_trunc_dev(float x) { return __float2int_rz(__fmul_rn(clamp1(x), 32767.0f)); }
-
 // ------------------------------------------------------------------------------------------------
 // flat ops
 // ------------------------------------------------------------------------------------------------
@@ -691,6 +671,10 @@ extern "C" int sk_planar_f32_to_pcm_dev(sk_ctx* ctx, const float* planar, size_t
         SK_LAUNCH_CHECK(ctx);
     }
     return SK_OK;
+}
+
+int sk_planar_f32_to_pcm_dev_impl(sk_ctx* ctx, const float* planar, size_t frames, int channels, int bits, int fmt, uint8_t* out) {
+    return sk_planar_f32_to_pcm_dev(ctx, planar, frames, channels, bits, fmt, out);
 }
 
 extern "C" int sk_planar_f32_to_pcm(sk_ctx* ctx, const float* planar, size_t frames, int channels, int bits, int fmt, uint8_t* out) {

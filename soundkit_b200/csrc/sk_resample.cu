@@ -372,7 +372,20 @@ struct OutDesc {
     long long lane_stride;    // floats between channel planes (mix none)
     int mix;                  // sk_mix_mode; != NONE only with exactly two lanes per stream
     long long n_out;
+    // byte epilogue (sk_normalize_batch_pcm_dev): the mono result leaves as f32_channels_to_bytes would write it
+    int pcm_bits = 0;         // 0 = planar f32 (the fields above), else 16 / 24 / 32
+    int pcm_float = 0;        // PCMFloat (32-bit only)
+    uint8_t* pcm_base = nullptr;
+    long long pcm_stream_stride = 0;  // bytes between streams
 };
+
+// one mono sample as f32_channels_to_bytes writes it (soundkit-decoder/src/lib.rs:3619-3683): little-endian bits in the low bytes
+__device__ __forceinline__ uint32_t pcm_quantize(float x, int bits, int is_float) {
+    if (is_float) return __float_as_uint(x);
+    if (bits == 16) return (uint32_t)float_sample_to_i16_dev(x) & 0xffffu;
+    if (bits == 24) return (uint32_t)f32_to_s24_dev(x) & 0xffffffu;
+    return (uint32_t)f32_to_i32_dev(x);
+}
 
 // ================================================================================================
 // integer-step kernel
@@ -475,9 +488,31 @@ __device__ __forceinline__ void int_epilogue(const float (&y)[R], const OutDesc&
             if (dst.mix == SK_MIX_SCALE_THEN_SUM) o[q] = __fadd_rn(__fadd_rn(0.0f, __fmul_rn(l, 0.5f)), __fmul_rn(rr, 0.5f));
             else o[q] = __fmul_rn(__fadd_rn(__fadd_rn(0.0f, l), rr), 0.5f);
         }
-        float* op = dst.base + stream * dst.stream_stride;
         const long long no = nb + (long long)H * lane;  // first output this thread stores
         const int cnt = lane == 0 ? H : R - H;
+        if (dst.pcm_bits) {  // bytes out: quantise the mono samples in registers, 8 / 12 / 16 bytes per thread when aligned
+            uint8_t* bp = dst.pcm_base + stream * dst.pcm_stream_stride;
+            const int ob = dst.pcm_bits >> 3;
+            if (R == 8 && nb + 8 <= dst.n_out && ((dst.pcm_stream_stride & 15) == 0) && (((uintptr_t)dst.pcm_base) & 15) == 0) {
+                uint32_t q4[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) q4[q] = pcm_quantize(o[q], dst.pcm_bits, dst.pcm_float);
+                if (ob == 2) *reinterpret_cast<uint2*>(bp + no * 2) = make_uint2(q4[0] | (q4[1] << 16), q4[2] | (q4[3] << 16));
+                else if (ob == 3) {
+                    uint32_t* w = reinterpret_cast<uint32_t*>(bp + no * 3);
+                    w[0] = q4[0] | (q4[1] << 24); w[1] = (q4[1] >> 8) | (q4[2] << 16); w[2] = (q4[2] >> 16) | (q4[3] << 8);
+                } else *reinterpret_cast<uint4*>(bp + no * 4) = make_uint4(q4[0], q4[1], q4[2], q4[3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < H; q++)
+                    if (q < cnt && no + q < dst.n_out) {
+                        const uint32_t v = pcm_quantize(o[q], dst.pcm_bits, dst.pcm_float);
+                        for (int b = 0; b < ob; b++) bp[(no + q) * ob + b] = (uint8_t)(v >> (8 * b));
+                    }
+            }
+            return;
+        }
+        float* op = dst.base + stream * dst.stream_stride;
         if (R == 8 && nb + 8 <= dst.n_out && ((dst.stream_stride & 3) == 0)) {
             *reinterpret_cast<float4*>(op + no) = make_float4(o[0], o[1], o[2], o[3]);
         } else {
@@ -1194,6 +1229,55 @@ extern "C" int sk_normalize_batch_dev(sk_ctx* ctx, const sk_batch_desc* d) {
     }
     dst.mix = mix;
     return run_plan(ctx, src, dst, plan, d->in_rate, d->out_rate, d->n_streams, d->channels);
+}
+
+// apply_output_options with bytes out for a whole batch (soundkit-decoder/src/lib.rs:3324-3456, rate-changing arm down to
+// one channel): convert -> resample -> downmix -> f32_channels_to_bytes.  Two-channel integer-ratio sources leave the fused
+// kernel as bytes directly; every other combination goes through an f32 scratch and the interleave kernel.
+int sk_planar_f32_to_pcm_dev_impl(sk_ctx* ctx, const float* planar, size_t frames, int channels, int bits, int fmt, uint8_t* out);
+extern "C" int sk_normalize_batch_pcm_dev(sk_ctx* ctx, const sk_batch_desc* d, int out_bits, int out_fmt, void* out, size_t out_stride_bytes) {
+    if (!ctx || !d) return SK_E_ARG;
+    if (out_fmt == SK_FMT_FLOAT && out_bits != 32) SK_FAIL(ctx, SK_E_ARG, "PCMFloat output requires 32-bit samples");
+    if (out_bits != 16 && out_bits != 24 && out_bits != 32) SK_FAIL(ctx, SK_E_ARG, "Unsupported output bits per sample: %d", out_bits);
+    if (d->channels <= 0 || d->channels > 255) SK_FAIL(ctx, SK_E_ARG, "Channel count must be > 0");
+    if (d->channels != 1 && d->mix_mode == SK_MIX_NONE) SK_FAIL(ctx, SK_E_ARG, "byte output needs a mono result: set mix_mode (or use sk_planar_f32_to_pcm_dev)");
+    if (!d->in_rate || !d->out_rate) SK_FAIL(ctx, SK_E_ARG, "sampling_rate must be > 0");
+    if (!d->n_streams) return SK_OK;
+    if (!d->in || !out) SK_FAIL(ctx, SK_E_ARG, "null buffer");
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    sk_plan* plan;
+    int rc = build_stream_plan(ctx, d->in_rate, d->out_rate, d->frames, d->semantics, &plan);
+    if (rc) return rc;
+    if (!plan->n_out) return SK_OK;
+    const size_t ob = (size_t)out_bits / 8;
+    if (out_stride_bytes < plan->n_out * ob) SK_FAIL(ctx, SK_E_ARG, "out_stride_bytes %zu < %zu bytes per stream", out_stride_bytes, plan->n_out * ob);
+    if (d->channels == 2 && plan->integer_step) {
+        SrcDesc src;
+        if ((rc = src_desc_for(ctx, &src, d->in, d->in_stride, d->bits, d->fmt, d->big_endian, d->channels, d->scale_mode, d->frames))) return rc;
+        OutDesc dst;
+        dst.base = nullptr; dst.stream_stride = 0; dst.lane_stride = 0; dst.mix = d->mix_mode; dst.n_out = (long long)plan->n_out;
+        dst.pcm_bits = out_bits; dst.pcm_float = out_fmt == SK_FMT_FLOAT; dst.pcm_base = (uint8_t*)out; dst.pcm_stream_stride = (long long)out_stride_bytes;
+        return run_plan(ctx, src, dst, plan, d->in_rate, d->out_rate, d->n_streams, d->channels);
+    }
+    // general case: mono f32 into a scratch (slabs of streams), then the interleave kernel with one channel
+    const size_t plane = sk_round_up(plan->n_out, 4);
+    size_t slab = std::max<size_t>(1, (size_t)(1u << 27) / plane);  // <= 512 MiB of floats
+    slab = std::min(slab, d->n_streams);
+    if (ctx->d_tmp_cap < slab * plane * sizeof(float)) {
+        if (ctx->d_tmp) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->d_tmp); ctx->d_tmp = nullptr; ctx->d_tmp_cap = 0; }
+        SK_CUDA(ctx, cudaMalloc(&ctx->d_tmp, slab * plane * sizeof(float)));
+        ctx->d_tmp_cap = slab * plane * sizeof(float);
+    }
+    float* mono = (float*)ctx->d_tmp;
+    for (size_t s0 = 0; s0 < d->n_streams; s0 += slab) {
+        const size_t ns = std::min(slab, d->n_streams - s0);
+        sk_batch_desc dd = *d;
+        dd.in = (const char*)d->in + s0 * d->in_stride; dd.n_streams = ns; dd.out = mono; dd.out_stride = plane; dd.out_stride_ch = plane;
+        if ((rc = sk_normalize_batch_dev(ctx, &dd))) return rc;
+        for (size_t s = 0; s < ns; s++)
+            if ((rc = sk_planar_f32_to_pcm_dev_impl(ctx, mono + s * plane, plan->n_out, 1, out_bits, out_fmt, (uint8_t*)out + (s0 + s) * out_stride_bytes))) return rc;
+    }
+    return SK_OK;
 }
 
 extern "C" int sk_normalize_stream(sk_ctx* ctx, const uint8_t* in, size_t bytes, int bits, int fmt, int big_endian, int channels, int scale_mode,

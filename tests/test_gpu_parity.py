@@ -809,3 +809,49 @@ def test_f32_deinterleave_interleave_round_trip_at_config_size():
     want = torch.where(want > 16384, want - 1, want).to(torch.int16)
     assert torch.equal(b16, want)
     c.close()
+
+
+# ---------------------------------------------------------------------------------------------- bytes out (apply_output_options in one call)
+@pytest.mark.parametrize("out_bits,out_fmt", [(16, 0), (24, 0), (32, 0), (32, 1)])
+@pytest.mark.parametrize("case", [("s24 stereo 48->16 (fused epilogue)", 24, 0, 2, 48000, 16000),
+                                  ("s16 stereo 48->8 (fused epilogue)", 16, 0, 2, 48000, 8000),
+                                  ("f32 stereo 44.1->16 (scratch + pass)", 32, 1, 2, 44100, 16000),
+                                  ("s16 mono 48->16 (scratch + pass)", 16, 0, 1, 48000, 16000),
+                                  ("s24 5.1 48->16 (scratch + pass)", 24, 0, 6, 48000, 16000)])
+def test_normalize_batch_pcm_dev_matches_output_stage(oracle, case, out_bits, out_fmt):
+    """convert -> resample -> downmix_channels(.., 1) -> f32_channels_to_bytes, the rate-changing arm of
+    apply_output_options (soundkit-decoder/src/lib.rs:3324-3456), for a device-resident batch with ragged lengths"""
+    import torch
+    _, bits, fmt, channels, i_rate, o_rate = case
+    c = capi.Context(0)
+    c.use_torch_stream()
+    S, frames = 3, 20011
+    rng = np.random.default_rng(out_bits + bits + channels)
+    fb = (bits // 8) * channels
+    stride = (frames * fb + 15) // 16 * 16
+    host = np.zeros((S, stride), np.uint8)
+    for s in range(S):
+        if fmt == 1:
+            host[s, :frames * fb] = rng.uniform(-1.1, 1.1, frames * channels).astype(np.float32).view(np.uint8)
+        else:
+            host[s, :frames * fb] = rng.integers(0, 256, frames * fb, dtype=np.uint8)
+    d_in = torch.from_numpy(host).cuda()
+    n_out = c.batch_plan(i_rate, o_rate, frames, capi.SEM_STREAMING)
+    ob = out_bits // 8
+    ostride = (n_out * ob + 15) // 16 * 16
+    d_out = torch.full((S, ostride), 0xEE, dtype=torch.uint8, device="cuda")
+    d = capi.BatchDesc(d_in.data_ptr(), stride, S, frames, bits, fmt, 0, channels, capi.MODE_B, i_rate, o_rate, capi.SEM_STREAMING,
+                       capi.MIX_SCALE_THEN_SUM, 0, 0, 0)
+    c.normalize_batch_pcm_dev(d, out_bits, out_fmt, d_out, ostride)
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy()
+    for s in range(S):
+        planar = oracle.pcm_to_planar_f32(host[s, :frames * fb], bits, fmt, False, channels, capi.MODE_B)
+        st = oracle.Stream(i_rate, o_rate, channels)
+        res = np.concatenate([st.process(planar), st.flush()], axis=1)
+        mono = oracle.downmix_channels(res, 1) if channels > 1 else res
+        want = oracle.f32_channels_to_bytes(mono, out_bits, out_fmt)
+        assert want.size == n_out * ob
+        assert np.array_equal(out[s, :n_out * ob], want), (s, case[0])
+        assert np.all(out[s, n_out * ob:] == 0xEE)  # nothing written past the stream's bytes
+    c.close()
