@@ -1,0 +1,7 @@
+// sk_resample_int12.cu — instantiation of the integer-ratio resampler kernels for t_ratio = 12 (see sk_resample_dev.cuh)
+#include "sk_resample_dev.cuh"
+
+int sk_launch_int_12(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, const float* h_table, const float* d_table,
+                     size_t n_streams, int lanes_per_stream) {
+    return launch_int<12>(ctx, src, dst, plan, h_table, d_table, n_streams, lanes_per_stream);
+}
