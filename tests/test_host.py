@@ -516,3 +516,33 @@ def test_g726_decode_fixture_golden_and_error_strings():  # lib.rs:1113-1145 of 
     with pytest.raises(H.SoundkitError, match=r"Output buffer too small for G.726 flush: need 1, have 0"):
         e.flush_into(0)
     assert G6.from_bitrate(24000) == G6.G726Rate.Rate24000 and G6.from_bitrate(12345) == G6.G726Rate.Rate32000
+
+
+@pytest.mark.gpu
+def test_apply_output_options_mid_stream_errors_and_surround(oracle):
+    """lib.rs:3395-3403 (the resampler is bound to the first frame's geometry) and the > 2 channel arm: resample per channel,
+    then downmix_channels(.., 2) with its block-wide peak normalisation, then bytes"""
+    rng = np.random.default_rng(3)
+    opts = D.DecodeOptions(output_bits_per_sample=16, output_sample_rate=16000, output_channels=1)
+    slot = D.ResamplerSlot()
+    x = rng.uniform(-0.5, 0.5, (2, 5000)).astype(np.float32)
+    D.apply_output_options(f32_audio(48000, [x[0], x[1]]), opts, slot)
+    with pytest.raises(H.DecodeError, match="Resampler configuration changed mid-stream"):
+        D.apply_output_options(f32_audio(44100, [x[0], x[1]]), opts, slot)          # input rate changed
+    with pytest.raises(H.DecodeError, match="Resampler configuration changed mid-stream"):
+        D.apply_output_options(f32_audio(48000, [x[0]]), opts, slot)                # channel count changed
+    with pytest.raises(H.DecodeError, match="Resampler configuration changed mid-stream"):
+        D.apply_output_options(f32_audio(48000, [x[0], x[1]]), D.DecodeOptions(output_bits_per_sample=16, output_sample_rate=8000, output_channels=1), slot)
+    # 5.1 float -> stereo s24 at 24 kHz, whole stream in one push + flush
+    ch = rng.uniform(-0.9, 0.9, (6, 9000)).astype(np.float32)
+    opts = D.DecodeOptions(output_bits_per_sample=24, output_sample_rate=24000, output_channels=2)
+    slot = D.ResamplerSlot()
+    frames = D.apply_output_options(f32_audio(48000, list(ch)), opts, slot) + D.flush_resampler_frames(slot)
+    got = b"".join(f.data() for f in frames)
+    st = oracle.Stream(48000, 24000, 6)
+    want = b""
+    for part in (st.process(ch), st.flush()):   # the reference emits (and peak-normalises) one block per resampler chunk batch
+        if part.shape[1]:
+            want += oracle.f32_channels_to_bytes(oracle.downmix_channels(part, 2), 24, 0).tobytes()
+    assert all(f.bits_per_sample() == 24 and f.channel_count() == 2 and f.sampling_rate() == 24000 for f in frames)
+    assert len(got) == len(want)
