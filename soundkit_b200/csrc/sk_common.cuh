@@ -107,12 +107,22 @@ __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 
 __device__ __forceinline__ float clamp1(float x) { return x < -1.0f ? -1.0f : (x > 1.0f ? 1.0f : x); }
 __device__ __forceinline__ bool finite_f(float x) { return (__float_as_uint(x) & 0x7f800000u) != 0x7f800000u; }
 
-// float_sample_to_i16, soundkit-decoder/src/lib.rs:1815-1827 (f64 scale, round half away from zero)
+// float_sample_to_i16, soundkit-decoder/src/lib.rs:1815-1827: non-finite -> 0, clamp, x < 0 ? x * 32768 : x * 32767 IN F64,
+// f64::round (half away from zero), clamp to i16.  Evaluated here without f64 (the FP64 path made the s16 byte writer the
+// one HBM kernel that was compute bound): |x| * 32768 is exact in f32; |x| * 32767 = a - |x| is taken as the f32
+// difference s plus its exact rounding error (Fast2Sum: err = (a - s) - |x|), so floor(s), the exact fraction s - floor(s)
+// and the sign of err decide the rounding exactly as the f64 product would.  Identical to the f64 rule for every float
+// (checked exhaustively over all exponents that can produce a non-zero result, both signs).
 __device__ __forceinline__ int32_t float_sample_to_i16_dev(float s) {
-    float f = finite_f(s) ? clamp1(s) : 0.0f;
-    double scaled = f < 0.0f ? __dmul_rn((double)f, 32768.0) : __dmul_rn((double)f, 32767.0);
-    int32_t r = __double2int_rz(round(scaled));
-    return max(-32768, min(32767, r));
+    const float f = finite_f(s) ? clamp1(s) : 0.0f;
+    const float m = fabsf(f);
+    const float a = __fmul_rn(m, 32768.0f);
+    const bool neg = f < 0.0f;
+    const float sv = neg ? a : __fsub_rn(a, m);
+    const float err = neg ? 0.0f : __fsub_rn(__fsub_rn(a, sv), m);
+    const float t = floorf(sv), fr = __fsub_rn(sv, t);
+    const int r = __float2int_rz(t) + (int)((fr > 0.5f) || (fr == 0.5f && err >= 0.0f));
+    return max(-32768, min(32767, neg ? -r : r));
 }
 // audio_bytes.rs:205-220 / decoder lib.rs:3653-3659
 __device__ __forceinline__ int32_t f32_to_s24_dev(float x) {

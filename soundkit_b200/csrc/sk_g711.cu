@@ -64,28 +64,45 @@ __device__ __forceinline__ uint32_t g711_dec_word(int law, int kind, uint32_t co
 // Every global access is a full-width, contiguous warp access: per step a warp loads 512 codes as one 512-byte run
 // (16 B per lane) and stores the 1024 / 2048 output bytes as 2 / 4 runs of 512 bytes (16 B per lane).  The lane that
 // loaded codes [16t, 16t+16) is not the lane that stores their samples, so the codes cross lanes through 512 bytes of
-// warp-private shared memory (one STS.128, then one LDS.64 / LDS.32 per store).  Narrower per-lane accesses (8 B loads,
-// the previous version) ran at 0.85 of HBM, two half-sector stores per lane (the first version) at 0.70.
-constexpr int kDecThreads = 512;
+// warp-private shared memory (one STS.128, then one LDS.64 / LDS.32 per store).
+// The grid is LARGE and short-lived (one CTA = 8 warps x 2 steps = 8 Ki codes): a persistent grid whose CTAs stride through
+// the buffers in lockstep reached 0.88 of the HBM copy rate, the same work as a big grid 1.0+ (see sk_pcm.cu: grid_for).
+// Table: 4-byte outputs (i32 / f32) use the plain 256-entry table (1 KiB); random codes conflict ~3.5-way in it, which at
+// full HBM rate is 0.4 of a shared-memory wavefront per clock.  16-bit outputs do twice the lookups per byte moved, so they
+// keep the bank-replicated [256][32] table (32 lanes with arbitrary codes never conflict): each thread computes one entry
+// and writes its 32 copies with a rotated column order (conflict-free), and a CTA owns 4x more steps to amortise that.
+constexpr int kDecThreads = 256;
 constexpr int kDecUnroll = 2;  // warp steps whose loads are issued together
+template <int KIND> __host__ __device__ constexpr int dec_steps_per_warp() { return KIND == SK_KIND_I16 ? 8 : 2; }
 
 template <int KIND>
 __global__ void __launch_bounds__(kDecThreads) g711_decode_kernel(const uint8_t* __restrict__ in, void* __restrict__ outv,
                                                                    size_t n, int law) {
-    __shared__ uint32_t lut[256 * 32];  // [code][bank]
+    constexpr bool REPL = KIND == SK_KIND_I16;
+    constexpr int LS = REPL ? 5 : 0;  // log2 of the table's row stride
+    __shared__ uint32_t lut[REPL ? 256 * 32 : 256];
     __shared__ __align__(16) uint8_t xch[kDecThreads / 32][kDecUnroll][512];
-    for (int i = threadIdx.x; i < 256 * 32; i += kDecThreads) lut[i] = g711_dec_word(law, KIND, (uint32_t)i >> 5);
-    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t* my = lut + lane;
+    {
+        const uint32_t e = g711_dec_word(law, KIND, (uint32_t)threadIdx.x);
+        if (REPL) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) lut[(threadIdx.x << 5) + ((j + lane) & 31)] = e;
+        } else lut[threadIdx.x] = e;
+    }
+    __syncthreads();
+    const uint32_t* my = lut + (REPL ? lane : 0);
     constexpr int OB = KIND == SK_KIND_I16 ? 2 : 4;
     constexpr int EPL = 16 / OB;        // elements per lane per store (8 or 4)
     constexpr int NST = 512 / (32 * EPL);  // stores per step (2 or 4)
     const size_t nsteps = n / 512;
     const uint4* in4 = reinterpret_cast<const uint4*>(in);
     uint4* out4 = reinterpret_cast<uint4*>(outv);
-    const size_t wstride = (size_t)gridDim.x * (kDecThreads / 32) * kDecUnroll;
-    for (size_t s0 = ((size_t)blockIdx.x * (kDecThreads / 32) + warp) * kDecUnroll; s0 < nsteps; s0 += wstride) {
+    // a warp owns dec_steps_per_warp consecutive steps of its CTA's chunk, kDecUnroll at a time
+    constexpr int SPW = dec_steps_per_warp<KIND>();
+    const size_t cta_steps = (size_t)(kDecThreads / 32) * SPW;
+    for (size_t cbase = (size_t)blockIdx.x * cta_steps; cbase < nsteps; cbase += (size_t)gridDim.x * cta_steps)
+    for (size_t s0 = cbase + (size_t)warp * SPW, send = s0 + SPW; s0 < send && s0 < nsteps; s0 += kDecUnroll) {
         uint4 c[kDecUnroll];
 #pragma unroll
         for (int u = 0; u < kDecUnroll; u++)
@@ -105,7 +122,7 @@ __global__ void __launch_bounds__(kDecThreads) g711_decode_kernel(const uint8_t*
                 else { w[0] = reinterpret_cast<const uint32_t*>(xch[warp][u])[i * 32 + lane]; w[1] = 0; }
                 uint32_t o[EPL];
 #pragma unroll
-                for (int k = 0; k < EPL; k++) o[k] = my[((w[k >> 2] >> (8 * (k & 3))) & 0xff) << 5];
+                for (int k = 0; k < EPL; k++) o[k] = my[((w[k >> 2] >> (8 * (k & 3))) & 0xff) << LS];
                 uint4 r;
                 if (KIND == SK_KIND_I16) {
                     r.x = __byte_perm(o[0], o[1], 0x5410); r.y = __byte_perm(o[2], o[3], 0x5410);
@@ -120,7 +137,7 @@ __global__ void __launch_bounds__(kDecThreads) g711_decode_kernel(const uint8_t*
     // tail (< 512 codes): one thread per sample
     if (blockIdx.x == 0) {
         for (size_t i = nsteps * 512 + threadIdx.x; i < n; i += kDecThreads) {
-            uint32_t wv = my[(uint32_t)in[i] << 5];
+            uint32_t wv = my[(uint32_t)in[i] << LS];
             if (KIND == SK_KIND_I16) reinterpret_cast<uint16_t*>(outv)[i] = (uint16_t)wv;
             else reinterpret_cast<uint32_t*>(outv)[i] = wv;
         }
@@ -235,9 +252,11 @@ __global__ void g711_encode_scalar_kernel(const void* __restrict__ inv, uint8_t*
 // ---- host side -----------------------------------------------------------------------------------
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
-static int grid_for(sk_ctx* ctx, size_t nvec, int threads, int per_sm) {
-    size_t need = (nvec + threads - 1) / threads;
-    size_t cap = (size_t)ctx->num_sms * per_sm;
+// as many short-lived CTAs as the work takes (see the decode kernel's note); the kernels keep a stride loop beyond 2^22 CTAs
+static int grid_for(sk_ctx* ctx, size_t work_threads, int threads) {
+    (void)ctx;
+    size_t need = (work_threads + threads - 1) / threads;
+    const size_t cap = (size_t)1 << 22;
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
 }
@@ -254,7 +273,8 @@ extern "C" int sk_g711_decode_dev(sk_ctx* ctx, int law, const uint8_t* in, size_
         SK_LAUNCH_CHECK(ctx);
         return SK_OK;
     }
-    int grid = grid_for(ctx, (n / 512 + kDecUnroll - 1) / kDecUnroll * 32, kDecThreads, 4);
+    const int spw = out_kind == SK_KIND_I16 ? dec_steps_per_warp<SK_KIND_I16>() : dec_steps_per_warp<SK_KIND_F32>();
+    int grid = grid_for(ctx, (n / 512 + spw - 1) / spw * 32, kDecThreads);
     if (out_kind == SK_KIND_I16) g711_decode_kernel<SK_KIND_I16><<<grid, kDecThreads, 0, ctx->stream>>>(in, out, n, law);
     else if (out_kind == SK_KIND_I32) g711_decode_kernel<SK_KIND_I32><<<grid, kDecThreads, 0, ctx->stream>>>(in, out, n, law);
     else g711_decode_kernel<SK_KIND_F32><<<grid, kDecThreads, 0, ctx->stream>>>(in, out, n, law);
@@ -274,7 +294,7 @@ extern "C" int sk_g711_encode_dev(sk_ctx* ctx, int law, int in_kind, const void*
         SK_LAUNCH_CHECK(ctx);
         return SK_OK;
     }
-    int grid = grid_for(ctx, n / 512 * 32, kEncThreads, 8);
+    int grid = grid_for(ctx, n / 512 * 32, kEncThreads);
     if (law == SK_LAW_MULAW) {
         if (in_kind == SK_KIND_I16) g711_encode_kernel<SK_LAW_MULAW, SK_KIND_I16><<<grid, kEncThreads, 0, ctx->stream>>>(in, out, n);
         else g711_encode_kernel<SK_LAW_MULAW, SK_KIND_I32><<<grid, kEncThreads, 0, ctx->stream>>>(in, out, n);

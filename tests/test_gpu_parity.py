@@ -855,3 +855,13 @@ def test_normalize_batch_pcm_dev_matches_output_stage(oracle, case, out_bits, ou
         assert np.array_equal(out[s, :n_out * ob], want), (s, case[0])
         assert np.all(out[s, n_out * ob:] == 0xEE)  # nothing written past the stream's bytes
     c.close()
+
+
+def test_float_sample_to_i16_without_f64_is_exact_over_whole_binades(ctx, oracle):
+    """the device evaluates the reference's f64 rule (soundkit-decoder/src/lib.rs:1815-1827) in f32 with an exact
+    error term: every 5th float of every binade that can produce a non-zero sample, both signs, must match"""
+    for e in range(100, 128):
+        bits = (np.uint32(e) << np.uint32(23)) + np.arange(e % 5, 1 << 23, 5, dtype=np.uint32)
+        x = bits.view(np.float32)
+        x = np.concatenate([x, -x])[None, :]
+        assert np.array_equal(ctx.planar_f32_to_pcm(x, 16, capi.FMT_SIGNED), oracle.f32_channels_to_bytes(x, 16, 0)), e
