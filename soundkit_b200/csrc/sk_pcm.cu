@@ -603,7 +603,7 @@ template <int BITS, int CH, bool ISFLOAT>
 __global__ void __launch_bounds__(kPcmThreads) interleave_kernel(const float* __restrict__ planar, size_t frames, uint8_t* __restrict__ out,
                                                                   size_t ntiles) {
     constexpr int OB = BITS / 8;
-    constexpr int G = (OB == 3) ? (CH == 1 ? 16 : 8) : (OB == 2 ? (CH == 1 ? 8 : 4) : 4);
+    constexpr int G = (OB == 3) ? (CH == 1 ? 16 : 8) : (OB == 2 ? (CH == 1 ? 16 : 8) : 4);
     constexpr int NW = G * CH * OB / 4, NV_OUT = NW / 4, NV_IN = G / 4;
     constexpr int NVX = NV_IN > NV_OUT ? NV_IN : NV_OUT;
     static_assert((G * CH * OB) % 16 == 0 && G % 4 == 0, "vector group");
@@ -646,7 +646,7 @@ __global__ void interleave_scalar_kernel(const float* __restrict__ planar, size_
 template <int BITS, int CH, bool ISFLOAT>
 static size_t launch_interleave_vec(sk_ctx* ctx, const float* planar, size_t frames, uint8_t* out) {
     constexpr int OB = BITS / 8;
-    constexpr int G = (OB == 3) ? (CH == 1 ? 16 : 8) : (OB == 2 ? (CH == 1 ? 8 : 4) : 4);
+    constexpr int G = (OB == 3) ? (CH == 1 ? 16 : 8) : (OB == 2 ? (CH == 1 ? 16 : 8) : 4);
     const size_t ntiles = frames / (32 * (size_t)G);
     if (!ntiles) return 0;
     interleave_kernel<BITS, CH, ISFLOAT><<<grid_for(ctx, ntiles * 32, kPcmThreads), kPcmThreads, 0, ctx->stream>>>(planar, frames, out, ntiles);
