@@ -766,33 +766,41 @@ extern "C" int sk_normalize_batch(sk_ctx* ctx, const sk_batch_desc* d) {
         }
     }
     const size_t raw_bytes = d->frames * (size_t)(d->bits / 8) * d->channels;
-    size_t islab = 0;
-    for (size_t s0 = 0; s0 < d->n_streams; s0 += slab, islab++) {
-        const int b = (int)(islab & 1);
-        const size_t ns = std::min(slab, d->n_streams - s0);
-        if (islab >= 2) {
-            SK_CUDA(ctx, cudaStreamWaitEvent(p.s_in, p.ev_k[b], 0));        // kernel of slab-2 finished reading d_in[b]
-            SK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p.ev_out[b], 0)); // D2H of slab-2 finished reading d_out[b]
+    // the slab loop; whatever it returns, no copy may still be reading d->in or writing d->out when this call returns
+    auto pump = [&]() -> int {
+        size_t islab = 0;
+        for (size_t s0 = 0; s0 < d->n_streams; s0 += slab, islab++) {
+            const int b = (int)(islab & 1);
+            const size_t ns = std::min(slab, d->n_streams - s0);
+            if (islab >= 2) {
+                SK_CUDA(ctx, cudaStreamWaitEvent(p.s_in, p.ev_k[b], 0));        // kernel of slab-2 finished reading d_in[b]
+                SK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p.ev_out[b], 0)); // D2H of slab-2 finished reading d_out[b]
+            }
+            for (size_t s = 0; s < ns; s++)
+                SK_CUDA(ctx, cudaMemcpyAsync((char*)p.d_in[b] + s * in_bytes, (const char*)d->in + (s0 + s) * d->in_stride, raw_bytes,
+                                             cudaMemcpyHostToDevice, p.s_in));
+            SK_CUDA(ctx, cudaEventRecord(p.ev_in[b], p.s_in));
+            SK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p.ev_in[b], 0));
+            sk_batch_desc dd = *d;
+            dd.in = p.d_in[b]; dd.in_stride = in_bytes; dd.n_streams = ns; dd.mix_mode = mix;
+            dd.out = p.d_out[b]; dd.out_stride = out_floats; dd.out_stride_ch = plane;
+            if (int rc2 = sk_normalize_batch_dev(ctx, &dd)) return rc2;
+            SK_CUDA(ctx, cudaEventRecord(p.ev_k[b], ctx->stream));
+            SK_CUDA(ctx, cudaStreamWaitEvent(p.s_out, p.ev_k[b], 0));
+            for (size_t s = 0; s < ns; s++)
+                for (int c = 0; c < planes; c++)
+                    SK_CUDA(ctx, cudaMemcpyAsync(d->out + (s0 + s) * d->out_stride + (size_t)c * d->out_stride_ch, p.d_out[b] + s * out_floats + (size_t)c * plane,
+                                                 plan->n_out * sizeof(float), cudaMemcpyDeviceToHost, p.s_out));
+            SK_CUDA(ctx, cudaEventRecord(p.ev_out[b], p.s_out));
         }
-        for (size_t s = 0; s < ns; s++)
-            SK_CUDA(ctx, cudaMemcpyAsync((char*)p.d_in[b] + s * in_bytes, (const char*)d->in + (s0 + s) * d->in_stride, raw_bytes,
-                                         cudaMemcpyHostToDevice, p.s_in));
-        SK_CUDA(ctx, cudaEventRecord(p.ev_in[b], p.s_in));
-        SK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p.ev_in[b], 0));
-        sk_batch_desc dd = *d;
-        dd.in = p.d_in[b]; dd.in_stride = in_bytes; dd.n_streams = ns; dd.mix_mode = mix;
-        dd.out = p.d_out[b]; dd.out_stride = out_floats; dd.out_stride_ch = plane;
-        if ((rc = sk_normalize_batch_dev(ctx, &dd))) return rc;
-        SK_CUDA(ctx, cudaEventRecord(p.ev_k[b], ctx->stream));
-        SK_CUDA(ctx, cudaStreamWaitEvent(p.s_out, p.ev_k[b], 0));
-        for (size_t s = 0; s < ns; s++)
-            for (int c = 0; c < planes; c++)
-                SK_CUDA(ctx, cudaMemcpyAsync(d->out + (s0 + s) * d->out_stride + (size_t)c * d->out_stride_ch, p.d_out[b] + s * out_floats + (size_t)c * plane,
-                                             plan->n_out * sizeof(float), cudaMemcpyDeviceToHost, p.s_out));
-        SK_CUDA(ctx, cudaEventRecord(p.ev_out[b], p.s_out));
-    }
-    SK_CUDA(ctx, cudaStreamSynchronize(p.s_out));
-    SK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return SK_OK;
+    };
+    rc = pump();
+    const cudaError_t e_in = cudaStreamSynchronize(p.s_in), e_k = cudaStreamSynchronize(ctx->stream), e_out = cudaStreamSynchronize(p.s_out);
+    if (rc) return rc;
+    SK_CUDA(ctx, e_in);
+    SK_CUDA(ctx, e_k);
+    SK_CUDA(ctx, e_out);
     return SK_OK;
 }
 
