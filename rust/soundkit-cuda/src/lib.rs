@@ -9,6 +9,7 @@ use std::ffi::CStr;
 
 pub mod audio_bytes;
 pub mod audio_pipeline;
+pub mod decoder;
 pub mod g711;
 pub mod g726;
 
