@@ -2,7 +2,8 @@
 //! device. Same names, argument meaning and error strings as the private functions they replace; the bookkeeping that is
 //! not arithmetic (`accum`, the flush trim, every validation string) stays in Rust.  SOURCE ONLY — the compiled and
 //! tested twin is namespace `soundkit_decoder` in `soundkit_b200/csrc/host/soundkit_host.hpp`.
-use crate::{check, sys, with_ctx};
+use crate::{check, with_ctx};
+use soundkit_cuda_sys as sys;
 
 pub const RESAMPLE_CHUNK_SIZE: usize = 4096; // soundkit-decoder/src/lib.rs:79
 
