@@ -422,10 +422,13 @@ __device__ __forceinline__ void convert4(const uint32_t* w, float* l, float* r) 
             } else if (SRCW == 3) {
                 const int o = 3 * (2 * k + c), wi = o >> 2, sh = o & 3;
                 const uint32_t lo = w[wi], hi = (sh >= 2) ? w[wi + 1] : 0u;
-                // sample bytes -> result bytes 1..3 (most significant byte on top), then arithmetic >> 8 sign-extends
-                const uint32_t sel = !BE ? ((uint32_t)(sh + 2) << 12) | ((uint32_t)(sh + 1) << 8) | ((uint32_t)sh << 4)
-                                         : ((uint32_t)sh << 12) | ((uint32_t)(sh + 1) << 8) | ((uint32_t)(sh + 2) << 4);
-                f = __int2float_rn(((int32_t)__byte_perm(lo, hi, sel)) >> 8);
+                // one PRMT per sample: result bytes 0..2 are the sample's bytes, least significant first, and byte 3 replicates the
+                // sign of its top byte (selector nibble | 8), i.e. the sign-extended 24-bit integer
+                const uint32_t top = !BE ? (uint32_t)(sh + 2) : (uint32_t)sh, low = !BE ? (uint32_t)sh : (uint32_t)(sh + 2);
+                const uint32_t sel = ((top | 8u) << 12) | (top << 8) | ((uint32_t)(sh + 1) << 4) | low;
+                uint32_t v;  // prmt.b32 directly: the __byte_perm intrinsic documents only 3 selector bits per nibble
+                asm("prmt.b32 %0, %1, %2, %3;" : "=r"(v) : "r"(lo), "r"(hi), "r"(sel));
+                f = __int2float_rn((int32_t)v);
             } else {
                 uint32_t u = w[2 * k + c];
                 if (BE) u = bswap32(u);
