@@ -27,6 +27,9 @@ struct sk_ctx {
     void* d_in = nullptr;    size_t d_in_cap = 0;
     void* d_out = nullptr;   size_t d_out_cap = 0;
     void* d_tmp = nullptr;   size_t d_tmp_cap = 0;     // scratch of sk_normalize_batch_pcm_dev (mono f32 before quantisation)
+    // tile tickets of the persistent integer-step kernel: one counter per launch, taken round-robin from a ring so that
+    // launches in flight on different streams of one context never share a counter (sk_resample_dev.cuh)
+    unsigned int* d_tickets = nullptr; unsigned int ticket_next = 0;
     void* batch_pipe = nullptr;                       // sk_resample.cu: slab pipeline of sk_normalize_batch (streams, events, device slabs)
     bool g726_tables_ready = false;                   // sk_g726.cu: __constant__ tables uploaded on this device
     // sinc tables per ratio, built lazily

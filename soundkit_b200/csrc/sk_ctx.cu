@@ -41,6 +41,7 @@ extern "C" void sk_ctx_destroy(sk_ctx* ctx) {
     if (ctx->d_in) cudaFree(ctx->d_in);
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_tmp) cudaFree(ctx->d_tmp);
+    if (ctx->d_tickets) cudaFree(ctx->d_tickets);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }

@@ -499,7 +499,7 @@ struct TileGeom { int stream; int n0; int wa; int g_lo; int g_hi; int pad[3]; };
 template <int STEP, int SRCW, bool PCM>
 __global__ void __launch_bounds__(kIntThreads, SK_TMA_CTAS_PER_SM)
 resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant__ SrcDesc src, const __grid_constant__ OutDesc dst, long long i0_first,
-                        unsigned tiles_per_stream, unsigned total_tiles, const float* __restrict__ row1) {
+                        unsigned tiles_per_stream, unsigned total_tiles, const float* __restrict__ row1, unsigned* __restrict__ ticket) {
     constexpr int R = IntCfg<STEP>::R;
     constexpr int T = int_tile_outputs<STEP>();
     constexpr int LEAD = tma_lead<STEP>();
@@ -513,11 +513,15 @@ resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant
     uint64_t* bars = reinterpret_cast<uint64_t*>(raw + 2 * RAWB);
     __shared__ TileGeom geoms[4];
 
-    const unsigned nk = (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;  // tiles this CTA owns
+    // Tiles are handed out by ticket (one atomic per tile), not by a static stride: the three co-resident CTAs of an SM do not
+    // progress at the same rate (measured with %globaltimer: with equal static shares the first CTA finished after 57 % of the
+    // kernel and its SM ran under-occupied from then on), so every CTA keeps drawing tiles until the batch is exhausted.
 
-    // one elected thread: geometry of tile k -> geoms[k & 3], then the TMA request for its raw bytes
+    // one elected thread: ticket and geometry of the CTA's k-th tile -> geoms[k & 3] (stream = -1: no tile left), then the TMA
+    // request for its raw bytes
     auto issue = [&](unsigned k) {
-        const unsigned t = blockIdx.x + k * gridDim.x;
+        const unsigned t = atomicAdd(ticket, 1u);
+        if (t >= total_tiles) { geoms[k & 3].stream = -1; return; }
         const unsigned stream = t / tiles_per_stream;
         const long long n0 = (long long)(t - stream * tiles_per_stream) * T;
         const long long wa = i0_first + (long long)STEP * n0 - LEAD;                  // first frame of the shared window
@@ -541,14 +545,15 @@ resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant
         mbar_init(smem_u32(&bars[0]), 1);
         mbar_init(smem_u32(&bars[1]), 1);
         mbar_fence_init();
-        if (nk > 0) issue(0);
-        if (nk > 1) issue(1);
+        issue(0);
+        issue(1);
     }
     __syncthreads();
 
     const int lane = threadIdx.x & 1, b = threadIdx.x >> 1;
-    for (unsigned k = 0; k < nk; k++) {
+    for (unsigned k = 0;; k++) {
         const TileGeom g = geoms[k & 3];
+        if (g.stream < 0) break;  // tickets are monotonic: nothing was requested for this or any later k
         const int buf = (int)(k & 1);
         mbar_wait(smem_u32(&bars[buf]), (k >> 1) & 1);
 
@@ -564,7 +569,7 @@ resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant
                                  : convert_window<SRCW, WF, WS, false, false, false>(rb, win, src, g.stream, g.wa, g.g_lo, g.g_hi);
         }
         const int any_big = __syncthreads_or((int)big);  // windows ready, raw[buf] free
-        if (threadIdx.x == 0 && k + 2 < nk) issue(k + 2);
+        if (threadIdx.x == 0) issue(k + 2);
 
         // ---- FIR
         const float* w = win + lane * WS + STEP * R * b;
@@ -609,12 +614,16 @@ static int launch_int_tma(sk_ctx* ctx, const Taps& taps, const SrcDesc& src, con
         s2.scale = 1.0f;
     }
     if (dst.pcm_bits && !kPcm) SK_FAIL(ctx, SK_E_STATE, "internal: no byte epilogue for integer step %d", STEP);
+    constexpr unsigned kTicketRing = 256;
+    if (!ctx->d_tickets) SK_CUDA(ctx, cudaMalloc((void**)&ctx->d_tickets, kTicketRing * sizeof(unsigned)));
+    unsigned* ticket = ctx->d_tickets + (ctx->ticket_next++ % kTicketRing);
+    SK_CUDA(ctx, cudaMemsetAsync(ticket, 0, sizeof(unsigned), ctx->stream));
     if (dst.pcm_bits)
         resample_int_tma_kernel<STEP, SRCW, kPcm><<<(unsigned)grid, kIntThreads, smem, ctx->stream>>>(t2, s2, dst, plan->i0_first, (unsigned)tiles_per_stream,
-                                                                                                    (unsigned)total, d_table + SINC_LEN);
+                                                                                                    (unsigned)total, d_table + SINC_LEN, ticket);
     else
         resample_int_tma_kernel<STEP, SRCW, false><<<(unsigned)grid, kIntThreads, smem, ctx->stream>>>(t2, s2, dst, plan->i0_first, (unsigned)tiles_per_stream,
-                                                                                                     (unsigned)total, d_table + SINC_LEN);
+                                                                                                     (unsigned)total, d_table + SINC_LEN, ticket);
     SK_LAUNCH_CHECK(ctx);
     return SK_OK;
 }
