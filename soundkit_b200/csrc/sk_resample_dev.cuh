@@ -185,7 +185,11 @@ template <int STEP> struct IntCfg;
 // threads of an LDS.128 quarter-warp (4 thread-blocks x 2 lanes) hit 8 distinct 4-bank groups:
 // thread stride S = STEP*R words; need {S*b mod 32, b<4} U {S*b + SKEW mod 32} to be 8 distinct
 // multiples of 4.
+#ifdef SK_INT3_R12  // experiment: 12 outputs per thread (2 CTAs/SM)
+template <> struct IntCfg<3>  { static constexpr int R = 12, SKEW = 16; };  // S = 36: {0,4,8,12} + 16
+#else
 template <> struct IntCfg<3>  { static constexpr int R = 8, SKEW = 4;  };  // S = 24: {0,24,16,8} + 4
+#endif
 template <> struct IntCfg<2>  { static constexpr int R = 6, SKEW = 16; };  // S = 12: {0,12,24,4} + 16
 template <> struct IntCfg<4>  { static constexpr int R = 7, SKEW = 16; };  // S = 28: {0,28,24,20} + 16
 template <> struct IntCfg<6>  { static constexpr int R = 6, SKEW = 16; };  // S = 36: {0,4,8,12} + 16
@@ -297,6 +301,9 @@ __device__ __forceinline__ void int_epilogue(const float (&y)[R], const OutDesc&
         float* op = dst.base + stream * dst.stream_stride;
         if (R == 8 && nb + 8 <= dst.n_out && ((dst.stream_stride & 3) == 0)) {
             *reinterpret_cast<float4*>(op + no) = make_float4(o[0], o[1], o[2], o[3]);
+        } else if (R == 12 && nb + 12 <= dst.n_out && ((dst.stream_stride & 1) == 0)) {
+#pragma unroll
+            for (int v = 0; v < 3; v++) *reinterpret_cast<float2*>(op + no + 2 * v) = make_float2(o[(2 * v) % H], o[(2 * v + 1) % H]);
         } else {
 #pragma unroll
             for (int q = 0; q < H; q++)
@@ -489,6 +496,9 @@ __device__ __forceinline__ bool convert_window(const uint8_t* __restrict__ rb, f
     return big;
 }
 
+#ifdef SK_TRACE_CTAS
+__device__ unsigned long long sk_cta_trace[3 * 1024];
+#endif
 // per-tile geometry, computed once by the TMA-issuing thread and handed to the CTA through shared memory
 struct TileGeom { int stream; int n0; int wa; int g_lo; int g_hi; int pad[3]; };
 
@@ -517,6 +527,14 @@ resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant
     // progress at the same rate (measured with %globaltimer: with equal static shares the first CTA finished after 57 % of the
     // kernel and its SM ran under-occupied from then on), so every CTA keeps drawing tiles until the batch is exhausted.
 
+#ifdef SK_TRACE_CTAS  // development aid (tools/cta_trace.py): start time, SM and end time of every CTA
+    if (threadIdx.x == 0 && blockIdx.x < 1024) {
+        unsigned long long t; unsigned sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        sk_cta_trace[3 * blockIdx.x] = t; sk_cta_trace[3 * blockIdx.x + 1] = sm;
+    }
+#endif
     // one elected thread: ticket and geometry of the CTA's k-th tile -> geoms[k & 3] (stream = -1: no tile left), then the TMA
     // request for its raw bytes
     auto issue = [&](unsigned k) {
@@ -588,6 +606,13 @@ resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant
         int_epilogue<R, PCM>(y, dst, g.stream, g.n0, b, lane, 0, true);
         __syncthreads();  // windows free for the next tile
     }
+#ifdef SK_TRACE_CTAS
+    if (threadIdx.x == 0 && blockIdx.x < 1024) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        sk_cta_trace[3 * blockIdx.x + 2] = t;
+    }
+#endif
 }
 
 // ================================================================================================

@@ -5,3 +5,7 @@ int sk_launch_int_3(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const s
                      size_t n_streams, int lanes_per_stream) {
     return launch_int<3>(ctx, src, dst, plan, h_table, d_table, n_streams, lanes_per_stream);
 }
+
+#ifdef SK_TRACE_CTAS
+extern "C" int sk_debug_cta_trace(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, sk_cta_trace, sizeof(sk_cta_trace)); }
+#endif
