@@ -108,6 +108,9 @@ uint64_t sk_ctx_launch_count(const sk_ctx* ctx);
  * FFMA and the packed sm_100 FFMA2 instruction; _peak returns the larger of the two */
 int  sk_ctx_measure_ffma_peak(sk_ctx* ctx, double* tflops);
 int  sk_ctx_measure_ffma_peaks(sk_ctx* ctx, double* scalar_tflops, double* packed_tflops);
+/* Diagnostic: fill the shared memory of every SM with `pattern` (e.g. 0x7fc00000, a quiet NaN). Shared memory keeps its
+ * contents between kernels, so a parity run after this call exposes any kernel that reads a word it did not stage. */
+int  sk_ctx_poison_shared_memory(sk_ctx* ctx, uint32_t pattern);
 
 /* ------------------------------------------------------------------ kernel 2: G.711 */
 /* replaces soundkit_g711::decode_i16 (soundkit-g711/src/lib.rs:52) and

@@ -69,6 +69,7 @@ extern "C" {
     pub fn sk_ctx_launch_count(ctx: *const sk_ctx) -> u64;
     pub fn sk_ctx_measure_ffma_peak(ctx: *mut sk_ctx, tflops: *mut c_double) -> c_int;
     pub fn sk_ctx_measure_ffma_peaks(ctx: *mut sk_ctx, scalar: *mut c_double, packed: *mut c_double) -> c_int;
+    pub fn sk_ctx_poison_shared_memory(ctx: *mut sk_ctx, pattern: u32) -> c_int;
 
     pub fn sk_g711_decode(ctx: *mut sk_ctx, law: c_int, input: *const u8, n: usize, out_kind: c_int, out: *mut c_void) -> c_int;
     pub fn sk_g711_decode_dev(ctx: *mut sk_ctx, law: c_int, input: *const u8, n: usize, out_kind: c_int, out: *mut c_void) -> c_int;

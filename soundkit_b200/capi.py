@@ -31,7 +31,7 @@ G726_LEFT, G726_RIGHT = 0, 1
 EXPORTS = (
     "sk_abi_version", "sk_ctx_create", "sk_ctx_destroy", "sk_last_error", "sk_ctx_set_stream", "sk_ctx_reset_stream",
     "sk_ctx_synchronize",
-    "sk_ctx_launch_count", "sk_ctx_measure_ffma_peak", "sk_ctx_measure_ffma_peaks",
+    "sk_ctx_launch_count", "sk_ctx_measure_ffma_peak", "sk_ctx_measure_ffma_peaks", "sk_ctx_poison_shared_memory",
     "sk_g711_decode", "sk_g711_decode_dev", "sk_g711_encode", "sk_g711_encode_dev",
     "sk_pcm_flat_convert", "sk_pcm_flat_convert_dev", "sk_flat_op_widths", "sk_dvd_lpcm_unpack", "sk_dvd_lpcm_unpack_dev",
     "sk_deinterleave", "sk_interleave_i16",
@@ -90,6 +90,7 @@ def load():
         "sk_ctx_launch_count": (C.c_uint64, [vp]),
         "sk_ctx_measure_ffma_peak": (i, [vp, C.POINTER(C.c_double)]),
         "sk_ctx_measure_ffma_peaks": (i, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "sk_ctx_poison_shared_memory": (i, [vp, C.c_uint32]),
         "sk_g711_decode": (i, [vp, i, vp, sz, i, vp]),
         "sk_g711_decode_dev": (i, [vp, i, vp, sz, i, vp]),
         "sk_g711_encode": (i, [vp, i, i, vp, sz, vp]),
@@ -215,6 +216,10 @@ class Context:
         v = C.c_double()
         self._ck(self.L.sk_ctx_measure_ffma_peak(self.h, C.byref(v)))
         return v.value
+
+    def poison_shared_memory(self, pattern=0x7FC00000):
+        """diagnostic: every SM's shared memory is left full of `pattern` (default: quiet NaN) for the next kernels to find"""
+        self._ck(self.L.sk_ctx_poison_shared_memory(self.h, pattern))
 
     def ffma_peaks_tflops(self):
         a, b = C.c_double(), C.c_double()

@@ -228,3 +228,23 @@ extern "C" int sk_ctx_measure_ffma_peak(sk_ctx* ctx, double* tflops) {
     *tflops = a > b ? a : b;
     return SK_OK;
 }
+
+// ---- diagnostic: poison shared memory -----------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1) poison_smem_kernel(uint32_t pattern, int words, unsigned* sink) {
+    extern __shared__ uint32_t poison_sm[];
+    for (int i = threadIdx.x; i < words; i += blockDim.x) poison_sm[i] = pattern;
+    __syncthreads();
+    if (threadIdx.x == 0 && poison_sm[words - 1] != pattern) *sink = 1;  // keeps the stores alive
+}
+
+extern "C" int sk_ctx_poison_shared_memory(sk_ctx* ctx, uint32_t pattern) {
+    if (!ctx) return SK_E_ARG;
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int bytes = 226 * 1024;  // one CTA owns (nearly) the whole shared memory of its SM, so the first wave covers every SM
+    SK_CUDA(ctx, cudaFuncSetAttribute(poison_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    int rc = sk_ensure_dev_out(ctx, 256);
+    if (rc) return rc;
+    poison_smem_kernel<<<ctx->num_sms * 2, 1024, bytes, ctx->stream>>>(pattern, bytes / 4, (unsigned*)ctx->d_out);
+    SK_LAUNCH_CHECK(ctx);
+    return SK_OK;
+}

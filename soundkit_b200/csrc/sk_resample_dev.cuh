@@ -184,16 +184,14 @@ template <int STEP> struct IntCfg;
 // R outputs per thread and the bank skew between the two lanes' windows, chosen so that the 8
 // threads of an LDS.128 quarter-warp (4 thread-blocks x 2 lanes) hit 8 distinct 4-bank groups:
 // thread stride S = STEP*R words; need {S*b mod 32, b<4} U {S*b + SKEW mod 32} to be 8 distinct
-// multiples of 4.
-#ifdef SK_INT3_R12  // experiment: 12 outputs per thread (2 CTAs/SM)
-template <> struct IntCfg<3>  { static constexpr int R = 12, SKEW = 16; };  // S = 36: {0,4,8,12} + 16
-#else
-template <> struct IntCfg<3>  { static constexpr int R = 8, SKEW = 4;  };  // S = 24: {0,24,16,8} + 4
-#endif
-template <> struct IntCfg<2>  { static constexpr int R = 6, SKEW = 16; };  // S = 12: {0,12,24,4} + 16
-template <> struct IntCfg<4>  { static constexpr int R = 7, SKEW = 16; };  // S = 28: {0,28,24,20} + 16
-template <> struct IntCfg<6>  { static constexpr int R = 6, SKEW = 16; };  // S = 36: {0,4,8,12} + 16
-template <> struct IntCfg<12> { static constexpr int R = 7, SKEW = 16; };  // S = 84: {0,20,8,28} + 16
+// multiples of 4.  CTAS = resident CTAs per SM of the persistent TMA kernel (register budget).
+// Step 3 (48 -> 16 kHz, the headline) runs 12 outputs per thread at 2 CTAs/SM: one LDCU.128 then feeds 12 FFMA2 instead of 8
+// and the input span per output shrinks, which is worth more than the third CTA (57.8 -> 60.1 G frames/s on B200).
+template <> struct IntCfg<3>  { static constexpr int R = 12, SKEW = 16, CTAS = 2; };  // S = 36: {0,4,8,12} + 16
+template <> struct IntCfg<2>  { static constexpr int R = 6, SKEW = 16, CTAS = 3; };   // S = 12: {0,12,24,4} + 16
+template <> struct IntCfg<4>  { static constexpr int R = 7, SKEW = 16, CTAS = 3; };   // S = 28: {0,28,24,20} + 16
+template <> struct IntCfg<6>  { static constexpr int R = 6, SKEW = 16, CTAS = 3; };   // S = 36: {0,4,8,12} + 16
+template <> struct IntCfg<12> { static constexpr int R = 7, SKEW = 16, CTAS = 3; };  // S = 84: {0,20,8,28} + 16
 
 constexpr int kIntThreads = 256;                 // 128 thread-blocks x 2 lanes
 constexpr int kIntBlocksPerLane = kIntThreads / 2;
@@ -288,6 +286,26 @@ __device__ __forceinline__ void int_epilogue(const float (&y)[R], const OutDesc&
                     uint32_t* w = reinterpret_cast<uint32_t*>(bp + no * 3);
                     w[0] = q4[0] | (q4[1] << 24); w[1] = (q4[1] >> 8) | (q4[2] << 16); w[2] = (q4[2] >> 16) | (q4[3] << 8);
                 } else *reinterpret_cast<uint4*>(bp + no * 4) = make_uint4(q4[0], q4[1], q4[2], q4[3]);
+            } else if (R == 12 && nb + 12 <= dst.n_out && ((dst.pcm_stream_stride & 7) == 0) && (((uintptr_t)dst.pcm_base) & 7) == 0) {
+                uint32_t q6[6];  // 6 samples per thread: 12 bytes (4-byte aligned), 18 bytes (2-byte aligned) or 24 bytes (8-byte aligned)
+#pragma unroll
+                for (int q = 0; q < 6; q++) q6[q] = pcm_quantize(o[q % H], dst.pcm_bits, dst.pcm_float);
+                if (ob == 2) {
+                    uint32_t* w = reinterpret_cast<uint32_t*>(bp + no * 2);
+#pragma unroll
+                    for (int v = 0; v < 3; v++) w[v] = q6[2 * v] | (q6[2 * v + 1] << 16);
+                } else if (ob == 3) {
+                    uint16_t* h = reinterpret_cast<uint16_t*>(bp + no * 3);
+#pragma unroll
+                    for (int v = 0; v < 3; v++) {
+                        const uint32_t a = q6[2 * v], c = q6[2 * v + 1];
+                        h[3 * v] = (uint16_t)a; h[3 * v + 1] = (uint16_t)((a >> 16) | (c << 8)); h[3 * v + 2] = (uint16_t)(c >> 8);
+                    }
+                } else {
+                    uint2* w = reinterpret_cast<uint2*>(bp + no * 4);
+#pragma unroll
+                    for (int v = 0; v < 3; v++) w[v] = make_uint2(q6[2 * v], q6[2 * v + 1]);
+                }
             } else {
 #pragma unroll
                 for (int q = 0; q < H; q++)
@@ -301,7 +319,7 @@ __device__ __forceinline__ void int_epilogue(const float (&y)[R], const OutDesc&
         float* op = dst.base + stream * dst.stream_stride;
         if (R == 8 && nb + 8 <= dst.n_out && ((dst.stream_stride & 3) == 0)) {
             *reinterpret_cast<float4*>(op + no) = make_float4(o[0], o[1], o[2], o[3]);
-        } else if (R == 12 && nb + 12 <= dst.n_out && ((dst.stream_stride & 1) == 0)) {
+        } else if (R == 12 && nb + 12 <= dst.n_out && ((dst.stream_stride & 1) == 0) && (((uintptr_t)dst.base) & 7) == 0) {
 #pragma unroll
             for (int v = 0; v < 3; v++) *reinterpret_cast<float2*>(op + no + 2 * v) = make_float2(o[(2 * v) % H], o[(2 * v + 1) % H]);
         } else {
@@ -344,7 +362,9 @@ resample_int_kernel(const __grid_constant__ Taps taps, const __grid_constant__ S
 
     if (threadIdx.x == 0) s_big = 0;
     __syncthreads();
-    const bool big = stage_window<kIntThreads>(src, stream, lane0, lane1_valid, w0, W, smem, smem + WS);
+    // W + 4: when the tile's last output has an odd window offset its final FFMA2 pairs tap 255 with a zero coefficient, and
+    // that zero multiplies the word one past the window — it must be staged data (finite), not whatever shared memory held
+    const bool big = stage_window<kIntThreads>(src, stream, lane0, lane1_valid, w0, W + 4, smem, smem + WS);
     if (big) s_big = 1;
     __syncthreads();
 
@@ -502,12 +522,9 @@ __device__ unsigned long long sk_cta_trace[3 * 1024];
 // per-tile geometry, computed once by the TMA-issuing thread and handed to the CTA through shared memory
 struct TileGeom { int stream; int n0; int wa; int g_lo; int g_hi; int pad[3]; };
 
-#ifndef SK_TMA_CTAS_PER_SM
-#define SK_TMA_CTAS_PER_SM 3
-#endif
 
 template <int STEP, int SRCW, bool PCM>
-__global__ void __launch_bounds__(kIntThreads, SK_TMA_CTAS_PER_SM)
+__global__ void __launch_bounds__(kIntThreads, IntCfg<STEP>::CTAS)
 resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant__ SrcDesc src, const __grid_constant__ OutDesc dst, long long i0_first,
                         unsigned tiles_per_stream, unsigned total_tiles, const float* __restrict__ row1, unsigned* __restrict__ ticket) {
     constexpr int R = IntCfg<STEP>::R;
@@ -517,6 +534,9 @@ resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant
     constexpr int WS = tma_lane_stride<STEP>();
     constexpr int FB = 2 * SRCW;  // bytes per stereo frame
     constexpr int RAWB = tma_raw_bytes<STEP, SRCW>();
+    // the word one past the tile's window is only read (against a zero coefficient) when the last output's offset is odd; the
+    // converted region must then reach it
+    static_assert(((LEAD + STEP * (R - 1)) & 1) == 0 || WF > LEAD + int_window<STEP>(), "stage one more frame for this STEP / R");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     float* win = reinterpret_cast<float*>(smem_raw);
     uint8_t* raw = smem_raw + 2 * WS * sizeof(float);
@@ -627,7 +647,7 @@ static int launch_int_tma(sk_ctx* ctx, const Taps& taps, const SrcDesc& src, con
     if (kPcm) SK_CUDA(ctx, cudaFuncSetAttribute(resample_int_tma_kernel<STEP, SRCW, kPcm>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const long long tiles_per_stream = (long long)((plan->n_out + T - 1) / T);
     const long long total = tiles_per_stream * (long long)n_streams;
-    const int per_sm = std::max(1, std::min(SK_TMA_CTAS_PER_SM, (220 * 1024) / smem));
+    const int per_sm = std::max(1, std::min(IntCfg<STEP>::CTAS, (220 * 1024) / smem));
     const long long grid = std::min<long long>(total, (long long)ctx->num_sms * per_sm);
     // integer sources are staged unscaled (see convert4): fold the exact power-of-two scale into the taps and let the
     // per-frame edge path (decode_sample_bits) stage the same unscaled values
@@ -653,6 +673,10 @@ static int launch_int_tma(sk_ctx* ctx, const Taps& taps, const SrcDesc& src, con
     return SK_OK;
 }
 
+int sk_launch_int3_tma_w2(sk_ctx* ctx, const Taps& taps, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, const float* d_table, size_t n_streams);
+int sk_launch_int3_tma_w3(sk_ctx* ctx, const Taps& taps, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, const float* d_table, size_t n_streams);
+int sk_launch_int3_tma_w4(sk_ctx* ctx, const Taps& taps, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, const float* d_table, size_t n_streams);
+
 template <int STEP>
 static int launch_int(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, const float* h_table, const float* d_table,
                       size_t n_streams, int lanes_per_stream) {
@@ -664,9 +688,15 @@ static int launch_int(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const
     if (src.width != 0 && src.channels == 2 && lanes_per_stream == 2 && src.origin == 0 && src.valid_lo == 0 &&
         plan->i0_first == -(long long)(SINC_LEN / 2) + STEP && ((uintptr_t)src.base % 16) == 0 && (src.stream_stride % 16) == 0 &&
         (long long)n_streams * (long long)((plan->n_out + int_tile_outputs<STEP>() - 1) / int_tile_outputs<STEP>()) < (1ll << 31)) {
-        if (src.width == 2) return launch_int_tma<STEP, 2>(ctx, taps, src, dst, plan, d_table, n_streams);
-        if (src.width == 3) return launch_int_tma<STEP, 3>(ctx, taps, src, dst, plan, d_table, n_streams);
-        return launch_int_tma<STEP, 4>(ctx, taps, src, dst, plan, d_table, n_streams);
+        if constexpr (STEP == 3) {  // its six TMA kernels are the longest compiles of the build: one translation unit per sample width
+            if (src.width == 2) return sk_launch_int3_tma_w2(ctx, taps, src, dst, plan, d_table, n_streams);
+            if (src.width == 3) return sk_launch_int3_tma_w3(ctx, taps, src, dst, plan, d_table, n_streams);
+            return sk_launch_int3_tma_w4(ctx, taps, src, dst, plan, d_table, n_streams);
+        } else {
+            if (src.width == 2) return launch_int_tma<STEP, 2>(ctx, taps, src, dst, plan, d_table, n_streams);
+            if (src.width == 3) return launch_int_tma<STEP, 3>(ctx, taps, src, dst, plan, d_table, n_streams);
+            return launch_int_tma<STEP, 4>(ctx, taps, src, dst, plan, d_table, n_streams);
+        }
     }
     constexpr int T = int_tile_outputs<STEP>();
     constexpr int smem = int_smem_bytes<STEP>();

@@ -865,3 +865,36 @@ def test_float_sample_to_i16_without_f64_is_exact_over_whole_binades(ctx, oracle
         x = bits.view(np.float32)
         x = np.concatenate([x, -x])[None, :]
         assert np.array_equal(ctx.planar_f32_to_pcm(x, 16, capi.FMT_SIGNED), oracle.f32_channels_to_bytes(x, 16, 0)), e
+
+
+# ---------------------------------------------------------------------------------------------- poisoned shared memory
+@pytest.mark.parametrize("pattern", [0x7FC00000, 0xFF800000])
+def test_resamplers_do_not_read_unstaged_shared_memory(oracle, pattern):
+    """Shared memory keeps its contents between kernels.  With every SM's shared memory full of NaN (or -Inf) bit patterns, a
+    kernel that multiplies a word it never staged — even by a zero coefficient — produces NaN.  (Found the hard way: the
+    scalar-staging 48->16 kHz kernel paired tap 255 of a tile's last output with the word one past its window.)"""
+    c = capi.Context(0)
+    rng = np.random.default_rng(pattern & 0xFFFF)
+    cases = [(48000, 16000, 1, 16), (48000, 16000, 6, 24), (48000, 16000, 2, 24), (48000, 24000, 3, 16), (48000, 8000, 2, 16),
+             (44100, 16000, 2, 16), (44100, 48000, 1, 24), (96000, 8000, 1, 16), (48000, 12000, 2, 32)]
+    for i_rate, o_rate, channels, bits in cases:
+        frames = 20011
+        data = rng.integers(0, 256, frames * channels * (bits // 8), dtype=np.uint8)
+        planar = oracle.pcm_to_planar_f32(data, bits, 0, False, channels, capi.MODE_B)
+        st = oracle.Stream(i_rate, o_rate, channels)
+        want = np.concatenate([st.process(planar), st.flush()], axis=1)
+        c.poison_shared_memory(pattern)
+        got = c.normalize_stream(data, bits, capi.FMT_SIGNED, False, channels, capi.MODE_B, i_rate, o_rate, capi.SEM_STREAMING, capi.MIX_NONE)
+        assert got.shape == want.shape
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (i_rate, o_rate, channels, bits)
+    # the 48 kHz normalizer stages through shared memory as well
+    data = rng.integers(0, 256, 30011 * 4, dtype=np.uint8)
+    wl, wr = oracle.normalize48k([(data, 16, 0, False, 2, 44100)])
+    c.poison_shared_memory(pattern)
+    gn = c.normalizer48k()
+    gl, gr = gn.push(data, 16, 0, False, 2, 44100)
+    fl, fr = gn.finish()
+    gn.close()
+    assert np.array_equal(np.concatenate([gl, fl]).view(np.uint32), wl.view(np.uint32))
+    assert np.array_equal(np.concatenate([gr, fr]).view(np.uint32), wr.view(np.uint32))
+    c.close()
