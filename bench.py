@@ -9,13 +9,17 @@ collective (weak scaling, independent streams).
 
   value     output Msamples/s (mono f32 frames), inputs resident in HBM, CUDA-event timed
   e2e       same metric through the host-buffer C-ABI call (sk_normalize_batch): pinned host input,
-            H2D + kernel + D2H inside the timed region
-  roofline  FP32 CUDA-core roofline of the dominant kernel (resample_int_kernel<3>), peak = FFMA
-            microbenchmark measured in the same run; HBM figures alongside
+            H2D + kernel + D2H inside the timed region; beside it the machine's own ceiling for the
+            same bytes (concurrent pinned H2D + D2H cudaMemcpyAsync, all ranks at once)
+  roofline  FP32 CUDA-core roofline of the dominant kernel (resample_int_tma_kernel<3, 3>), peak = FFMA
+            microbenchmark measured in the same run (nominal figure beside it); HBM figures alongside
+  parity    outside the timed region: whole streams of this very wave (device path and e2e path) are
+            compared bit for bit with the CPU oracle; a mismatch fails the run
   cpu_baseline  the oracle (C restatement of the reference's Rust path, rubato AVX2+FMA order) timed on
             the box's host cores on a bounded sample
 
-`--impl reference` times that CPU path only (rank 0), same metric/unit/config.
+`--impl reference` times that CPU path only (rank 0) on the SAME wave (same streams, same lengths).
+No NCCL anywhere: ranks meet on a gloo barrier for timing only.
 """
 import argparse
 import json
@@ -33,6 +37,8 @@ IN_RATE, OUT_RATE = 48000, 16000
 BITS, CHANNELS = 24, 2
 FLOPS_PER_FRAME = 1024.0  # 2 channels x 256 taps x 2 flop (P = 1: integer t_ratio)
 BYTES_PER_FRAME = 22.0    # 3 input frames x 6 B + 4 B out
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4: SMs x FP32 lanes x 2 flop x max SM clock
+METRIC = "output Msamples/s, 48k->16k sinc resample"
 
 
 def parse():
@@ -44,22 +50,28 @@ def parse():
     ap.add_argument("--streams", type=int, default=32, help="streams per GPU per step (one wave)")
     ap.add_argument("--seconds", type=float, default=600.0, help="stream length in seconds")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary kernel measurements")
+    ap.add_argument("--extras", default=None, help="comma list of extras groups to run (g711,convert,bytes,flat,g726,norm48k,resample,latency,stream)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     return ap.parse_args()
 
 
-def config_dict(args, frames, n_out):
+def config_dict(args, frames, n_out, world):
     return {"workload": f"BASELINE configs[4] wave: {args.streams} streams/GPU x {args.seconds:g} s s24le stereo 48 kHz -> "
                         f"f32 mono 16 kHz (fused convert + sinc resample + downmix, streaming semantics)",
-            "streams_per_gpu": args.streams, "frames_per_stream": frames, "out_frames_per_stream": n_out,
+            "streams_per_gpu": args.streams, "streams_total": args.streams * world, "frames_per_stream": frames, "out_frames_per_stream": n_out,
             "in_rate": IN_RATE, "out_rate": OUT_RATE, "bits": BITS, "channels": CHANNELS,
             "l2": "inputs larger than L2 (each stream's input alone is %.0f MB)" % (frames * 6 / 1e6),
-            "parallelism": "streams sharded over GPUs, no collective"}
+            "wave_size": "32 streams = 5.5 GB in + 1.2 GB out per GPU; the persistent kernel's rate does not depend on the wave size "
+                         "(tiles are drawn by ticket), and the e2e leg needs the same wave in pinned HOST memory on every rank, which is "
+                         "what bounds it (8 ranks x 6.8 GB pinned), not the 180 GB of HBM",
+            "parallelism": "streams sharded over GPUs, no collective (gloo barrier for timing only)"}
 
 
 # ------------------------------------------------------------------------------------------- CPU leg
-def cpu_chain(threads, streams_per_thread, seconds, seed=0):
-    """oracle chain on `threads` host threads, one stream per call; returns (mono frames, wall seconds)."""
+def cpu_wave(threads, n_streams, seconds, seed=0):
+    """the oracle chain over `n_streams` whole streams on `threads` host threads (streams dealt round robin, one call per
+    stream); returns (mono frames produced, wall seconds).  Synthetic input: one random stream buffer shared by all streams
+    (the cost is data independent)."""
     import numpy as np
     from oracle import oracle as O
     O.build()
@@ -67,11 +79,12 @@ def cpu_chain(threads, streams_per_thread, seconds, seed=0):
     rng = np.random.default_rng(seed)
     raw = rng.integers(0, 256, frames * CHANNELS * 3, dtype=np.uint8)
     O.normalize_chain_mono(raw[: 4800 * 6], BITS, O.SIGNED, False, CHANNELS, IN_RATE, OUT_RATE)  # warm the table code
+    threads = max(1, min(threads, n_streams))
     outs = [0] * threads
 
     def work(t):
         n = 0
-        for _ in range(streams_per_thread):
+        for _ in range(t, n_streams, threads):
             n += O.normalize_chain_mono(raw, BITS, O.SIGNED, False, CHANNELS, IN_RATE, OUT_RATE).size
         outs[t] = n
 
@@ -84,43 +97,49 @@ def cpu_chain(threads, streams_per_thread, seconds, seed=0):
     return sum(outs), time.perf_counter() - t0
 
 
+def avx_label():
+    from oracle import oracle as O
+    return "AVX2+FMA" if O.lib().sko_resampler_uses_avx() else "scalar fmaf"
+
+
 def cpu_baseline(seconds=30.0, target_wall=8.0):
     cores = os.cpu_count() or 1
-    frames, wall = cpu_chain(cores, 1, seconds)
+    frames, wall = cpu_wave(cores, cores, seconds)
     reps = max(1, min(16, int(target_wall / max(wall, 1e-3))))
     if reps > 1:
-        frames, wall = cpu_chain(cores, reps, seconds)
-    else:
-        reps = 1
-    from oracle import oracle as O
+        frames, wall = cpu_wave(cores, cores * reps, seconds)
     return {"value": frames / wall / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
             "sample": f"{cores} threads x {reps} streams x {seconds:g} s s24le stereo 48k -> f32 mono 16k, oracle C restatement "
-                      f"(rubato order, {'AVX2+FMA' if O.lib().sko_resampler_uses_avx() else 'scalar fmaf'}, both interpolation products)",
+                      f"(rubato order, {avx_label()}, both interpolation products)",
             "wall_s": wall}
 
 
 def run_reference(args):
+    """the reference's CPU path (its C restatement: the Rust crate cannot be built here) over the SAME wave our arm runs:
+    streams_per_gpu x n_gpus whole streams per step on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = max(1, args.gpus)
     frames = int(args.seconds * IN_RATE)
     cores = os.cpu_count() or 1
-    sample_s = 30.0
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_chain(cores, 1, sample_s)
+    n_streams = args.streams * world
+    for _ in range(max(0, args.warmup)):
+        cpu_wave(cores, min(cores, n_streams), min(args.seconds, 30.0))  # warm caches / clocks on a short sample
     total_frames, total_wall = 0, 0.0
     for _ in range(max(1, args.steps)):
-        f, w = cpu_chain(cores, 1, sample_s)
+        f, w = cpu_wave(cores, n_streams, args.seconds)
         total_frames += f
         total_wall += w
+    n_out = total_frames // (n_streams * max(1, args.steps))
     val = total_frames / total_wall / 1e6
-    from oracle import oracle as O
-    sample = (f"each step = {cores} threads x 1 stream x {sample_s:g} s of the same workload (the Rust reference cannot be built here: "
-              f"no cargo/rustc; this is its C restatement, {'AVX2+FMA' if O.lib().sko_resampler_uses_avx() else 'scalar fmaf'})")
-    line = {"impl": "reference", "metric": "output Msamples/s, 48k->16k sinc resample", "value": val, "unit": "Msamples/s",
+    sample = (f"each step = the whole wave: {n_streams} streams x {args.seconds:g} s on {min(cores, n_streams)} host threads, one stream per call "
+              f"(the Rust reference cannot be built here: no cargo/rustc; this is its C restatement, {avx_label()}, both interpolation "
+              f"products as rubato executes them); warm-up steps run a 30 s sample")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Msamples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_wall / max(1, args.steps) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args, frames, None),
+            "config": config_dict(args, frames, n_out, world),
             "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -167,27 +186,35 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------- GPU leg
 def extras(ctx, torch, peaks, only=None):
-    """secondary kernels (BASELINE configs 2-4), device resident, CUDA-event timed, each > L2 sized.
-    `only`: optional list of substrings selecting which groups run (g711 / convert / resample)."""
+    """secondary kernels (BASELINE configs 1-3 and the SURVEY 8(f) rows), device resident, CUDA-event timed, each > L2 sized.
+    Every entry carries the best and the median of its repetitions.  `only`: optional list of group names."""
+    import numpy as np
     from soundkit_b200 import capi
     res = {}
 
     def want(group):
-        return only is None or any(o in group for o in only)
+        return only is None or group in only
 
     def timed(fn, reps=5):
         fn(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        best = 1e30
+        ts = []
         for _ in range(reps):
             e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
-        return best * 1e-3
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        return min(ts), statistics.median(ts)
 
     hbm = peaks.get("hbm_gbs", 6650.0)
 
     def hbm_entry(nbytes, t, samples):
-        return {"GB/s": nbytes / t / 1e9, "frac_of_measured_hbm": nbytes / t / 1e9 / hbm, "Msamples/s": samples / t / 1e6}
+        best, med = t
+        return {"GB/s": nbytes / best / 1e9, "frac_of_measured_hbm": nbytes / best / 1e9 / hbm, "Msamples/s": samples / best / 1e6,
+                "median": {"GB/s": nbytes / med / 1e9, "frac_of_measured_hbm": nbytes / med / 1e9 / hbm, "Msamples/s": samples / med / 1e6}}
+
+    def flop_entry(flops, t, samples):
+        best, med = t
+        return {"TFLOP/s": flops / best / 1e12, "Msamples/s": samples / best / 1e6,
+                "median": {"TFLOP/s": flops / med / 1e12, "Msamples/s": samples / med / 1e6}}
 
     if want("g711"):
         n = 1 << 30  # 1 Gi samples of G.711 (BASELINE configs[2] is 15.7 Gi samples; one wave)
@@ -230,7 +257,7 @@ def extras(ctx, torch, peaks, only=None):
         d = capi.BatchDesc(raw.data_ptr(), stride, S, frames, 24, capi.FMT_SIGNED, 0, 2, capi.MODE_B, 48000, 16000, capi.SEM_STREAMING,
                            capi.MIX_SCALE_THEN_SUM, 0, 0, 0)
         t = timed(lambda: ctx.normalize_batch_pcm_dev(d, 16, 0, o, ostride), reps=3)
-        res["chain_s24_stereo_48k_to_s16_mono_16k_bytes"] = {"Msamples/s": S * n_out / t / 1e6, "TFLOP/s": 1024.0 * S * n_out / t / 1e12}
+        res["chain_s24_stereo_48k_to_s16_mono_16k_bytes"] = flop_entry(1024.0 * S * n_out, t, S * n_out)
         del raw, o
     if want("flat"):
         # a few of the remaining R1 entry points (soundkit/src/audio_bytes.rs flat functions, f32_channels_to_bytes)
@@ -251,10 +278,10 @@ def extras(ctx, torch, peaks, only=None):
         S, n = 65536, 32000
         codes = torch.randint(0, 256, (S, n // 2), dtype=torch.uint8, device="cuda")
         pcm = torch.empty((S, n), dtype=torch.int16, device="cuda")
-        t = timed(lambda: ctx.g726_decode_batch_dev(4, 0, codes, n // 2, S, n // 2, capi.KIND_I16, pcm, n), reps=3)
-        res["g726_32k_decode_i16"] = {"Msamples/s": S * n / t / 1e6, "GB/s": S * n * 2.5 / t / 1e9, "streams": S}
-        t = timed(lambda: ctx.g726_encode_batch_dev(4, 0, capi.KIND_I16, pcm, n, S, n, codes, n // 2), reps=3)
-        res["g726_32k_encode_i16"] = {"Msamples/s": S * n / t / 1e6, "GB/s": S * n * 2.5 / t / 1e9, "streams": S}
+        b, m = timed(lambda: ctx.g726_decode_batch_dev(4, 0, codes, n // 2, S, n // 2, capi.KIND_I16, pcm, n), reps=3)
+        res["g726_32k_decode_i16"] = {"Msamples/s": S * n / b / 1e6, "GB/s": S * n * 2.5 / b / 1e9, "streams": S, "median": {"Msamples/s": S * n / m / 1e6}}
+        b, m = timed(lambda: ctx.g726_encode_batch_dev(4, 0, capi.KIND_I16, pcm, n, S, n, codes, n // 2), reps=3)
+        res["g726_32k_encode_i16"] = {"Msamples/s": S * n / b / 1e6, "GB/s": S * n * 2.5 / b / 1e9, "streams": S, "median": {"Msamples/s": S * n / m / 1e6}}
         del codes, pcm
     if want("norm48k"):
         # StreamingStereo48kNormalizer, 64 whole streams x 60 s s16le stereo 44.1 kHz -> f32 stereo 48 kHz
@@ -267,20 +294,120 @@ def extras(ctx, torch, peaks, only=None):
         res["normalizer48k_s16le_stereo_44k1"] = hbm_entry(S * (frames * 4 + n_out * 8), t, S * n_out * 2)
         del raw, o
     if want("resample"):
-        # non-integer ratios, stereo f32, one-shot semantics (BASELINE configs[3] wave: 44.1k -> 48k; plus the common
-        # downsampling case 44.1k -> 16k).  P = 2: both interpolation products, 1027 flop per output sample.
-        for in_rate, out_rate in ((44100, 48000), (44100, 16000)):
+        # non-integer ratios, stereo f32 (BASELINE configs[3] wave: 44.1k -> 48k, one-shot and chunk-4096 streaming; plus the
+        # common downsampling case 44.1k -> 16k).  P = 2: both interpolation products, 1027 flop per output sample.
+        for in_rate, out_rate, sem, tag in ((44100, 48000, capi.SEM_ONESHOT, ""), (44100, 48000, capi.SEM_STREAMING, "_streaming"),
+                                            (44100, 16000, capi.SEM_ONESHOT, "")):
             S, frames = 16, 2646000
-            n_out = ctx.batch_plan(in_rate, out_rate, frames, capi.SEM_ONESHOT)
+            n_out = ctx.batch_plan(in_rate, out_rate, frames, sem)
             x = (torch.rand((S, frames * 2), device="cuda") - 0.5)
             o = torch.empty((S, 2, n_out), dtype=torch.float32, device="cuda")
-            d = capi.BatchDesc(x.data_ptr(), x.stride(0) * 4, S, frames, 32, 1, 0, 2, capi.MODE_A, in_rate, out_rate, capi.SEM_ONESHOT,
+            d = capi.BatchDesc(x.data_ptr(), x.stride(0) * 4, S, frames, 32, 1, 0, 2, capi.MODE_A, in_rate, out_rate, sem,
                                capi.MIX_NONE, o.data_ptr(), 2 * n_out, n_out)
+            f0 = ctx.resample_fallback_outputs()
             t = timed(lambda: ctx.normalize_batch_dev(d), reps=3)
-            fl = 1027.0 * S * 2 * n_out
-            res[f"resample_{in_rate}_to_{out_rate}_stereo_f32"] = {"TFLOP/s": fl / t / 1e12, "Msamples/s": S * 2 * n_out / t / 1e6}
+            fb = (ctx.resample_fallback_outputs() - f0) / 4.0 / (S * 2 * n_out)
+            e = flop_entry(1027.0 * S * 2 * n_out, t, S * 2 * n_out)
+            e["fallback_share"] = fb
+            res[f"resample_{in_rate}_to_{out_rate}_stereo_f32{tag}"] = e
             del x, o
+    if want("stream") and hasattr(ctx, "resampler_batch"):
+        # batched stateful streaming (sk_resampler_batch_*): N live streams, one 4096-frame chunk each per call, state on the device
+        for in_rate, out_rate in ((48000, 16000), (44100, 48000)):
+            S, ch, chunks = 4096, 2, 8
+            rb = ctx.resampler_batch(in_rate, out_rate, ch, S)
+            x = torch.rand((S, ch, 4096), device="cuda") - 0.5
+            o = torch.empty((S, ch, rb.out_max), dtype=torch.float32, device="cuda")
+            def run():
+                for _ in range(chunks):
+                    rb.process_dev(x, o)
+            t = timed(run, reps=3)
+            n_per = 4096.0 * out_rate / in_rate
+            P = 1 if in_rate % out_rate == 0 else 2
+            res[f"stream_batch_{in_rate}_to_{out_rate}_{S}x{ch}ch_chunk4096"] = flop_entry((512.0 * P + 3) * S * ch * n_per * chunks, t, S * ch * n_per * chunks)
+            rb.close()
+            del x, o
+    if want("latency"):
+        res["latency"] = latency_table(ctx, np)
     return res
+
+
+def latency_table(ctx, np):
+    """small-call latency of the host-pointer drop-in API (no CPU fallback: every call is a PCIe round trip) with the CPU port
+    beside it: median microseconds per call."""
+    from oracle import oracle as O
+    from soundkit_b200 import capi
+    O.build()
+    rng = np.random.default_rng(5)
+    out = {}
+
+    def med_us(fn, reps):
+        fn(); fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        return statistics.median(ts) * 1e6
+
+    for n, reps in ((160, 200), (4096, 200), (4 << 20, 20)):
+        codes = rng.integers(0, 256, n, dtype=np.uint8)
+        out[f"g711_decode_ulaw_{n}B"] = {"gpu_us": med_us(lambda: ctx.g711_decode(capi.LAW_MULAW, codes), reps),
+                                         "cpu_port_us": med_us(lambda: O.g711_decode(capi.LAW_MULAW, codes), reps)}
+    # one 4096-frame stereo chunk through the stateful resampler (StreamingResampler::process granularity)
+    x = rng.uniform(-0.5, 0.5, (2, 4096)).astype(np.float32)
+    r = ctx.resampler(48000, 16000, 2, 4096)
+    ro = O.Resampler(48000, 16000, 4096, 2)
+    out["resampler_chunk_4096x2ch_48k_16k"] = {"gpu_us": med_us(lambda: r.process(x), 100), "cpu_port_us": med_us(lambda: ro.process(x), 100)}
+    r.close()
+    # BASELINE configs[0] (C1): one 60 s s16le stereo 48 kHz stream -> f32 mono 16 kHz via downsample_audio, single thread
+    frames = 2_880_000
+    pcm = rng.integers(-20000, 20000, frames * 2).astype(np.int16).view(np.uint8)
+    g = med_us(lambda: ctx.normalize_stream(pcm, 16, 0, False, 2, capi.MODE_A, 48000, 16000, capi.SEM_ONESHOT, capi.MIX_SUM_THEN_SCALE), 5)
+    c = med_us(lambda: O.mixdown_to_mono_f32(O.downsample_audio(pcm, 16, 0, 2, 48000, 16000, threads=1)), 3)
+    out["c1_downsample_audio_60s_s16_stereo"] = {"gpu_us": g, "cpu_port_us": c, "gpu_Msamples/s": 959956 / g, "cpu_port_1thread_Msamples/s": 959956 / c,
+                                                  "note": "host buffers in pageable memory both ways (what a Rust Vec gives); CPU port executes both "
+                                                          "interpolation products like rubato"}
+    return out
+
+
+def aggregate_extras(per_rank, hbm):
+    """sum the per-rank rates of the extras (every rank ran the same kernels on its own GPU at the same time)"""
+    if len(per_rank) == 1:
+        return per_rank[0]
+    agg = {}
+    rate_keys = ("GB/s", "Msamples/s", "TFLOP/s")
+    for name, e0 in per_rank[0].items():
+        if not isinstance(e0, dict) or name == "latency":
+            agg[name] = e0
+            continue
+        e = dict(e0)
+        for k in rate_keys:
+            if k in e0:
+                e[k] = sum(r.get(name, {}).get(k, 0.0) for r in per_rank)
+        if "frac_of_measured_hbm" in e0:
+            e["frac_of_measured_hbm"] = e["GB/s"] / (hbm * len(per_rank))
+        if "median" in e0:
+            e["median"] = {k: sum(r.get(name, {}).get("median", {}).get(k, 0.0) for r in per_rank) for k in e0["median"] if k in rate_keys}
+        e["per_gpu_min"] = {k: min(r.get(name, {}).get(k, 0.0) for r in per_rank) for k in rate_keys if k in e0}
+        agg[name] = e
+    return agg
+
+
+def copy_ceiling(torch, h_in, h_out, d_in, d_out, reps, barrier):
+    """what the machine gives for the e2e step's bytes: the same pinned buffers copied H2D and D2H concurrently on two
+    streams, nothing else running; all ranks start together.  Returns seconds per repetition (wall clock, synchronised)."""
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    def once():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+    once(); torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps
 
 
 def run_ours(args):
@@ -297,7 +424,7 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("gloo")  # timing barrier + max over ranks only: the data path has no collective, NCCL is not used
     from soundkit_b200 import shard
     numa_node = shard.bind_to_gpu_numa_node(local) if world > 1 else None  # before any pinned allocation
     ctx = capi.Context(local)
@@ -340,7 +467,7 @@ def run_ours(args):
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     clocks = sampler.stop()
-    total_ms_max = shard.max_over_ranks(total_ms, dist, "cuda")
+    total_ms_max = shard.max_over_ranks(total_ms, dist)
     frames_all = float(S) * n_out * world * args.steps
     value = frames_all / (total_ms_max * 1e-3) / 1e6
 
@@ -358,21 +485,61 @@ def run_ours(args):
         ctx.normalize_batch_host(hdesc)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    e2e_s = shard.max_over_ranks(e2e_s, dist, "cuda")
+    e2e_s = shard.max_over_ranks(e2e_s, dist)
     e2e_val = float(S) * n_out * world * e2e_steps / e2e_s / 1e6
     same = bool(torch.equal(h_out[:, :n_out], out[:, :n_out].cpu()))
 
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
+    # ---- parity, outside every timed region: whole streams of THIS wave against the CPU oracle (first and last of the rank),
+    # both the device-resident result and what the host-buffer call returned
+    from oracle import oracle as O
+    O.build()
+    checked, exact = [], True
+    for s in sorted({0, S - 1}):
+        want = O.normalize_chain_mono(h_in[s, : frames * 6].numpy(), BITS, O.SIGNED, False, CHANNELS, IN_RATE, OUT_RATE)
+        ok = want.size == n_out and np.array_equal(want.view(np.uint32), out[s, :n_out].cpu().numpy().view(np.uint32)) \
+            and np.array_equal(want.view(np.uint32), h_out[s, :n_out].numpy().view(np.uint32))
+        checked.append(lo + s)
+        exact = exact and bool(ok)
+    parity = {"oracle": "oracle/ C restatement (bit-for-bit)", "streams_checked": checked, "frames_each": n_out, "bit_exact": exact,
+              "e2e_equals_device_path": same}
+    if not exact or not same:
+        print(json.dumps({"error": "parity failure: the wave's output differs from the oracle", "parity": parity}), flush=True)
+        raise SystemExit(3)
 
+    # the machine's ceiling for the same bytes (concurrent H2D + D2H of the pinned buffers, all ranks at once)
+    ceil_s = copy_ceiling(torch, h_in, h_out, raw, out, 3, barrier)
+    ceil_s = shard.max_over_ranks(ceil_s, dist)
+    ceil_val = float(S) * n_out * world / ceil_s / 1e6
+
+    only = [x for x in args.extras.split(",") if x] if args.extras else None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    ext = None
+    if not args.no_extras:
+        try:
+            del raw, out, h_in, h_out
+            torch.cuda.empty_cache()
+            barrier()
+            groups = only if only is not None else ["g711", "convert", "bytes", "flat", "g726", "norm48k", "resample", "stream", "latency"]
+            mine = extras(ctx, torch, peaks, [x for x in groups if rank == 0 or x != "latency"])
+        except Exception as e:  # extras must never cost the headline line
+            mine = {"error": repr(e)}
+        if dist is not None:
+            allx = [None] * world
+            dist.all_gather_object(allx, mine)
+            ext = aggregate_extras(allx, hbm_peak) if rank == 0 else None
+        else:
+            ext = mine
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
     ffma_peak = ctx.ffma_peak_tflops()
     launch_ms = statistics.mean(per_launch_ms)
     kernels_per_step = max(1, launches // max(1, args.steps))
@@ -389,30 +556,31 @@ def run_ours(args):
         pass
     roofline = {"bound": "fp32", "kernel": "resample_int_tma_kernel<3, 3> (fused s24->f32 + 256-tap FIR x2ch + downmix)",
                 "achieved": ach, "peak": ffma_peak, "unit": "TFLOP/s", "frac": ach / ffma_peak,
-                "peak_source": "FFMA microbenchmark measured in this run (sk_ctx_measure_ffma_peak); nominal 148 SM x 128 x 2 x 1.965 GHz = 74.4",
-                "algorithmic_flops_per_launch": FLOPS_PER_FRAME * S * n_out, "launch_ms": launch_ms,
+                "peak_source": "FFMA / FFMA2 register microbenchmark measured in this run (sk_ctx_measure_ffma_peak); MEASURED_PEAKS.json has no FP32 "
+                               "CUDA-core entry",
+                "peak_nominal": FP32_NOMINAL_TFLOPS, "frac_of_nominal": ach / FP32_NOMINAL_TFLOPS,
+                "algorithmic_flops_per_launch": FLOPS_PER_FRAME * S * n_out, "launch_ms": launch_ms, "launch_ms_median": statistics.median(per_launch_ms),
                 "kernels_per_step": kernels_per_step, "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
                 "traffic_source": traffic_src, "algorithmic_bytes_per_launch": BYTES_PER_FRAME * S * n_out,
                 "hbm": {"achieved_GBs": BYTES_PER_FRAME * S * n_out / (launch_ms * 1e-3) / 1e9, "peak_GBs": hbm_peak,
                         "frac": BYTES_PER_FRAME * S * n_out / (launch_ms * 1e-3) / 1e9 / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"}}
-    line = {"metric": "output Msamples/s, 48k->16k sinc resample", "value": value, "unit": "Msamples/s", "n_gpus": world,
+    line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (uniform random s24 samples, full range)",
-            "config": config_dict(args, frames, n_out), "clocks": clocks,
+            "config": config_dict(args, frames, n_out, world), "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": S * frames * CHANNELS * 3,
-                    "d2h_bytes_per_step": S * n_out * 4, "steps": e2e_steps, "api": "sk_normalize_batch (host pointers, pinned)", "numa_node": numa_node,
-                    "matches_device_path": same},
-            "gpu_launches": launches, "roofline": roofline}
+                    "d2h_bytes_per_step": S * n_out * 4, "steps": e2e_steps, "api": "sk_normalize_batch (host pointers, pinned; 3-deep slab pipeline)",
+                    "numa_node": numa_node, "copy_ceiling": {"value": ceil_val, "unit": "Msamples/s",
+                                                             "how": "the step's H2D and D2H bytes as two concurrent cudaMemcpyAsync on the same pinned "
+                                                                    "buffers, no kernel, all ranks at once",
+                                                             "GB/s_h2d_plus_d2h_all_ranks": world * (S * frames * 6 + S * n_out * 4) / ceil_s / 1e9},
+                    "frac_of_copy_ceiling": e2e_val / ceil_val},
+            "parity": parity, "gpu_launches": launches, "roofline": roofline}
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline()
-    if world == 1 and not args.no_extras:
-        try:
-            del raw, out
-            torch.cuda.empty_cache()
-            line["extras"] = extras(ctx, torch, peaks)
-        except Exception as e:  # extras must never cost the headline line
-            line["extras"] = {"error": repr(e)}
+    if ext is not None:
+        line["extras"] = ext
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -5,7 +5,7 @@
  * functions and two traits.  This header is the `extern "C"` surface a thin `soundkit-cuda-sys`
  * crate binds; each entry point cites the reference interface it replaces
  * (paths relative to the reference repo root).  Argument VALIDATION that produces the reference's
- * exact error strings stays in the host layer above this ABI (rust/ and soundkit_b200/host.py);
+ * exact error strings stays in the host layer above this ABI (rust/soundkit-cuda and soundkit_b200/csrc/host/soundkit_host.hpp);
  * this layer returns negative status codes + sk_last_error().
  *
  * Conventions
@@ -104,6 +104,13 @@ int  sk_ctx_reset_stream(sk_ctx* ctx);
 int  sk_ctx_synchronize(sk_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py reports it as gpu_launches) */
 uint64_t sk_ctx_launch_count(const sk_ctx* ctx);
+/* input bytes per slab of the host-pointer batch pipeline (sk_normalize_batch keeps three slabs of this size plus their
+ * outputs on the device; default 256 MiB).  Smaller slabs bound the device footprint, larger ones amortise launches. */
+int  sk_ctx_set_batch_slab_bytes(sk_ctx* ctx, size_t bytes);
+/* Diagnostic: how many output samples of the general-ratio resampler so far left the tiled fast path and were computed by the
+ * per-output exact path (non-uniform table rows inside a warp tile, ragged tile ends).  Results are identical either way;
+ * the parity tests report and bound the share.  Synchronises the context's stream. */
+int  sk_ctx_resample_fallback_outputs(sk_ctx* ctx, uint64_t* count);
 /* measured FP32 FMA peak of this device in TFLOP/s: register-resident microbenchmarks of the scalar
  * FFMA and the packed sm_100 FFMA2 instruction; _peak returns the larger of the two */
 int  sk_ctx_measure_ffma_peak(sk_ctx* ctx, double* tflops);

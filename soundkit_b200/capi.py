@@ -31,7 +31,7 @@ G726_LEFT, G726_RIGHT = 0, 1
 EXPORTS = (
     "sk_abi_version", "sk_ctx_create", "sk_ctx_destroy", "sk_last_error", "sk_ctx_set_stream", "sk_ctx_reset_stream",
     "sk_ctx_synchronize",
-    "sk_ctx_launch_count", "sk_ctx_measure_ffma_peak", "sk_ctx_measure_ffma_peaks", "sk_ctx_poison_shared_memory",
+    "sk_ctx_launch_count", "sk_ctx_set_batch_slab_bytes", "sk_ctx_resample_fallback_outputs", "sk_ctx_measure_ffma_peak", "sk_ctx_measure_ffma_peaks", "sk_ctx_poison_shared_memory",
     "sk_g711_decode", "sk_g711_decode_dev", "sk_g711_encode", "sk_g711_encode_dev",
     "sk_pcm_flat_convert", "sk_pcm_flat_convert_dev", "sk_flat_op_widths", "sk_dvd_lpcm_unpack", "sk_dvd_lpcm_unpack_dev",
     "sk_deinterleave", "sk_interleave_i16",
@@ -88,6 +88,8 @@ def load():
         "sk_ctx_reset_stream": (i, [vp]),
         "sk_ctx_synchronize": (i, [vp]),
         "sk_ctx_launch_count": (C.c_uint64, [vp]),
+        "sk_ctx_set_batch_slab_bytes": (i, [vp, sz]),
+        "sk_ctx_resample_fallback_outputs": (i, [vp, C.POINTER(C.c_uint64)]),
         "sk_ctx_measure_ffma_peak": (i, [vp, C.POINTER(C.c_double)]),
         "sk_ctx_measure_ffma_peaks": (i, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "sk_ctx_poison_shared_memory": (i, [vp, C.c_uint32]),
@@ -211,6 +213,16 @@ class Context:
     @property
     def launches(self):
         return int(self.L.sk_ctx_launch_count(self.h))
+
+    def set_batch_slab_bytes(self, nbytes):
+        """input bytes per slab of the host-pointer batch pipeline (normalize_batch_host)"""
+        self._ck(self.L.sk_ctx_set_batch_slab_bytes(self.h, nbytes))
+
+    def resample_fallback_outputs(self):
+        """outputs of the general-ratio resampler that took the per-output exact path so far (synchronises)"""
+        v = C.c_uint64()
+        self._ck(self.L.sk_ctx_resample_fallback_outputs(self.h, C.byref(v)))
+        return v.value
 
     def ffma_peak_tflops(self):
         v = C.c_double()

@@ -35,7 +35,12 @@ struct sk_ctx {
     // sinc tables per ratio, built lazily
     std::map<uint64_t, float*> sinc_tables;          // key = (in_rate << 32) | out_rate -> device [256][256]
     std::map<uint64_t, std::vector<float>> sinc_host; // same key -> host copy
-    std::map<std::string, sk_plan*> plans;            // batch plans keyed by rate/frames/semantics
+    std::map<std::string, sk_plan*> plans;            // batch plans keyed by rate/frames/semantics (bounded LRU, sk_resample.cu)
+    uint64_t plan_clock = 0;
+    void* d_res = nullptr;   size_t d_res_cap = 0;     // result planes of sk_normalize_stream (grow-only; no per-call cudaMalloc)
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};     // pinned-stage slot events of sk_h2d / sk_d2h (created once)
+    size_t batch_slab_bytes = (size_t)256 << 20;      // input bytes per slab of the sk_normalize_batch pipeline (sk_ctx_set_batch_slab_bytes)
+    unsigned long long* d_stats = nullptr;            // [0] outputs of the general-ratio resampler that took the per-output exact path
 };
 
 #define SK_FAIL(ctx, code, ...)                                 \
@@ -63,6 +68,7 @@ struct sk_ctx {
 int sk_ensure_host(sk_ctx* ctx, size_t bytes);
 int sk_ensure_dev_in(sk_ctx* ctx, size_t bytes);
 int sk_ensure_dev_out(sk_ctx* ctx, size_t bytes);
+int sk_ensure_stats(sk_ctx* ctx);  // device counters (zeroed on first use)
 // host -> device through the pinned stage (chunked), device -> host likewise; both synchronous wrt host
 int sk_h2d(sk_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int sk_d2h(sk_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);

@@ -41,6 +41,10 @@ extern "C" void sk_ctx_destroy(sk_ctx* ctx) {
     if (ctx->d_in) cudaFree(ctx->d_in);
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_tmp) cudaFree(ctx->d_tmp);
+    if (ctx->d_res) cudaFree(ctx->d_res);
+    if (ctx->d_stats) cudaFree(ctx->d_stats);
+    for (int i = 0; i < 2; i++)
+        if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
     if (ctx->d_tickets) cudaFree(ctx->d_tickets);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -68,6 +72,32 @@ extern "C" int sk_ctx_synchronize(sk_ctx* ctx) {
 
 extern "C" uint64_t sk_ctx_launch_count(const sk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int sk_ctx_set_batch_slab_bytes(sk_ctx* ctx, size_t bytes) {
+    if (!ctx) return SK_E_ARG;
+    if (bytes < ((size_t)1 << 20) || bytes > ((size_t)16 << 30)) SK_FAIL(ctx, SK_E_ARG, "slab size must be between 1 MiB and 16 GiB");
+    ctx->batch_slab_bytes = bytes;
+    return SK_OK;
+}
+
+int sk_ensure_stats(sk_ctx* ctx) {
+    if (ctx->d_stats) return SK_OK;
+    SK_CUDA(ctx, cudaMalloc((void**)&ctx->d_stats, 8 * sizeof(unsigned long long)));
+    SK_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    return SK_OK;
+}
+
+extern "C" int sk_ctx_resample_fallback_outputs(sk_ctx* ctx, uint64_t* count) {
+    if (!ctx || !count) return SK_E_ARG;
+    *count = 0;
+    if (!ctx->d_stats) return SK_OK;
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned long long v = 0;
+    SK_CUDA(ctx, cudaMemcpyAsync(&v, ctx->d_stats, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+    SK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *count = v;
+    return SK_OK;
+}
+
 // ---- staging -------------------------------------------------------------------------------
 int sk_ensure_host(sk_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->h_cap) return SK_OK;
@@ -91,25 +121,33 @@ int sk_ensure_dev_out(sk_ctx* ctx, size_t bytes) { return ensure_dev(ctx, &ctx->
 // Host buffers of the drop-in API are pageable (Rust Vec / slices): stage through pinned memory in
 // 8 MiB pieces so the DMA engine runs at full PCIe rate and the pinned footprint stays bounded.
 static const size_t kStagePiece = 8u << 20;
+// the two slot events live in the context (created once): a small call costs no event create / destroy
+static int stage_events(sk_ctx* ctx) {
+    for (int i = 0; i < 2; i++)
+        if (!ctx->stage_ev[i]) SK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+    return SK_OK;
+}
 int sk_h2d(sk_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
     if (!bytes) return SK_OK;
     int rc = sk_ensure_host(ctx, 2 * kStagePiece);
     if (rc) return rc;
+    if ((rc = stage_events(ctx))) return rc;
     char* stage = (char*)ctx->h_stage;
-    cudaEvent_t ev[2];
-    for (int i = 0; i < 2; i++) SK_CUDA(ctx, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    cudaEvent_t* ev = ctx->stage_ev;
     size_t off = 0; int slot = 0; bool used[2] = {false, false};
-    while (off < bytes) {
+    cudaError_t e = cudaSuccess;
+    while (off < bytes && e == cudaSuccess) {
         size_t n = bytes - off < kStagePiece ? bytes - off : kStagePiece;
-        if (used[slot]) cudaEventSynchronize(ev[slot]);
+        if (used[slot]) e = cudaEventSynchronize(ev[slot]);
+        if (e != cudaSuccess) break;
         memcpy(stage + slot * kStagePiece, (const char*)src_host + off, n);
-        cudaMemcpyAsync((char*)dst_dev + off, stage + slot * kStagePiece, n, cudaMemcpyHostToDevice, ctx->stream);
-        cudaEventRecord(ev[slot], ctx->stream);
+        e = cudaMemcpyAsync((char*)dst_dev + off, stage + slot * kStagePiece, n, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[slot], ctx->stream);
         used[slot] = true;
         off += n; slot ^= 1;
     }
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < 2; i++) cudaEventDestroy(ev[i]);
+    const cudaError_t es = cudaStreamSynchronize(ctx->stream);  // the stage must be idle when this returns, error or not
+    if (e == cudaSuccess) e = es;
     if (e != cudaSuccess) SK_FAIL(ctx, SK_E_CUDA, "h2d copy failed: %s", cudaGetErrorString(e));
     return SK_OK;
 }
@@ -117,28 +155,30 @@ int sk_d2h(sk_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
     if (!bytes) return SK_OK;
     int rc = sk_ensure_host(ctx, 2 * kStagePiece);
     if (rc) return rc;
+    if ((rc = stage_events(ctx))) return rc;
     char* stage = (char*)ctx->h_stage;
+    cudaEvent_t* ev = ctx->stage_ev;
     size_t off = 0; int slot = 0;
     size_t pend_off[2] = {0, 0}, pend_n[2] = {0, 0};
-    cudaEvent_t ev[2];
-    for (int i = 0; i < 2; i++) SK_CUDA(ctx, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
-    while (off < bytes || pend_n[0] || pend_n[1]) {
+    cudaError_t e = cudaSuccess;
+    while ((off < bytes || pend_n[0] || pend_n[1]) && e == cudaSuccess) {
         if (pend_n[slot]) {
-            cudaEventSynchronize(ev[slot]);
+            e = cudaEventSynchronize(ev[slot]);
+            if (e != cudaSuccess) break;
             memcpy((char*)dst_host + pend_off[slot], stage + slot * kStagePiece, pend_n[slot]);
             pend_n[slot] = 0;
         }
         if (off < bytes) {
             size_t n = bytes - off < kStagePiece ? bytes - off : kStagePiece;
-            cudaMemcpyAsync(stage + slot * kStagePiece, (const char*)src_dev + off, n, cudaMemcpyDeviceToHost, ctx->stream);
-            cudaEventRecord(ev[slot], ctx->stream);
+            e = cudaMemcpyAsync(stage + slot * kStagePiece, (const char*)src_dev + off, n, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaEventRecord(ev[slot], ctx->stream);
             pend_off[slot] = off; pend_n[slot] = n;
             off += n;
         }
         slot ^= 1;
     }
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < 2; i++) cudaEventDestroy(ev[i]);
+    const cudaError_t es = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = es;
     if (e != cudaSuccess) SK_FAIL(ctx, SK_E_CUDA, "d2h copy failed: %s", cudaGetErrorString(e));
     return SK_OK;
 }

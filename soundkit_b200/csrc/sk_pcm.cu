@@ -677,10 +677,6 @@ extern "C" int sk_planar_f32_to_pcm_dev(sk_ctx* ctx, const float* planar, size_t
     return SK_OK;
 }
 
-int sk_planar_f32_to_pcm_dev_impl(sk_ctx* ctx, const float* planar, size_t frames, int channels, int bits, int fmt, uint8_t* out) {
-    return sk_planar_f32_to_pcm_dev(ctx, planar, frames, channels, bits, fmt, out);
-}
-
 extern "C" int sk_planar_f32_to_pcm(sk_ctx* ctx, const float* planar, size_t frames, int channels, int bits, int fmt, uint8_t* out) {
     if (!ctx) return SK_E_ARG;
     if (channels <= 0 || channels > 255) SK_FAIL(ctx, SK_E_ARG, "Channel count must be > 0");
@@ -708,8 +704,11 @@ extern "C" int sk_pcm_narrow_i16(sk_ctx* ctx, const uint8_t* in, size_t bytes, i
 }
 
 // ---- mono mixdown ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPcmThreads) mixdown_kernel(const float* __restrict__ planar, size_t plane, size_t frames, int channels, int mode,
-                                                               float scale, float* __restrict__ out, int vec) {
+// blockIdx.y = stream: a whole batch is one launch (in_stream / out_stream = floats between consecutive streams)
+__global__ void __launch_bounds__(kPcmThreads) mixdown_kernel(const float* __restrict__ planar_all, size_t in_stream, size_t plane, size_t frames,
+                                                               int channels, int mode, float scale, float* __restrict__ out_all, size_t out_stream, int vec) {
+    const float* planar = planar_all + (size_t)blockIdx.y * in_stream;
+    float* out = out_all + (size_t)blockIdx.y * out_stream;
     const size_t stride = (size_t)gridDim.x * kPcmThreads;
     if (vec) {
         const size_t n4 = frames / 4;
@@ -739,21 +738,74 @@ __global__ void __launch_bounds__(kPcmThreads) mixdown_kernel(const float* __res
     }
 }
 
-int sk_mixdown_strided_dev(sk_ctx* ctx, const float* planar, size_t plane_stride, size_t frames, int channels, int mix_mode, float* out) {
+// n_streams planar blocks -> n_streams mono rows in one launch (the unfused arms of sk_normalize_batch_dev)
+int sk_mixdown_batch_dev(sk_ctx* ctx, const float* planar, size_t in_stream_stride, size_t plane_stride, size_t frames, int channels, int mix_mode,
+                         float* out, size_t out_stream_stride, size_t n_streams) {
     if (!ctx) return SK_E_ARG;
     if (channels <= 0 || channels > 255) SK_FAIL(ctx, SK_E_ARG, "Channel count must be > 0");
     if (mix_mode != SK_MIX_SUM_THEN_SCALE && mix_mode != SK_MIX_SCALE_THEN_SUM) SK_FAIL(ctx, SK_E_ARG, "unknown mix mode %d", mix_mode);
-    if (!frames) return SK_OK;
+    if (!frames || !n_streams) return SK_OK;
     if (!planar || !out) SK_FAIL(ctx, SK_E_ARG, "null buffer");
     SK_CUDA(ctx, cudaSetDevice(ctx->device));
     if (channels == 1 && mix_mode == SK_MIX_SUM_THEN_SCALE) {  // mixdown_to_mono_f32 returns channels[0].clone()
-        SK_CUDA(ctx, cudaMemcpyAsync(out, planar, frames * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+        SK_CUDA(ctx, cudaMemcpy2DAsync(out, out_stream_stride * sizeof(float), planar, in_stream_stride * sizeof(float), frames * sizeof(float),
+                                       n_streams, cudaMemcpyDeviceToDevice, ctx->stream));
         return SK_OK;
     }
-    float scale = 1.0f / (float)channels;
-    int vec = aligned16(planar) && aligned16(out) && plane_stride % 4 == 0;
-    mixdown_kernel<<<grid_for(ctx, frames / 4 + 1, kPcmThreads), kPcmThreads, 0, ctx->stream>>>(planar, plane_stride, frames, channels, mix_mode, scale, out, vec);
-    SK_LAUNCH_CHECK(ctx);
+    const float scale = 1.0f / (float)channels;
+    const int vec = aligned16(planar) && aligned16(out) && plane_stride % 4 == 0 && (n_streams == 1 || (in_stream_stride % 4 == 0 && out_stream_stride % 4 == 0));
+    const unsigned gx = (unsigned)std::min<int>(grid_for(ctx, frames / 4 + 1, kPcmThreads), 1 << 20);
+    for (size_t s0 = 0; s0 < n_streams; s0 += 65535) {
+        const size_t ns = std::min<size_t>(65535, n_streams - s0);
+        mixdown_kernel<<<dim3(gx, (unsigned)ns), kPcmThreads, 0, ctx->stream>>>(planar + s0 * in_stream_stride, in_stream_stride, plane_stride, frames, channels,
+                                                                               mix_mode, scale, out + s0 * out_stream_stride, out_stream_stride, vec);
+        SK_LAUNCH_CHECK(ctx);
+    }
+    return SK_OK;
+}
+
+int sk_mixdown_strided_dev(sk_ctx* ctx, const float* planar, size_t plane_stride, size_t frames, int channels, int mix_mode, float* out) {
+    return sk_mixdown_batch_dev(ctx, planar, 0, plane_stride, frames, channels, mix_mode, out, 0, 1);
+}
+
+// mono f32 rows -> bytes as f32_channels_to_bytes writes one channel (soundkit-decoder/src/lib.rs:3619-3683), a whole batch per
+// launch: blockIdx.y = stream, 4 samples per thread where the row pointers allow 128-bit loads
+__global__ void __launch_bounds__(256) quantize_mono_batch_kernel(const float* __restrict__ in_all, size_t in_stream, size_t n, int bits, int isfloat,
+                                                                   uint8_t* __restrict__ out_all, size_t out_stream_bytes, int vec) {
+    const float* in = in_all + (size_t)blockIdx.y * in_stream;
+    uint8_t* out = out_all + (size_t)blockIdx.y * out_stream_bytes;
+    const int ob = bits >> 3;
+    const size_t stride = (size_t)gridDim.x * 256;
+    auto q1 = [&](float x) -> uint32_t {
+        return isfloat ? quantize<32, true>(x) : (bits == 16 ? quantize<16, false>(x) : (bits == 24 ? quantize<24, false>(x) : quantize<32, false>(x)));
+    };
+    const size_t n4 = vec ? n / 4 : 0;
+    for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < n4; g += stride) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(in) + g);
+        const uint32_t q[4] = {q1(v.x), q1(v.y), q1(v.z), q1(v.w)};
+        if (ob == 2) *reinterpret_cast<uint2*>(out + g * 8) = make_uint2(q[0] | (q[1] << 16), q[2] | (q[3] << 16));
+        else if (ob == 3) {
+            uint32_t* w = reinterpret_cast<uint32_t*>(out + g * 12);
+            w[0] = q[0] | (q[1] << 24); w[1] = (q[1] >> 8) | (q[2] << 16); w[2] = (q[2] >> 16) | (q[3] << 8);
+        } else *reinterpret_cast<uint4*>(out + g * 16) = make_uint4(q[0], q[1], q[2], q[3]);
+    }
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+        const uint32_t r = q1(in[i]);
+        for (int b = 0; b < ob; b++) out[i * ob + b] = (uint8_t)(r >> (8 * b));
+    }
+}
+
+int sk_quantize_mono_batch_dev(sk_ctx* ctx, const float* in, size_t in_stream_stride, size_t n, int bits, int fmt, uint8_t* out, size_t out_stream_bytes,
+                               size_t n_streams) {
+    if (!n || !n_streams) return SK_OK;
+    const int vec = aligned16(in) && in_stream_stride % 4 == 0 && ((uintptr_t)out % 16) == 0 && out_stream_bytes % 16 == 0;
+    const unsigned gx = (unsigned)std::min<int>(grid_for(ctx, n / 4 + 1, 256), 1 << 20);
+    for (size_t s0 = 0; s0 < n_streams; s0 += 65535) {
+        const size_t ns = std::min<size_t>(65535, n_streams - s0);
+        quantize_mono_batch_kernel<<<dim3(gx, (unsigned)ns), 256, 0, ctx->stream>>>(in + s0 * in_stream_stride, in_stream_stride, n, bits, fmt == SK_FMT_FLOAT,
+                                                                                    out + s0 * out_stream_bytes, out_stream_bytes, vec);
+        SK_LAUNCH_CHECK(ctx);
+    }
     return SK_OK;
 }
 

@@ -177,14 +177,40 @@ static int finalize_general_plan(sk_ctx* ctx, sk_plan* p, uint32_t in_rate, uint
 }
 
 static bool integer_step_of(uint32_t in_rate, uint32_t out_rate, int* step) {
-    if (in_rate % out_rate) return false;
+    if (!in_rate || !out_rate || in_rate % out_rate) return false;
     uint32_t s = in_rate / out_rate;
     if (s == 2 || s == 3 || s == 4 || s == 6 || s == 12) { *step = (int)s; return true; }
     return false;
 }
 
+// The plan cache is bounded: a general-ratio plan keeps 9 bytes per output frame on the device (0.5 GB for an hour at
+// 16 kHz) and callers with variable-length inputs (one plan per distinct length) would otherwise grow it for the life of
+// the context.  Least-recently-used plans go first, never the one just built; kernels still reading an evicted plan's
+// arrays are drained first.
+static const size_t kPlanCacheMaxEntries = 64;
+static const size_t kPlanCacheMaxBytes = (size_t)768 << 20;
+static size_t plan_dev_bytes(const sk_plan* p) { return p->d_i0 ? p->n_out * 9 : 0; }
+static void evict_plans(sk_ctx* ctx, const sk_plan* keep) {
+    bool drained = false;
+    for (;;) {
+        size_t bytes = 0;
+        for (auto& kv : ctx->plans) bytes += plan_dev_bytes(kv.second);
+        if (ctx->plans.size() <= kPlanCacheMaxEntries && bytes <= kPlanCacheMaxBytes) return;
+        auto victim = ctx->plans.end();
+        for (auto it = ctx->plans.begin(); it != ctx->plans.end(); ++it)
+            if (it->second != keep && (victim == ctx->plans.end() || it->second->last_use < victim->second->last_use)) victim = it;
+        if (victim == ctx->plans.end()) return;  // only the plan in use is left
+        if (!drained && victim->second->d_i0) { cudaStreamSynchronize(ctx->stream); drained = true; }
+        free_plan(victim->second);
+        ctx->plans.erase(victim);
+    }
+}
+
 // whole-stream plan for the batch entry points
 static int build_stream_plan(sk_ctx* ctx, uint32_t in_rate, uint32_t out_rate, size_t frames, int semantics, sk_plan** out) {
+    // every entry point funnels through here: no caller can reach the ratio arithmetic with a zero rate
+    // (downsample_audio: "sampling_rate must be > 0", audio_pipeline.rs:449; apply_output_options: "Output sample rate must be > 0")
+    if (!in_rate || !out_rate) SK_FAIL(ctx, SK_E_ARG, "sampling_rate must be > 0");
     // frame and output indices travel as int32 inside the kernels (12.4 hours at 48 kHz): refuse longer streams loudly
     if (frames > 0x7fff0000ull || (double)frames * (double)out_rate / (double)in_rate > 2.0e9)
         SK_FAIL(ctx, SK_E_ARG, "stream of %zu frames is too long for one call (limit 2^31 frames in and out); split it", frames);
@@ -192,7 +218,7 @@ static int build_stream_plan(sk_ctx* ctx, uint32_t in_rate, uint32_t out_rate, s
     char key[96];
     snprintf(key, sizeof(key), "%u:%u:%zu:%d", in_rate, out_rate, frames, semantics);
     auto it = ctx->plans.find(key);
-    if (it != ctx->plans.end()) { *out = it->second; return SK_OK; }
+    if (it != ctx->plans.end()) { it->second->last_use = ++ctx->plan_clock; *out = it->second; return SK_OK; }
     const double ratio = (double)out_rate / (double)in_rate;
     sk_plan* p = new sk_plan();
     int step = 0;
@@ -226,8 +252,10 @@ static int build_stream_plan(sk_ctx* ctx, uint32_t in_rate, uint32_t out_rate, s
         int rc = finalize_general_plan(ctx, p, in_rate, out_rate, w);
         if (rc) { free_plan(p); return rc; }
     }
+    p->last_use = ++ctx->plan_clock;
     ctx->plans[key] = p;
     *out = p;
+    evict_plans(ctx, p);
     return SK_OK;
 }
 
@@ -375,7 +403,7 @@ template <int NT>  // 256 threads x 2 CTAs/SM when two windows fit an SM, else 5
 __global__ void __launch_bounds__(NT, 512 / NT)
 resample_gen2_kernel(const __grid_constant__ SrcDesc src, const __grid_constant__ OutDesc dst, const int32_t* __restrict__ pi0,
                      const uint8_t* __restrict__ ps0, const float* __restrict__ pfrac, const float* __restrict__ table, int period,
-                     int lanes_per_stream) {
+                     int lanes_per_stream, unsigned long long* __restrict__ stats) {
     extern __shared__ __align__(16) float win_all[];
     float* rows_smem = win_all;                                   // [8 warps][4 rows][256]
     float* win = win_all + (NT / 32) * 4 * SINC_LEN;
@@ -436,6 +464,8 @@ resample_gen2_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
             }
             if (all4) { op[n[0][0]] = y[0][0]; op[n[1][0]] = y[1][0]; op[n[0][1]] = y[0][1]; op[n[1][1]] = y[1][1]; }
         } else {
+            const int nfb = (int)ok[0][0] + (int)ok[0][1] + (int)ok[1][0] + (int)ok[1][1];
+            if (nfb) atomicAdd(stats, (unsigned long long)nfb);
 #pragma unroll
             for (int a = 0; a < 2; a++)
 #pragma unroll
@@ -475,6 +505,7 @@ static int src_desc_for(sk_ctx* ctx, SrcDesc* s, const void* in, size_t in_strid
 
 static int launch_gen2(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, const float* d_table, size_t n_streams,
                        int lanes_per_stream) {
+    if (int rc = sk_ensure_stats(ctx)) return rc;
     const int smem256 = (plan->max_window2 + 8 + (256 / 32) * 4 * SINC_LEN) * (int)sizeof(float);
     const bool two_ctas = 2 * (smem256 + 1024) <= 227 * 1024;
     const int nt = two_ctas ? 256 : 512;
@@ -492,8 +523,8 @@ static int launch_gen2(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, cons
         s2.base += (long long)stream0 * src.stream_stride;
         d2.base += (long long)stream0 * dst.stream_stride;
         dim3 grid((unsigned)tiles, (unsigned)nl);
-        if (two_ctas) resample_gen2_kernel<256><<<grid, 256, smem, ctx->stream>>>(s2, d2, plan->d_i0, plan->d_s0, plan->d_frac, d_table, plan->period2, lanes_per_stream);
-        else resample_gen2_kernel<512><<<grid, 512, smem, ctx->stream>>>(s2, d2, plan->d_i0, plan->d_s0, plan->d_frac, d_table, plan->period2, lanes_per_stream);
+        if (two_ctas) resample_gen2_kernel<256><<<grid, 256, smem, ctx->stream>>>(s2, d2, plan->d_i0, plan->d_s0, plan->d_frac, d_table, plan->period2, lanes_per_stream, ctx->d_stats);
+        else resample_gen2_kernel<512><<<grid, 512, smem, ctx->stream>>>(s2, d2, plan->d_i0, plan->d_s0, plan->d_frac, d_table, plan->period2, lanes_per_stream, ctx->d_stats);
         SK_LAUNCH_CHECK(ctx);
     }
     return SK_OK;
@@ -563,7 +594,11 @@ extern "C" int sk_normalize_batch_plan(sk_ctx* ctx, uint32_t in_rate, uint32_t o
     return SK_OK;
 }
 
-int sk_mixdown_strided_dev(sk_ctx* ctx, const float* planar, size_t plane_stride, size_t frames, int channels, int mix_mode, float* out);  // sk_pcm.cu
+// sk_pcm.cu: whole-batch mixdown / mono quantiser (blockIdx.y = stream)
+int sk_mixdown_batch_dev(sk_ctx* ctx, const float* planar, size_t in_stream_stride, size_t plane_stride, size_t frames, int channels, int mix_mode,
+                         float* out, size_t out_stream_stride, size_t n_streams);
+int sk_quantize_mono_batch_dev(sk_ctx* ctx, const float* in, size_t in_stream_stride, size_t n, int bits, int fmt, uint8_t* out, size_t out_stream_bytes,
+                               size_t n_streams);
 
 extern "C" int sk_normalize_batch_dev(sk_ctx* ctx, const sk_batch_desc* d) {
     if (!ctx || !d) return SK_E_ARG;
@@ -597,10 +632,9 @@ extern "C" int sk_normalize_batch_dev(sk_ctx* ctx, const sk_batch_desc* d) {
             OutDesc d2; d2.base = scratch; d2.stream_stride = (long long)per_stream; d2.lane_stride = (long long)plane; d2.mix = SK_MIX_NONE;
             d2.n_out = (long long)plan->n_out;
             if ((rc = run_plan(ctx, s2, d2, plan, d->in_rate, d->out_rate, ns, d->channels))) return rc;
-            for (size_t s = 0; s < ns; s++) {
-                if ((rc = sk_mixdown_strided_dev(ctx, scratch + s * per_stream, plane, plan->n_out, d->channels, mix, d->out + (s0 + s) * d->out_stride)))
-                    return rc;
-            }
+            // one launch mixes the whole slab (blockIdx.y = stream)
+            if ((rc = sk_mixdown_batch_dev(ctx, scratch, per_stream, plane, plan->n_out, d->channels, mix, d->out + s0 * d->out_stride, d->out_stride, ns)))
+                return rc;
         }
         return SK_OK;
     }
@@ -611,7 +645,6 @@ extern "C" int sk_normalize_batch_dev(sk_ctx* ctx, const sk_batch_desc* d) {
 // apply_output_options with bytes out for a whole batch (soundkit-decoder/src/lib.rs:3324-3456, rate-changing arm down to
 // one channel): convert -> resample -> downmix -> f32_channels_to_bytes.  Two-channel integer-ratio sources leave the fused
 // kernel as bytes directly; every other combination goes through an f32 scratch and the interleave kernel.
-int sk_planar_f32_to_pcm_dev_impl(sk_ctx* ctx, const float* planar, size_t frames, int channels, int bits, int fmt, uint8_t* out);
 extern "C" int sk_normalize_batch_pcm_dev(sk_ctx* ctx, const sk_batch_desc* d, int out_bits, int out_fmt, void* out, size_t out_stride_bytes) {
     if (!ctx || !d) return SK_E_ARG;
     if (out_fmt == SK_FMT_FLOAT && out_bits != 32) SK_FAIL(ctx, SK_E_ARG, "PCMFloat output requires 32-bit samples");
@@ -651,8 +684,7 @@ extern "C" int sk_normalize_batch_pcm_dev(sk_ctx* ctx, const sk_batch_desc* d, i
         sk_batch_desc dd = *d;
         dd.in = (const char*)d->in + s0 * d->in_stride; dd.n_streams = ns; dd.out = mono; dd.out_stride = plane; dd.out_stride_ch = plane;
         if ((rc = sk_normalize_batch_dev(ctx, &dd))) return rc;
-        for (size_t s = 0; s < ns; s++)
-            if ((rc = sk_planar_f32_to_pcm_dev_impl(ctx, mono + s * plane, plan->n_out, 1, out_bits, out_fmt, (uint8_t*)out + (s0 + s) * out_stride_bytes))) return rc;
+        if ((rc = sk_quantize_mono_batch_dev(ctx, mono, plane, plan->n_out, out_bits, out_fmt, (uint8_t*)out + s0 * out_stride_bytes, out_stride_bytes, ns))) return rc;
     }
     return SK_OK;
 }
@@ -681,8 +713,15 @@ extern "C" int sk_normalize_stream(sk_ctx* ctx, const uint8_t* in, size_t bytes,
     const size_t in_bytes = frames * B * channels;
     if ((rc = sk_ensure_dev_in(ctx, in_bytes + 16))) return rc;
     if ((rc = sk_h2d(ctx, ctx->d_in, in, in_bytes))) return rc;
-    float* d_res = nullptr;
-    SK_CUDA(ctx, cudaMalloc((void**)&d_res, plane * planes * sizeof(float)));
+    // result planes in the context's grow-only d_res (d_out may serve as the mix scratch of the unfused arms): this is the
+    // call downsample_audio / the decoder's per-AudioData stage bind to, so it must not pay cudaMalloc + cudaFree per call
+    if (ctx->d_res_cap < plane * planes * sizeof(float)) {
+        if (ctx->d_res) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->d_res); ctx->d_res = nullptr; ctx->d_res_cap = 0; }
+        const size_t cap = sk_round_up(plane * planes * sizeof(float), (size_t)1 << 20);
+        if (cudaMalloc(&ctx->d_res, cap) != cudaSuccess) SK_FAIL(ctx, SK_E_ALLOC, "device alloc of %zu bytes failed", cap);
+        ctx->d_res_cap = cap;
+    }
+    float* d_res = (float*)ctx->d_res;
     sk_batch_desc d;
     memset(&d, 0, sizeof(d));
     d.in = ctx->d_in; d.in_stride = in_bytes; d.n_streams = 1; d.frames = frames; d.bits = bits; d.fmt = fmt; d.big_endian = big_endian;
@@ -690,28 +729,34 @@ extern "C" int sk_normalize_stream(sk_ctx* ctx, const uint8_t* in, size_t bytes,
     d.out = d_res; d.out_stride = plane * planes; d.out_stride_ch = plane;
     rc = sk_normalize_batch_dev(ctx, &d);
     for (int c = 0; c < planes && !rc; c++) rc = sk_d2h(ctx, out + (size_t)c * out_cap_per_plane, d_res + (size_t)c * plane, n * sizeof(float));
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_res);
     return rc;
 }
 
 // Host-pointer batch: the same fused chain for n_streams host-resident streams, pipelined in slabs —
 // H2D of slab i+1 and D2H of slab i-1 overlap the kernel of slab i on three streams.  `in` / `out`
 // of the descriptor are HOST pointers here (pinned memory gives full PCIe rate; pageable works).
+constexpr int kPipeDepth = 3;  // slabs in flight: H2D of slab i+1, kernel of slab i and D2H of slab i-1 overlap with one slab of slack
 struct BatchPipe {
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-    void* d_in[2] = {nullptr, nullptr}; size_t in_cap = 0;
-    float* d_out[2] = {nullptr, nullptr}; size_t out_cap = 0;
+    cudaEvent_t ev_in[kPipeDepth] = {}, ev_k[kPipeDepth] = {}, ev_out[kPipeDepth] = {};
+    void* d_in[kPipeDepth] = {}; size_t in_cap = 0;
+    float* d_out[kPipeDepth] = {}; size_t out_cap = 0;
 };
 // one per context, owned by the context (contexts are thread-confined; no process-wide state, so pipelines on different
 // threads never meet)
+static void pipe_free_slabs(BatchPipe& p) {
+    for (int b = 0; b < kPipeDepth; b++) {
+        if (p.d_in[b]) cudaFree(p.d_in[b]);
+        if (p.d_out[b]) cudaFree(p.d_out[b]);
+        p.d_in[b] = nullptr; p.d_out[b] = nullptr;
+    }
+    p.in_cap = 0; p.out_cap = 0;
+}
 void sk_resample_free_pipe(sk_ctx* ctx) {
     if (!ctx->batch_pipe) return;
     BatchPipe& p = *static_cast<BatchPipe*>(ctx->batch_pipe);
-    for (int b = 0; b < 2; b++) {
-        if (p.d_in[b]) cudaFree(p.d_in[b]);
-        if (p.d_out[b]) cudaFree(p.d_out[b]);
+    pipe_free_slabs(p);
+    for (int b = 0; b < kPipeDepth; b++) {
         if (p.ev_in[b]) cudaEventDestroy(p.ev_in[b]);
         if (p.ev_k[b]) cudaEventDestroy(p.ev_k[b]);
         if (p.ev_out[b]) cudaEventDestroy(p.ev_out[b]);
@@ -726,6 +771,8 @@ extern "C" int sk_normalize_batch(sk_ctx* ctx, const sk_batch_desc* d) {
     if (!ctx || !d) return SK_E_ARG;
     if (d->channels <= 0 || d->channels > 255) SK_FAIL(ctx, SK_E_ARG, "Channel count must be > 0");
     if (d->bits != 16 && d->bits != 24 && d->bits != 32) SK_FAIL(ctx, SK_E_ARG, "Unsupported bits_per_sample: %d", d->bits);
+    if (!d->in_rate || !d->out_rate) SK_FAIL(ctx, SK_E_ARG, "sampling_rate must be > 0");
+    if (d->mix_mode < SK_MIX_NONE || d->mix_mode > SK_MIX_SCALE_THEN_SUM) SK_FAIL(ctx, SK_E_ARG, "unknown mix mode %d", d->mix_mode);
     if (!d->n_streams) return SK_OK;
     if (!d->in || !d->out) SK_FAIL(ctx, SK_E_ARG, "null buffer");
     SK_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -735,50 +782,55 @@ extern "C" int sk_normalize_batch(sk_ctx* ctx, const sk_batch_desc* d) {
     if (!plan->n_out) return SK_OK;
     const int mix = d->channels == 1 ? SK_MIX_NONE : d->mix_mode;
     const int planes = mix == SK_MIX_NONE ? d->channels : 1;
-    const size_t in_bytes = sk_round_up(d->frames * (size_t)(d->bits / 8) * d->channels, 16);
+    const size_t raw_bytes = d->frames * (size_t)(d->bits / 8) * d->channels;
+    const size_t in_bytes = sk_round_up(raw_bytes, 16);
     const size_t plane = sk_round_up(plan->n_out, 4);
     const size_t out_floats = plane * planes;
-    // slab: as many streams as fit ~256 MiB of input (at least one)
-    size_t slab = std::max<size_t>(1, ((size_t)256 << 20) / std::max<size_t>(1, in_bytes));
+    // slab: as many streams as fit the configured slab size (default 256 MiB of input; at least one)
+    size_t slab = std::max<size_t>(1, ctx->batch_slab_bytes / std::max<size_t>(1, in_bytes));
     slab = std::min(slab, d->n_streams);
     if (!ctx->batch_pipe) ctx->batch_pipe = new BatchPipe();
     BatchPipe& p = *static_cast<BatchPipe*>(ctx->batch_pipe);
-    if (!p.s_in) {
-        SK_CUDA(ctx, cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking));
-        SK_CUDA(ctx, cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking));
-        for (int b = 0; b < 2; b++) {
-            SK_CUDA(ctx, cudaEventCreateWithFlags(&p.ev_in[b], cudaEventDisableTiming));
-            SK_CUDA(ctx, cudaEventCreateWithFlags(&p.ev_k[b], cudaEventDisableTiming));
-            SK_CUDA(ctx, cudaEventCreateWithFlags(&p.ev_out[b], cudaEventDisableTiming));
-        }
+    if (!p.s_in) SK_CUDA(ctx, cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking));
+    if (!p.s_out) SK_CUDA(ctx, cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking));
+    for (int b = 0; b < kPipeDepth; b++) {
+        if (!p.ev_in[b]) SK_CUDA(ctx, cudaEventCreateWithFlags(&p.ev_in[b], cudaEventDisableTiming));
+        if (!p.ev_k[b]) SK_CUDA(ctx, cudaEventCreateWithFlags(&p.ev_k[b], cudaEventDisableTiming));
+        if (!p.ev_out[b]) SK_CUDA(ctx, cudaEventCreateWithFlags(&p.ev_out[b], cudaEventDisableTiming));
     }
     if (p.in_cap < slab * in_bytes || p.out_cap < slab * out_floats) {
+        // grow: the capacities are committed only after every allocation succeeded, so a failed call leaves an empty
+        // (not a half-allocated) pipeline behind
         cudaDeviceSynchronize();
-        for (int b = 0; b < 2; b++) {
-            if (p.d_in[b]) cudaFree(p.d_in[b]);
-            if (p.d_out[b]) cudaFree(p.d_out[b]);
-            p.d_in[b] = nullptr; p.d_out[b] = nullptr;
+        const size_t want_in = std::max(p.in_cap, slab * in_bytes), want_out = std::max(p.out_cap, slab * out_floats);
+        pipe_free_slabs(p);
+        for (int b = 0; b < kPipeDepth; b++) {
+            if (cudaMalloc(&p.d_in[b], want_in) != cudaSuccess || cudaMalloc((void**)&p.d_out[b], want_out * sizeof(float)) != cudaSuccess) {
+                cudaGetLastError();
+                pipe_free_slabs(p);
+                SK_FAIL(ctx, SK_E_ALLOC, "device allocation of the batch pipeline failed (%d x (%zu + %zu) bytes)", kPipeDepth, want_in,
+                        want_out * sizeof(float));
+            }
         }
-        p.in_cap = slab * in_bytes; p.out_cap = slab * out_floats;
-        for (int b = 0; b < 2; b++) {
-            SK_CUDA(ctx, cudaMalloc(&p.d_in[b], p.in_cap));
-            SK_CUDA(ctx, cudaMalloc((void**)&p.d_out[b], p.out_cap * sizeof(float)));
-        }
+        p.in_cap = want_in; p.out_cap = want_out;
     }
-    const size_t raw_bytes = d->frames * (size_t)(d->bits / 8) * d->channels;
+    // a stream's rows are copied with one call when both sides are dense (the common case), else plane by plane
+    const bool out_dense = planes == 1 || d->out_stride_ch == plan->n_out;
     // the slab loop; whatever it returns, no copy may still be reading d->in or writing d->out when this call returns
     auto pump = [&]() -> int {
         size_t islab = 0;
         for (size_t s0 = 0; s0 < d->n_streams; s0 += slab, islab++) {
-            const int b = (int)(islab & 1);
+            const int b = (int)(islab % kPipeDepth);
             const size_t ns = std::min(slab, d->n_streams - s0);
-            if (islab >= 2) {
-                SK_CUDA(ctx, cudaStreamWaitEvent(p.s_in, p.ev_k[b], 0));        // kernel of slab-2 finished reading d_in[b]
-                SK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p.ev_out[b], 0)); // D2H of slab-2 finished reading d_out[b]
+            if (islab >= (size_t)kPipeDepth) {
+                SK_CUDA(ctx, cudaStreamWaitEvent(p.s_in, p.ev_k[b], 0));        // the kernel that last read d_in[b] has finished
+                SK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p.ev_out[b], 0)); // the D2H that last read d_out[b] has finished
             }
-            for (size_t s = 0; s < ns; s++)
-                SK_CUDA(ctx, cudaMemcpyAsync((char*)p.d_in[b] + s * in_bytes, (const char*)d->in + (s0 + s) * d->in_stride, raw_bytes,
-                                             cudaMemcpyHostToDevice, p.s_in));
+            if (d->in_stride == raw_bytes && in_bytes == raw_bytes)
+                SK_CUDA(ctx, cudaMemcpyAsync(p.d_in[b], (const char*)d->in + s0 * d->in_stride, ns * raw_bytes, cudaMemcpyHostToDevice, p.s_in));
+            else
+                SK_CUDA(ctx, cudaMemcpy2DAsync(p.d_in[b], in_bytes, (const char*)d->in + s0 * d->in_stride, d->in_stride, raw_bytes, ns,
+                                               cudaMemcpyHostToDevice, p.s_in));
             SK_CUDA(ctx, cudaEventRecord(p.ev_in[b], p.s_in));
             SK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p.ev_in[b], 0));
             sk_batch_desc dd = *d;
@@ -787,10 +839,14 @@ extern "C" int sk_normalize_batch(sk_ctx* ctx, const sk_batch_desc* d) {
             if (int rc2 = sk_normalize_batch_dev(ctx, &dd)) return rc2;
             SK_CUDA(ctx, cudaEventRecord(p.ev_k[b], ctx->stream));
             SK_CUDA(ctx, cudaStreamWaitEvent(p.s_out, p.ev_k[b], 0));
-            for (size_t s = 0; s < ns; s++)
-                for (int c = 0; c < planes; c++)
-                    SK_CUDA(ctx, cudaMemcpyAsync(d->out + (s0 + s) * d->out_stride + (size_t)c * d->out_stride_ch, p.d_out[b] + s * out_floats + (size_t)c * plane,
-                                                 plan->n_out * sizeof(float), cudaMemcpyDeviceToHost, p.s_out));
+            if (out_dense && planes == 1) {
+                SK_CUDA(ctx, cudaMemcpy2DAsync(d->out + s0 * d->out_stride, d->out_stride * sizeof(float), p.d_out[b], out_floats * sizeof(float),
+                                               plan->n_out * sizeof(float), ns, cudaMemcpyDeviceToHost, p.s_out));
+            } else {
+                for (size_t s = 0; s < ns; s++)
+                    SK_CUDA(ctx, cudaMemcpy2DAsync(d->out + (s0 + s) * d->out_stride, d->out_stride_ch * sizeof(float), p.d_out[b] + s * out_floats,
+                                                   plane * sizeof(float), plan->n_out * sizeof(float), (size_t)planes, cudaMemcpyDeviceToHost, p.s_out));
+            }
             SK_CUDA(ctx, cudaEventRecord(p.ev_out[b], p.s_out));
         }
         return SK_OK;

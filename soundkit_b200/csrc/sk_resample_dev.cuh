@@ -23,6 +23,7 @@ struct sk_plan {
     int max_window = 0;      // largest input window (frames) any tile of 32*period outputs needs
     int period2 = 0;         // resample_gen2_kernel: outputs per period (a multiple of L), 0 = kernel not applicable
     int max_window2 = 0;     // largest input window of a 64-period tile
+    uint64_t last_use = 0;   // plan cache clock value of the last lookup (least recently used plans are evicted first)
 };
 
 // ================================================================================================
