@@ -1,4 +1,6 @@
 // sk_ctx.cu — context, pinned staging, error plumbing, FFMA peak microbenchmark.
+#include <stdlib.h>
+
 #include "sk_common.cuh"
 
 extern void sk_resample_free_ctx(sk_ctx* ctx);  // sk_resample.cu: frees cached tables / plans
@@ -28,6 +30,7 @@ extern "C" int sk_ctx_create(int device, sk_ctx** out) {
         return SK_E_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    { const char* e = getenv("SK_DISABLE_GEN3"); ctx->disable_gen3 = e && e[0] == '1'; }  // A/B switch for measurements
     *out = ctx;
     return SK_OK;
 }

@@ -103,7 +103,6 @@ static double walk_chunk(double last_index, double ratio, size_t chunk, long lon
 }
 
 
-static uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
 
 static void free_plan(sk_plan* p) {
     if (!p) return;
@@ -128,6 +127,8 @@ static const int kGen2MaxWindow = 40000;  // resample_gen2_kernel: up to 160 KB 
 // finish a general plan from recorded walk arrays: choose the tile period and upload
 static int finalize_general_plan(sk_ctx* ctx, sk_plan* p, uint32_t in_rate, uint32_t out_rate, const WalkOut& w) {
     p->n_out = w.i0.size();
+    p->max_step3 = 0;
+    for (size_t n = 0; n + 3 < p->n_out; n++) p->max_step3 = std::max(p->max_step3, w.i0[n + 3] - w.i0[n]);
     const uint32_t g = gcd_u32(in_rate, out_rate);
     const uint32_t L = out_rate / g;
     auto window_for = [&](int period) {
@@ -557,6 +558,9 @@ static int launch_gen(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const
 SK_DECL_INT(2) SK_DECL_INT(3) SK_DECL_INT(4) SK_DECL_INT(6) SK_DECL_INT(12)
 #undef SK_DECL_INT
 
+int sk_launch_gen3(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, const float* d_table, uint32_t in_rate, uint32_t out_rate,
+                   size_t n_streams, int lanes_per_stream);
+
 static int run_plan(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, uint32_t in_rate, uint32_t out_rate, size_t n_streams,
                     int lanes_per_stream) {
     if (!plan->n_out || !n_streams) return SK_OK;
@@ -574,6 +578,10 @@ static int run_plan(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const s
         SK_FAIL(ctx, SK_E_STATE, "internal: no kernel for integer step %d", plan->step);
     }
     if (dst.mix != SK_MIX_NONE) SK_FAIL(ctx, SK_E_STATE, "internal: general kernel does not mix");
+    if (!ctx->disable_gen3) {  // packed 4 x 2 tile kernel (sk_resample_gen3.cu); 1 = does not apply to this plan / batch
+        rc = sk_launch_gen3(ctx, src, dst, plan, d_table, in_rate, out_rate, n_streams, lanes_per_stream);
+        if (rc <= 0) return rc;
+    }
     if (plan->period2 > 0) return launch_gen2(ctx, src, dst, plan, d_table, n_streams, lanes_per_stream);
     return launch_gen(ctx, src, dst, plan, d_table, n_streams, lanes_per_stream);
 }

@@ -12,6 +12,8 @@
 #define OVERSAMPLING 256
 #define STREAM_CHUNK 4096  // RESAMPLE_CHUNK_SIZE, soundkit-decoder/src/lib.rs:79
 
+static inline uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
+
 struct sk_plan {
     size_t n_out = 0;
     bool integer_step = false;
@@ -23,6 +25,7 @@ struct sk_plan {
     int max_window = 0;      // largest input window (frames) any tile of 32*period outputs needs
     int period2 = 0;         // resample_gen2_kernel: outputs per period (a multiple of L), 0 = kernel not applicable
     int max_window2 = 0;     // largest input window of a 64-period tile
+    int max_step3 = -1;      // general plans: largest i0[n + 3] - i0[n] (window advance inside a group of 4 consecutive outputs)
     uint64_t last_use = 0;   // plan cache clock value of the last lookup (least recently used plans are evicted first)
 };
 

@@ -193,3 +193,40 @@ def test_c5_host_batch_pipeline_matches_oracle(oracle):
             assert np.array_equal(_bits(got[s]), _bits(want)), f"stream {s} differs"
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("rates", [(44100, 48000), (44100, 16000), (48000, 44100), (8000, 16000), (32000, 48000), (22050, 16000)])
+@pytest.mark.parametrize("semantics", ["oneshot", "streaming"])
+def test_general_ratio_many_lanes_bit_exact(oracle, rates, semantics):
+    """>= 64 (stream, channel) lanes in one call: the packed 4 x 2 kernel runs with lane columns only (no period structure, no
+    fallback lanes).  41 stereo streams = 82 lanes: one full block of 64 and one ragged block of 18."""
+    import torch
+    i, o = rates
+    S, frames = 41, 30011
+    rng = np.random.default_rng(i * 7 + o)
+    x = rng.uniform(-0.5, 0.5, (S, frames * 2)).astype(np.float32)
+    sem = capi.SEM_ONESHOT if semantics == "oneshot" else capi.SEM_STREAMING
+    c = capi.Context(0)
+    c.use_torch_stream()
+    try:
+        n_out = c.batch_plan(i, o, frames, sem)
+        xd = torch.from_numpy(x).cuda()
+        od = torch.zeros((S, 2, n_out), dtype=torch.float32, device="cuda")
+        d = capi.BatchDesc(xd.data_ptr(), xd.stride(0) * 4, S, frames, 32, capi.FMT_FLOAT, 0, 2, capi.MODE_A, i, o, sem, capi.MIX_NONE,
+                           od.data_ptr(), 2 * n_out, n_out)
+        f0 = c.resample_fallback_outputs()
+        c.normalize_batch_dev(d)
+        torch.cuda.synchronize()
+        fb = c.resample_fallback_outputs() - f0
+        got = od.cpu().numpy()
+    finally:
+        c.close()
+    for s in (0, 1, 31, 32, 40):
+        if semantics == "oneshot":
+            want = oracle.downsample_audio(x[s].view(np.uint8), 32, 1, 2, i, o)
+        else:
+            st = oracle.Stream(i, o, 2)
+            want = np.concatenate([st.process(np.ascontiguousarray(x[s].reshape(-1, 2).T)), st.flush()], axis=1)
+        assert want.shape == (2, n_out)
+        assert np.array_equal(_bits(got[s]), _bits(want)), f"stream {s} differs"
+    print(f"[many lanes {i}->{o} {semantics}] fallback outputs {fb} of {S * 2 * n_out}")
