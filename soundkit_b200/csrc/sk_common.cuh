@@ -35,6 +35,7 @@ struct sk_ctx {
     // sinc tables per ratio, built lazily
     std::map<uint64_t, float*> sinc_tables;          // key = (in_rate << 32) | out_rate -> device [256][256]
     std::map<uint64_t, std::vector<float>> sinc_host; // same key -> host copy
+    std::map<uint64_t, float*> sinc_tables4;         // same key -> four word-shifted zero-padded copies (sk_resample_gen3.cu)
     std::map<std::string, sk_plan*> plans;            // batch plans keyed by rate/frames/semantics (bounded LRU, sk_resample.cu)
     uint64_t plan_clock = 0;
     void* d_res = nullptr;   size_t d_res_cap = 0;     // result planes of sk_normalize_stream (grow-only; no per-call cudaMalloc)

@@ -79,6 +79,28 @@ static int get_sinc_table(sk_ctx* ctx, uint32_t in_rate, uint32_t out_rate, cons
     return SK_OK;
 }
 
+// four word-shifted, zero-padded copies of the table for 16-byte row staging (layout: sk_resample_gen3.cu)
+int sk_get_shifted_sinc_table(sk_ctx* ctx, uint32_t in_rate, uint32_t out_rate, int pad_l, int row_len, const float** d_table4) {
+    const uint64_t key = rate_key(in_rate, out_rate);
+    auto it = ctx->sinc_tables4.find(key);
+    if (it == ctx->sinc_tables4.end()) {
+        const std::vector<float>* h;
+        int rc = get_sinc_table(ctx, in_rate, out_rate, nullptr, &h);
+        if (rc) return rc;
+        std::vector<float> g((size_t)4 * OVERSAMPLING * row_len, 0.0f);
+        for (int sh = 0; sh < 4; sh++)
+            for (int r = 0; r < OVERSAMPLING; r++)
+                memcpy(&g[((size_t)sh * OVERSAMPLING + r) * row_len + pad_l + sh], h->data() + (size_t)r * SINC_LEN, SINC_LEN * sizeof(float));
+        float* d = nullptr;
+        SK_CUDA(ctx, cudaMalloc((void**)&d, g.size() * sizeof(float)));
+        SK_CUDA(ctx, cudaMemcpyAsync(d, g.data(), g.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        SK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        it = ctx->sinc_tables4.emplace(key, d).first;
+    }
+    *d_table4 = it->second;
+    return SK_OK;
+}
+
 // one rubato chunk: walks idx from last_index, appends (chunk_start + floor(idx), subindex, frac)
 struct WalkOut {
     std::vector<int32_t> i0; std::vector<uint8_t> s0; std::vector<float> frac;
@@ -117,6 +139,8 @@ void sk_resample_free_ctx(sk_ctx* ctx) {
     sk_resample_free_pipe(ctx);
     for (auto& kv : ctx->sinc_tables) cudaFree(kv.second);
     ctx->sinc_tables.clear();
+    for (auto& kv : ctx->sinc_tables4) cudaFree(kv.second);
+    ctx->sinc_tables4.clear();
     for (auto& kv : ctx->plans) free_plan(kv.second);
     ctx->plans.clear();
 }

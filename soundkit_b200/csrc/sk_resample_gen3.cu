@@ -32,9 +32,24 @@
 constexpr int kG3Threads = 256;
 constexpr int kG3Warps = kG3Threads / 32;
 constexpr int kG3A = 4;   // consecutive outputs per thread
-constexpr int kG3B = 2;   // columns per thread
-constexpr int kG3Cols = 32 * kG3B;
+constexpr int kG3B = 4;   // columns per thread (a lane pair q, q + 16 shares them and splits the 8 accumulator lanes)
+constexpr int kG3Cols = 16 * kG3B;
 constexpr int kG3Rows = 2 * kG3A;
+
+// Pre-shifted copies of the sinc table for 16-byte row staging: copy sh (0..3) of row r is h_r delayed by sh words inside a
+// zero-padded row of kG3RowLen words: G[sh][r][i] = h_r[i - sh - kG3PadL] (0 outside [0, 256)).  A row shifted by d words is then
+// the 16-byte aligned slice G[d & 3][r][kG3PadL - (d - (d & 3)) ...] — staged with cp.async, no register round trip.
+constexpr int kG3PadL = 16;                       // largest staged shift (multiple of 4)
+constexpr int kG3RowLen = kG3PadL + 272 + 4;      // 292 words: the longest tap walk (272) starting at any offset <= kG3PadL, + the shift
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 struct Gen3Geom {
     int C;            // lanes (stream x channel) per CTA: power of two <= 64
@@ -44,6 +59,7 @@ struct Gen3Geom {
     int span;         // words staged per lane (window of the whole tile + overshoot of the padded tap walk)
     int tap_stride;   // words per staged (shifted, zero padded) table row; the tap walk covers m in [0, tap_stride)
     int xvec;         // 1: lane windows and group bases are 16-byte aligned -> LDS.128 input loads (P == 1 only)
+    int log2c;        // C == 1 << log2c
     long long n_lanes;
 };
 
@@ -89,14 +105,30 @@ __device__ __forceinline__ float reduce8_rotated(const unsigned long long (&acc)
     return ((rot & 2) != 0) ? __fadd_rn(t1, t0) : __fadd_rn(t0, t1);
 }
 
+__device__ __forceinline__ bool g3_nonfinite(float v) { return (__float_as_uint(v) & 0x7f800000u) == 0x7f800000u; }
+
+// the per-output arithmetic for one output of the lane whose staged window starts at `wc` (frame w0)
+__device__ __forceinline__ float g3_exact(const float* wc, int w0, const int32_t* __restrict__ pi0, const uint8_t* __restrict__ ps0, long long n,
+                                          const float* __restrict__ table, float fr) {
+    const int i0o = pi0[n], s0o = ps0[n];
+    int s1 = s0o + 1, d = 0;
+    if (s1 >= OVERSAMPLING) { s1 -= OVERSAMPLING; d = 1; }  // get_nearest_times_2
+    return gen3_single(wc + (i0o - w0), table + s0o * SINC_LEN, table + s1 * SINC_LEN, d, fr);
+}
+
+// XVEC == 4: lane columns only (P == 1, C == 64): every column shares every plan entry, windows and group bases are 16-byte
+// aligned (LDS.128 input loads).  XVEC == 1: period columns (P > 1): scalar input loads, per-column plan entries checked
+// against the group's reference entries.
 template <int XVEC, int MLEN>
 __global__ void __launch_bounds__(kG3Threads, 1)
 resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant__ OutDesc dst, const __grid_constant__ Gen3Geom geo,
                      const int32_t* __restrict__ pi0, const uint8_t* __restrict__ ps0, const float* __restrict__ pfrac,
-                     const float* __restrict__ table, int lanes_per_stream, unsigned long long* __restrict__ stats) {
+                     const float* __restrict__ table, const float* __restrict__ table4, int lanes_per_stream, unsigned long long* __restrict__ stats) {
     constexpr int A = kG3A, B = kG3B;
+    constexpr bool kLanes = XVEC == 4;
     extern __shared__ __align__(16) float g3_smem[];
-    __shared__ int s_big;
+    __shared__ const uint8_t* s_col_src[kG3Cols];  // per lane of this CTA: first sample of the lane (channel plane for planar sources); null = no lane
+    __shared__ float* s_col_dst[kG3Cols];          // output row of the lane
     constexpr int TS = MLEN;  // words per staged row == length of the (fully unrolled) tap walk
     float* taps_all = g3_smem;                                   // [warps][8 rows][TS]
     float* win = g3_smem + kG3Warps * kG3Rows * TS;              // [C][col_stride]
@@ -105,230 +137,341 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
 
     const long long tile_out = (long long)geo.period * geo.P;
     const long long n0 = (long long)blockIdx.x * tile_out;
-    const long long n1 = min(dst.n_out, n0 + tile_out) - 1;  // last output of this tile
-    const int w0 = pi0[n0] - (XVEC == 4 ? (pi0[n0] & 3) : 0);  // first staged frame (16-byte aligned window origin for LDS.128)
+    const int nt = (int)(min(dst.n_out, n0 + tile_out) - n0);  // outputs of this tile (tile-relative indices 0 .. nt - 1 from here on)
+    pi0 += n0; ps0 += n0; pfrac += n0;
+    const int w0 = pi0[0] - (kLanes ? (pi0[0] & 3) : 0);       // first staged frame (16-byte aligned window origin for LDS.128)
     const long long lane0 = (long long)blockIdx.y * geo.C;
 
     // frames staged per lane: the tile's windows plus the overshoot of the padded tap walk (zero taps meet these words: they must
-    // be staged, finite data)
-    const int count = min(geo.span, pi0[n1] - w0 + SINC_LEN + 2 + (TS - SINC_LEN) + 8);
+    // be staged data)
+    const int count = min(geo.span, pi0[nt - 1] - w0 + SINC_LEN + 2 + (TS - SINC_LEN) + 8);
 
-    // ---- stage the windows: warp w takes lanes w, w + 8, ...; threads walk the frames
-    if (threadIdx.x == 0) s_big = 0;
-    __syncthreads();
-    {
-        bool big = false;
-        for (int c = warp; c < geo.C; c += kG3Warps) {
-            const long long lane = lane0 + c;
-            float* wc = win + (size_t)c * geo.col_stride;
-            if (lane >= geo.n_lanes) {
-                for (int i = q; i < count; i += 32) wc[i] = 0.0f;
-                continue;
-            }
+    // ---- per-lane pointers (the divisions by the channel count happen once per CTA)
+    if (threadIdx.x < geo.C) {
+        const long long lane = lane0 + threadIdx.x;
+        const uint8_t* sp = nullptr; float* dp = nullptr;
+        if (lane < geo.n_lanes) {
             const long long stream = lane / lanes_per_stream;
             const int ch = (int)(lane % lanes_per_stream);
-            if (src.width == 0) {
-                const float* p = reinterpret_cast<const float*>(src.base + stream * src.stream_stride + (long long)ch * src.lane_stride);
-                for (int i = q; i < count; i += 32) {
-                    const long long f = (long long)w0 + i;
-                    const float v = (f >= src.valid_lo && f < src.valid_hi) ? __ldg(p + f + src.origin) : 0.0f;
-                    big |= (__float_as_uint(v) & 0x7f800000u) >= 0x78000000u;
-                    wc[i] = v;
-                }
-            } else {
-                const uint8_t* sbase = src.base + stream * src.stream_stride;
-                for (int i = q; i < count; i += 32) {
-                    const long long f = (long long)w0 + i;
-                    float v = 0.0f;
-                    if (f >= src.valid_lo && f < src.valid_hi) v = decode_sample_bits(load_sample_bits(sbase, f, ch, src), src);
-                    if (src.is_float) big |= (__float_as_uint(v) & 0x7f800000u) >= 0x78000000u;
-                    wc[i] = v;
-                }
-            }
+            sp = src.base + stream * src.stream_stride + (src.width == 0 ? (long long)ch * src.lane_stride : (long long)ch * src.width) +
+                 ((long long)w0 + src.origin) * (src.width == 0 ? 4 : (long long)src.channels * src.width);
+            dp = dst.base + stream * dst.stream_stride + (long long)ch * dst.lane_stride + n0;
         }
-        if (big) s_big = 1;
+        s_col_src[threadIdx.x] = sp; s_col_dst[threadIdx.x] = dp;
     }
     __syncthreads();
-    const bool tile_big = s_big != 0;
 
-    // ---- this thread's two columns: column j = q + 32 b -> (lane c = j % C, period k = j / C)
-    int col_c[B];
-    long long col_n0[B];   // first output of the column's period
-    bool col_ok[B];
-#pragma unroll
-    for (int b = 0; b < B; b++) {
-        const int j = q + 32 * b;
-        col_c[b] = j & (geo.C - 1);
-        col_n0[b] = n0 + (long long)(j / geo.C) * geo.period;
-        col_ok[b] = lane0 + col_c[b] < geo.n_lanes;
-    }
-    const int groups = (geo.period + A - 1) / A;
-    for (int g = warp; g < groups; g += kG3Warps) {
-        const int ph0 = g * A;
-        if (n0 + ph0 > n1) break;  // nothing of this group (or any later one) exists in period 0; later periods start later still
-        // reference plan entries of the group (period 0 of the tile), clamped at ragged ends (clamped entries are masked below)
-        int i0r[A], s0r[A];
-#pragma unroll
-        for (int a = 0; a < A; a++) {
-            long long nr = n0 + min(ph0 + a, geo.period - 1);
-            if (nr > n1) nr = n1;
-            i0r[a] = pi0[nr];
-            s0r[a] = ps0[nr];
-        }
-        const int fix = XVEC == 4 ? ((i0r[0] - w0) & 3) : 0;  // move the group base down to a 16-byte boundary, taps shift up instead
-        int dsh[A][2];
-        int dmax = 0;
-#pragma unroll
-        for (int a = 0; a < A; a++) {
-            dsh[a][0] = i0r[a] - i0r[0] + fix;
-            dsh[a][1] = dsh[a][0] + (s0r[a] == OVERSAMPLING - 1 ? 1 : 0);  // get_nearest_times_2: row 0 at the next input sample
-            dmax = max(dmax, dsh[a][1]);
-        }
-        constexpr int mlen = MLEN;
-        const bool group_ok = !tile_big && SINC_LEN + dmax <= MLEN;
-
-        // own plan entries: valid outputs of a column are a < nv[b]
-        int nv[B], xoff[B];
-        bool follows[B];
-        float fr[A][B];
-#pragma unroll
-        for (int b = 0; b < B; b++) {
-            const long long nb = col_n0[b] + ph0;
-            long long left = min((long long)(geo.period - ph0), n1 - nb + 1);
-            nv[b] = col_ok[b] ? (int)max(0ll, min((long long)A, left)) : 0;
-            follows[b] = group_ok;
-            int ibase = i0r[0];
-#pragma unroll
-            for (int a = 0; a < A; a++) {
-                fr[a][b] = 0.0f;
-                if (a < nv[b]) {
-                    const int i0o = pi0[nb + a], s0o = ps0[nb + a];
-                    fr[a][b] = pfrac[nb + a];
-                    const int rel = i0o - (i0r[a] - i0r[0]);  // implied window start of output 0 of this column
-                    if (a == 0) ibase = rel;
-                    follows[b] = follows[b] && rel == ibase && s0o == s0r[a];
+    // ---- stage the windows: a warp takes lanes warp, warp + 8, ... and walks each in chunks of 32 frames.  32-bit samples are
+    // fetched with 4-byte cp.async (every copy of the tile in flight at once, no register round trip) and, where the format
+    // needs it (big-endian / integer / non-finite scrub), converted in place by the thread that fetched them; 16 / 24-bit
+    // samples go through registers, eight independent loads per lane at a time.
+    {
+        const int fstride = src.width == 0 ? 4 : src.channels * src.width;  // bytes between consecutive frames of a lane
+        const int lo = (int)max(0ll, min((long long)count, src.valid_lo - w0)), hi = (int)max(0ll, min((long long)count, src.valid_hi - w0));
+        if (src.width == 0 || (src.width == 4 && !src.byte_loads)) {
+            const bool raw_float = src.width == 0 || (src.is_float && !src.big_endian && !src.scrub);
+            for (int c = warp; c < geo.C; c += kG3Warps) {
+                const uint8_t* sp = s_col_src[c];
+                float* d = win + (size_t)c * geo.col_stride;
+                for (int i = q; i < count; i += 32) {
+                    if (sp && i >= lo && i < hi) cp_async4(d + i, sp + (long long)i * fstride);
+                    else d[i] = 0.0f;
                 }
             }
-            xoff[b] = ibase - w0 - fix;  // x base of the column for this group, in frames of the staged window
-            follows[b] = follows[b] && xoff[b] >= 0 && xoff[b] + mlen <= count;
-            if (!follows[b]) xoff[b] = 0;  // any staged window: the result is discarded
+            cp_async_wait_all();
+            if (!raw_float) {
+                for (int c = warp; c < geo.C; c += kG3Warps) {  // the same elements this thread fetched
+                    if (!s_col_src[c]) continue;
+                    float* d = win + (size_t)c * geo.col_stride;
+                    for (int i = max(lo, q + ((lo - q + 31) & ~31)); i < hi; i += 32) {
+                        const uint32_t u = __float_as_uint(d[i]);
+                        d[i] = decode_sample_bits(src.big_endian ? bswap32(u) : u, src);
+                    }
+                }
+            }
+        } else {
+            constexpr int U = 8;
+            for (int c = warp; c < geo.C; c += kG3Warps) {
+                const uint8_t* sp = s_col_src[c];
+                float* d = win + (size_t)c * geo.col_stride;
+                for (int i0 = q; i0 < count; i0 += 32 * U) {
+                    uint32_t bits[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int i = i0 + 32 * u;
+                        bits[u] = 0;
+                        if (sp && i >= lo && i < hi) {
+                            const uint8_t* p = sp + (long long)i * fstride;
+                            if (src.width != 2 || src.byte_loads) {
+                                for (int bb = 0; bb < src.width; bb++) bits[u] |= (uint32_t)p[bb] << (8 * (src.big_endian ? src.width - 1 - bb : bb));
+                            } else {
+                                bits[u] = *reinterpret_cast<const uint16_t*>(p);
+                                if (src.big_endian) bits[u] = ((bits[u] & 0xff) << 8) | (bits[u] >> 8);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int i = i0 + 32 * u;
+                        if (i < count) d[i] = (sp && i >= lo && i < hi) ? decode_sample_bits(bits[u], src) : 0.0f;
+                    }
+                }
+            }
         }
+    }
+    __syncthreads();
 
-        float y[A][B];
+    // ---- this thread's four columns.  The two half-warps share the 64 columns of the warp: lane pair (ql, ql + 16) owns columns
+    // ql + 16 b (b < 4) and splits the 8 virtual accumulator lanes — half hh walks words m + 4 hh .. m + 4 hh + 3 of every 8-word
+    // block.  A tap LDS.128 then carries two useful 16-byte rows (one per half-warp) in the two wavefronts a broadcast costs
+    // anyway, and every tap register feeds 4 columns: 32 shared-memory wavefronts per 64 FFMA2 per thread.  Each thread keeps
+    // the two columns it will finish in slots 0-1 and its partner's in slots 2-3 (slot b = column (b ^ 2 hh)), so the exchange
+    // after the walk needs no selects.  column j -> (lane c = j % C, period k = j / C)
+    const int ql = q & 15, hh = q >> 4;
+    // slot b of this thread = column j = ql + 16 (b ^ 2 hh) -> lane c = j % C of the CTA, period k = j / C of the tile
+    auto col_lane = [&](int b) { return (ql + 16 * (b ^ (2 * hh))) & (geo.C - 1); };
+    auto col_first = [&](int b) { return kLanes ? 0 : ((ql + 16 * (b ^ (2 * hh))) >> geo.log2c) * geo.period; };  // first output of the period
+    unsigned col_ok = 0;  // bit = slot: the lane exists
+#pragma unroll
+    for (int b = 0; b < B; b++) col_ok |= (lane0 + col_lane(b) < geo.n_lanes ? 1u : 0u) << b;
+    const float* xcol[B];  // window of each slot's lane, + this half's word offset
+#pragma unroll
+    for (int b = 0; b < B; b++) xcol[b] = win + (size_t)col_lane(b) * geo.col_stride + 4 * hh;
+
+    // Reference plan entries of a group (period 0 of the tile; entries clamped at ragged ends are masked later), packed:
+    //   base = window start of output 0 (moved down to a 16-byte boundary for the LDS.128 form: the taps shift up instead),
+    //   s0p  = the four subindices, dp = the four tap shifts of product 0 (product 1: + 1 where the subindex is 255,
+    //   get_nearest_times_2: row 0 at the next input sample); shift 255 marks a group the packed walk cannot take.
+    struct GroupRef { int base; unsigned s0p, dp; };
+    auto shift_of = [&](const GroupRef& r, int a, int p) { return (int)((r.dp >> (8 * a)) & 255u) + (p && ((r.s0p >> (8 * a)) & 255u) == 255u ? 1 : 0); };
+    auto ref_ok = [&](const GroupRef& r) {
+        int dmax = 0;
+#pragma unroll
+        for (int a = 0; a < A; a++) dmax = max(dmax, shift_of(r, a, 1));
+        return SINC_LEN + dmax <= MLEN && dmax <= kG3PadL;
+    };
+    auto load_ref = [&](int ph0, int (&i0v)[A], int (&s0v)[A]) {
+#pragma unroll
+        for (int a = 0; a < A; a++) {
+            const int nr = min(min(ph0 + a, geo.period - 1), nt - 1);
+            i0v[a] = pi0[nr];
+            s0v[a] = ps0[nr];
+        }
+    };
+    auto make_ref = [&](const int (&i0v)[A], const int (&s0v)[A], GroupRef& r) {
+        const int fix = kLanes ? ((i0v[0] - w0) & 3) : 0;
+        r.base = i0v[0] - fix; r.s0p = 0; r.dp = 0;
+#pragma unroll
+        for (int a = 0; a < A; a++) {
+            r.s0p |= (unsigned)s0v[a] << (8 * a);
+            r.dp |= (unsigned)min(255, max(0, i0v[a] - i0v[0] + fix)) << (8 * a);
+        }
+    };
+    // stage the 8 shifted rows of a group (warp private): 16-byte cp.async from the pre-shifted table copies
+    auto stage_taps = [&](const GroupRef& r) {
+        if (!ref_ok(r)) return;
 #pragma unroll
         for (int a = 0; a < A; a++)
 #pragma unroll
-            for (int b = 0; b < B; b++) y[a][b] = 0.0f;
+            for (int p = 0; p < 2; p++) {
+                const int s0 = (int)((r.s0p >> (8 * a)) & 255u);
+                const int row = p == 0 ? s0 : ((s0 + 1) & (OVERSAMPLING - 1));
+                const int d = shift_of(r, a, p), sh = d & 3;
+                const float* grow = table4 + ((size_t)(sh * OVERSAMPLING + row)) * kG3RowLen + (kG3PadL - (d - sh));
+                float* t = T + (a * 2 + p) * TS;
+                for (int v = q; v < MLEN / 4; v += 32) cp_async16(t + 4 * v, grow + 4 * v);
+            }
+    };
 
-        if (group_ok) {
-            // ---- stage the 8 shifted rows of this group (warp private)
-            __syncwarp();
+    // The group loop is software pipelined: while group g is convolved, the reference entries of the warp's next group are in
+    // flight; its tap rows are requested as soon as the walk has read the last word of the current rows, so they arrive under
+    // the exchange / store phase, and the frac values the finish step needs are loaded before the walk.
+    const int groups = min((geo.period + A - 1) / A, (nt + A - 1) / A);  // groups that exist in period 0 (later periods start later still)
+    GroupRef cur = {0, 0u, 0u};
+    if (warp < groups) {
+        int i0v[A], s0v[A];
+        load_ref(warp * A, i0v, s0v);
+        make_ref(i0v, s0v, cur);
+        stage_taps(cur);
+    }
+    for (int g = warp; g < groups; g += kG3Warps) {
+        const int ph0 = g * A;
+        const bool have_next = g + kG3Warps < groups;
+        if (have_next) {  // pull the next group's plan entries into L1 now (no registers held across the walk)
+            const int nr = min((g + kG3Warps) * A, nt - 1);
+            prefetch_l1(pi0 + nr); prefetch_l1(ps0 + nr);
+        }
+        const bool cur_ok = ref_ok(cur);
+        const int fix = (int)(cur.dp & 255u);  // shift of output 0, product 0 == the alignment fix
+
+        // x base of each column for this group (frames of the staged window); period columns: does the column follow the
+        // reference pattern?  (lane columns share every plan entry: always)
+        int xoff[kLanes ? 1 : B];
+        unsigned follows = 0;  // bit = slot
+        if (kLanes) {
+            xoff[0] = cur.base - w0;
+            const bool f = cur_ok && xoff[0] >= 0 && xoff[0] + MLEN <= count;
+            if (!f) xoff[0] = 0;
+            follows = f ? 0xfu : 0u;
+        } else {
 #pragma unroll
-            for (int a = 0; a < A; a++)
+            for (int b = 0; b < B; b++) {
+                bool f = cur_ok;
+                int ibase = cur.base;
+                const int rb = col_first(b) + ph0;
+                const int nv = ((col_ok >> b) & 1u) ? max(0, min(A, min(geo.period - ph0, nt - rb))) : 0;
 #pragma unroll
-                for (int p = 0; p < 2; p++) {
-                    const int row = p == 0 ? s0r[a] : ((s0r[a] + 1) & (OVERSAMPLING - 1));
-                    const float* h = table + row * SINC_LEN;
-                    float* t = T + (a * 2 + p) * TS;
-                    const int d = dsh[a][p];
-                    for (int m = q; m < mlen; m += 32) {
-                        const int j = m - d;
-                        t[m] = (j >= 0 && j < SINC_LEN) ? __ldg(h + j) : 0.0f;
+                for (int a = 0; a < A; a++) {
+                    if (a < nv) {
+                        const int rel = pi0[rb + a] - ((int)((cur.dp >> (8 * a)) & 255u) - fix);  // implied window start of output 0 of this column
+                        if (a == 0) ibase = rel;
+                        f = f && rel == ibase && (unsigned)ps0[rb + a] == ((cur.s0p >> (8 * a)) & 255u);
                     }
                 }
-            __syncwarp();
+                xoff[b] = ibase - w0;
+                f = f && xoff[b] >= 0 && xoff[b] + MLEN <= count;
+                if (!f) xoff[b] = 0;  // any staged window: the result is discarded
+                follows |= (f ? 1u : 0u) << b;
+            }
+        }
+        // the finish step's frac values (slots 0, 1): into L1 ahead of the walk
+#pragma unroll
+        for (int bb = 0; bb < (kLanes ? 1 : 2); bb++) prefetch_l1(pfrac + min(col_first(bb) + ph0, nt - 1));
+        unsigned rot_odd = 0;  // bit a * 2 + p: parity of the accumulator-lane rotation of that product
+#pragma unroll
+        for (int a = 0; a < A; a++)
+#pragma unroll
+            for (int p = 0; p < 2; p++) rot_odd |= (unsigned)(shift_of(cur, a, p) & 1) << (a * 2 + p);
 
-            // ---- the packed FIR walk
+        cp_async_wait_all();  // this group's rows
+        __syncwarp();
+        unsigned long long acc[A][B][2][2];  // [output][slot][product][pair of this half's 4 virtual lanes]
+        if (cur_ok) {
+            // ---- the packed FIR walk over this half-warp's words
             const float* xb[B];
 #pragma unroll
-            for (int b = 0; b < B; b++) xb[b] = win + (size_t)col_c[b] * geo.col_stride + xoff[b];
-            unsigned long long acc[A][B][2][4];
+            for (int b = 0; b < B; b++) xb[b] = xcol[b] + xoff[kLanes ? 0 : b];
+            const float* Th = T + 4 * hh;
 #pragma unroll
-            for (int i = 0; i < A * B * 8; i++) (&acc[0][0][0][0])[i] = 0ull;
+            for (int i = 0; i < A * B * 4; i++) (&acc[0][0][0][0])[i] = 0ull;
 #pragma unroll
             for (int m = 0; m < MLEN; m += 8) {
+                unsigned long long xp[B][2];
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int mm = m + 4 * h;
-                    unsigned long long xp[B][2];
+                for (int b = 0; b < B; b++) {
+                    if (kLanes) {
+                        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xp[b][0]), "=l"(xp[b][1]) : "r"(smem_u32(xb[b] + m)));
+                    } else {
+                        xp[b][0] = pack2(xb[b][m], xb[b][m + 1]);
+                        xp[b][1] = pack2(xb[b][m + 2], xb[b][m + 3]);
+                    }
+                }
 #pragma unroll
-                    for (int b = 0; b < B; b++) {
-                        if (XVEC == 4) {
-                            asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xp[b][0]), "=l"(xp[b][1]) : "r"(smem_u32(xb[b] + mm)));
-                        } else {
-                            xp[b][0] = pack2(xb[b][mm], xb[b][mm + 1]);
-                            xp[b][1] = pack2(xb[b][mm + 2], xb[b][mm + 3]);
+                for (int a = 0; a < A; a++)
+#pragma unroll
+                    for (int p = 0; p < 2; p++) {
+                        unsigned long long t0, t1;
+                        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(t0), "=l"(t1) : "r"(smem_u32(Th + (a * 2 + p) * TS + m)));
+#pragma unroll
+                        for (int b = 0; b < B; b++) {
+                            ffma2(acc[a][b][p][0], xp[b][0], t0);
+                            ffma2(acc[a][b][p][1], xp[b][1], t1);
                         }
                     }
-#pragma unroll
-                    for (int a = 0; a < A; a++)
-#pragma unroll
-                        for (int p = 0; p < 2; p++) {
-                            unsigned long long t0, t1;
-                            asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(t0), "=l"(t1) : "r"(smem_u32(T + (a * 2 + p) * TS + mm)));
-#pragma unroll
-                            for (int b = 0; b < B; b++) {
-                                ffma2(acc[a][b][p][2 * h], xp[b][0], t0);
-                                ffma2(acc[a][b][p][2 * h + 1], xp[b][1], t1);
-                            }
-                        }
-                }
             }
+        }
+        // ---- the rows are consumed: request the next group's while this one is finished
+        __syncwarp();
+        if (have_next) {
+            int i0n[A], s0n[A];
+            load_ref((g + kG3Warps) * A, i0n, s0n);
+            make_ref(i0n, s0n, cur);
+            stage_taps(cur);
+        }
+        float P0[A][2], P1[A][2];  // the two products of the 4 outputs of the 2 columns this thread finishes (slots 0, 1)
+#pragma unroll
+        for (int a = 0; a < A; a++)
+#pragma unroll
+            for (int bb = 0; bb < 2; bb++) { P0[a][bb] = 0.0f; P1[a][bb] = 0.0f; }
+        if (cur_ok) {
+            // ---- exchange and reduce: this thread holds virtual lanes 4 hh .. 4 hh + 3 of all four slots and finishes slots 0, 1;
+            // its partner (lane ^ 16) holds the other four lanes and finishes this thread's slots 2, 3 (its own 0, 1).
+            // s_i = v_i + v_{i+4} pairs one value of each half and additions commute, so the halves need no ordering.
 #pragma unroll
             for (int a = 0; a < A; a++)
 #pragma unroll
-                for (int b = 0; b < B; b++) {
-                    const float p0 = reduce8_rotated(acc[a][b][0], dsh[a][0] & 7), p1 = reduce8_rotated(acc[a][b][1], dsh[a][1] & 7);
-                    y[a][b] = __fadd_rn(p0, __fmul_rn(fr[a][b], __fsub_rn(p1, p0)));  // interp_lin with the output's own frac
+                for (int p = 0; p < 2; p++)
+#pragma unroll
+                    for (int bb = 0; bb < 2; bb++) {
+                        float s4[4];
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            const unsigned long long recv = __shfl_xor_sync(0xffffffffu, acc[a][2 + bb][p][k], 16);
+                            float m0, m1, r0, r1;
+                            unpack2(acc[a][bb][p][k], m0, m1);
+                            unpack2(recv, r0, r1);
+                            s4[2 * k] = __fadd_rn(m0, r0); s4[2 * k + 1] = __fadd_rn(m1, r1);
+                        }
+                        // (a_l + a_{l+4}) = s4[(l + rot) & 3]; the tree adds pairs (0,1) and (2,3) of those: adjacent pairs starting at rot & 3
+                        const bool odd = ((rot_odd >> (a * 2 + p)) & 1u) != 0;
+                        const float t0 = odd ? __fadd_rn(s4[1], s4[2]) : __fadd_rn(s4[0], s4[1]);
+                        const float t1 = odd ? __fadd_rn(s4[3], s4[0]) : __fadd_rn(s4[2], s4[3]);
+                        const float r = __fadd_rn(t0, t1);
+                        if (p == 0) P0[a][bb] = r; else P1[a][bb] = r;
+                    }
+        }
+
+        // ---- finish slots 0, 1: interp_lin with each output's own frac; a non-finite result is recomputed with the per-output
+        // arithmetic (an Inf / NaN input word that met a zero-padded tap must not leak into an output whose true window excludes
+        // it), as are columns that do not follow the reference pattern; one 16-byte store per column
+#pragma unroll
+        for (int bb = 0; bb < 2; bb++) {
+            const int rb = col_first(bb) + ph0;
+            const int nv = ((col_ok >> bb) & 1u) ? max(0, min(A, min(geo.period - ph0, nt - rb))) : 0;
+            if (nv > 0) {
+                const bool f = ((follows >> bb) & 1u) != 0;
+                const int cl = col_lane(bb);
+                const float* wc = win + (size_t)cl * geo.col_stride;
+                float y[A];
+                int redo = 0;
+#pragma unroll
+                for (int a = 0; a < A; a++) {
+                    y[a] = 0.0f;
+                    if (a < nv) {
+                        const float fr = pfrac[rb + a];
+                        y[a] = __fadd_rn(P0[a][bb], __fmul_rn(fr, __fsub_rn(P1[a][bb], P0[a][bb])));  // interp_lin
+                        if (!f || g3_nonfinite(y[a])) { y[a] = g3_exact(wc, w0, pi0, ps0, rb + a, table, fr); redo++; }
+                    }
                 }
-        }
-
-        // ---- columns that do not follow the reference pattern (and whole groups / tiles on the exact slow path): per-output arithmetic
+                if (redo) atomicAdd(stats, (unsigned long long)redo);
+                float* op = s_col_dst[cl] + rb;
+                if (nv == A && ((((uintptr_t)op) & 15) == 0)) {
+                    *reinterpret_cast<float4*>(op) = make_float4(y[0], y[1], y[2], y[3]);
+                } else {
 #pragma unroll
-        for (int b = 0; b < B; b++) {
-            if (nv[b] == 0 || follows[b]) continue;
-            const long long nb = col_n0[b] + ph0;
-#pragma unroll
-            for (int a = 0; a < A; a++) {
-                if (a >= nv[b]) continue;
-                const int i0o = pi0[nb + a], s0o = ps0[nb + a];
-                int s1 = s0o + 1, d = 0;
-                if (s1 >= OVERSAMPLING) { s1 -= OVERSAMPLING; d = 1; }
-                y[a][b] = gen3_single(win + (size_t)col_c[b] * geo.col_stride + (i0o - w0), table + s0o * SINC_LEN, table + s1 * SINC_LEN, d, fr[a][b]);
-            }
-            atomicAdd(stats, (unsigned long long)nv[b]);
-        }
-
-        // ---- store: 4 consecutive outputs per column
-#pragma unroll
-        for (int b = 0; b < B; b++) {
-            if (nv[b] == 0) continue;
-            const long long nb = col_n0[b] + ph0;
-            const long long lane = lane0 + col_c[b];
-            float* op = dst.base + (lane / lanes_per_stream) * dst.stream_stride + (lane % lanes_per_stream) * dst.lane_stride + nb;
-            if (nv[b] == A && ((((uintptr_t)op) & 15) == 0)) {
-                *reinterpret_cast<float4*>(op) = make_float4(y[0][b], y[1][b], y[2][b], y[3][b]);
-            } else {
-#pragma unroll
-                for (int a = 0; a < A; a++)
-                    if (a < nv[b]) op[a] = y[a][b];
+                    for (int a = 0; a < A; a++)
+                        if (a < nv) op[a] = y[a];
+                }
             }
         }
     }
+    cp_async_wait_all();
 }
 
 // ================================================================================================
 // host: geometry and launch
 // ================================================================================================
 template <int XVEC, int MLEN>
-static int launch_gen3_t(sk_ctx* ctx, const SrcDesc& s2, const OutDesc& d2, const Gen3Geom& g2, const sk_plan* plan, const float* d_table, int lanes_per_stream,
-                         dim3 grid, int smem) {
+static int launch_gen3_t(sk_ctx* ctx, const SrcDesc& s2, const OutDesc& d2, const Gen3Geom& g2, const sk_plan* plan, const float* d_table,
+                         const float* d_table4, int lanes_per_stream, dim3 grid, int smem) {
     SK_CUDA(ctx, cudaFuncSetAttribute(resample_gen3_kernel<XVEC, MLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    resample_gen3_kernel<XVEC, MLEN><<<grid, kG3Threads, smem, ctx->stream>>>(s2, d2, g2, plan->d_i0, plan->d_s0, plan->d_frac, d_table, lanes_per_stream,
-                                                                            ctx->d_stats);
+    resample_gen3_kernel<XVEC, MLEN><<<grid, kG3Threads, smem, ctx->stream>>>(s2, d2, g2, plan->d_i0, plan->d_s0, plan->d_frac, d_table, d_table4,
+                                                                            lanes_per_stream, ctx->d_stats);
     SK_LAUNCH_CHECK(ctx);
     return SK_OK;
 }
+
+int sk_get_shifted_sinc_table(sk_ctx* ctx, uint32_t in_rate, uint32_t out_rate, int pad_l, int row_len, const float** d_table4);  // sk_resample.cu
 
 // returns SK_OK after a launch, 1 when this kernel does not apply to the plan / batch (the caller falls back to gen2 / gen)
 int sk_launch_gen3(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, const float* d_table, uint32_t in_rate, uint32_t out_rate,
@@ -343,6 +486,7 @@ int sk_launch_gen3(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk
     // largest tap shift inside a group: window advance over 3 outputs (exact, from the plan) + the subindex-255 shift + the
     // alignment fix of the LDS.128 form
     const int dmax = plan->max_step3 + 1 + (lanes_only ? 3 : 0);
+    if (dmax > kG3PadL) return 1;
     const int mlen = SINC_LEN + dmax <= 264 ? 264 : (SINC_LEN + dmax <= 272 ? 272 : 0);
     if (!mlen) return 1;                                        // steep downsampling ratios: the padded walk would waste too much; gen2 / gen serve them
     g.tap_stride = mlen;
@@ -381,7 +525,10 @@ int sk_launch_gen3(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk
         if (taps_bytes + C * stride * (int)sizeof(float) > smem_budget) return 1;
     }
     const int smem = taps_bytes + g.C * g.col_stride * (int)sizeof(float);
+    for (g.log2c = 0; (1 << g.log2c) < g.C; g.log2c++) {}
     if (int rc = sk_ensure_stats(ctx)) return rc;
+    const float* d_table4 = nullptr;
+    if (int rc = sk_get_shifted_sinc_table(ctx, in_rate, out_rate, kG3PadL, kG3RowLen, &d_table4)) return rc;
     const long long tile_out = (long long)g.period * g.P;
     const long long tiles = ((long long)plan->n_out + tile_out - 1) / tile_out;
     const long long lane_blocks = (n_lanes + g.C - 1) / g.C;
@@ -399,10 +546,10 @@ int sk_launch_gen3(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk
         }
         const dim3 grid((unsigned)tiles, (unsigned)nb);
         int rc;
-        if (g.xvec) rc = mlen == 264 ? launch_gen3_t<4, 264>(ctx, s2, d2, g2, plan, d_table, lanes_per_stream, grid, smem)
-                                     : launch_gen3_t<4, 272>(ctx, s2, d2, g2, plan, d_table, lanes_per_stream, grid, smem);
-        else rc = mlen == 264 ? launch_gen3_t<1, 264>(ctx, s2, d2, g2, plan, d_table, lanes_per_stream, grid, smem)
-                              : launch_gen3_t<1, 272>(ctx, s2, d2, g2, plan, d_table, lanes_per_stream, grid, smem);
+        if (g.xvec) rc = mlen == 264 ? launch_gen3_t<4, 264>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem)
+                                     : launch_gen3_t<4, 272>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem);
+        else rc = mlen == 264 ? launch_gen3_t<1, 264>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem)
+                              : launch_gen3_t<1, 272>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem);
         if (rc) return rc;
     }
     return SK_OK;
