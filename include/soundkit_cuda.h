@@ -206,6 +206,26 @@ int    sk_resampler_process_partial(sk_resampler*, const float* const* in_or_nul
 /* the [256][256] windowed-sinc table this resampler uses (for parity tests) */
 int    sk_resampler_copy_table(const sk_resampler*, float* out65536);
 
+/* N StreamingResamplers in lock step (soundkit-decoder/src/lib.rs:1917-2060: `StreamingResampler`, rubato chunk 4096): the state
+ * of n_streams live streams — per (stream, channel) the 512-sample rubato history and the not yet consumed input; the f64 index
+ * of the walk is shared, it is data independent — stays on the device between calls.  Every call serves all streams with one
+ * kernel launch.  `in` / `out` are DEVICE pointers to planar f32: in[s][c][0 .. frames), out[s][c][0 .. *n_out), strides in floats. */
+typedef struct sk_resampler_batch sk_resampler_batch;
+int    sk_resampler_batch_create(sk_ctx*, uint32_t in_rate, uint32_t out_rate, int channels, size_t n_streams,
+                                 size_t max_push_frames, sk_resampler_batch** out);
+void   sk_resampler_batch_destroy(sk_resampler_batch*);
+/* frames per channel one process / flush call can produce at most: every `out` row must hold this many */
+size_t sk_resampler_batch_out_cap(const sk_resampler_batch*);
+size_t sk_resampler_batch_pending(const sk_resampler_batch*);      /* frames pushed but not yet consumed (< 4096) */
+double sk_resampler_batch_last_index(const sk_resampler_batch*);
+/* StreamingResampler::process (:1970-2015) for every stream: append `frames` (<= max_push_frames) frames per channel, run every
+ * whole 4096-frame chunk that is pending; *n_out = frames produced per channel (0 while less than a chunk is pending) */
+int    sk_resampler_batch_process_dev(sk_resampler_batch*, const float* in, size_t in_stream_stride, size_t in_ch_stride,
+                                      size_t frames, float* out, size_t out_stream_stride, size_t out_ch_stride, size_t* n_out);
+/* StreamingResampler::flush (:2017-2059): zero-pad the remainder to one chunk, drop the padding's share of the output
+ * (round(padded * out / in) frames); with nothing pending: one chunk of zeros, untrimmed */
+int    sk_resampler_batch_flush_dev(sk_resampler_batch*, float* out, size_t out_stream_stride, size_t out_ch_stride, size_t* n_out);
+
 /* ------------------------------------------------------------------ kernel 4: fused batch chain */
 /* Batched, device-resident normalisation of n_streams equal-length streams:
  *   interleaved PCM (bits/fmt/endianness/channels) --convert(scale_mode)--> f32

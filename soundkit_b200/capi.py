@@ -39,6 +39,8 @@ EXPORTS = (
     "sk_planar_f32_to_pcm_dev", "sk_pcm_narrow_i16", "sk_mixdown_mono", "sk_mixdown_mono_dev", "sk_downmix_stereo",
     "sk_resampler_create", "sk_resampler_destroy", "sk_resampler_out_max", "sk_resampler_last_index",
     "sk_resampler_process", "sk_resampler_process_partial", "sk_resampler_copy_table",
+    "sk_resampler_batch_create", "sk_resampler_batch_destroy", "sk_resampler_batch_out_cap", "sk_resampler_batch_pending",
+    "sk_resampler_batch_last_index", "sk_resampler_batch_process_dev", "sk_resampler_batch_flush_dev",
     "sk_normalize_batch_plan", "sk_normalize_batch_dev", "sk_normalize_batch_pcm_dev", "sk_normalize_batch", "sk_normalize_stream",
     "sk_norm48k_create", "sk_norm48k_destroy", "sk_norm48k_push", "sk_norm48k_finish", "sk_norm48k_source_frames",
     "sk_norm48k_output_frames", "sk_norm48k_source_sample_rate", "sk_norm48k_source_channels", "sk_norm48k_max_output",
@@ -120,6 +122,13 @@ def load():
         "sk_resampler_process": (i, [vp, vp, vp, psz]),
         "sk_resampler_process_partial": (i, [vp, vp, sz, vp, psz]),
         "sk_resampler_copy_table": (i, [vp, vp]),
+        "sk_resampler_batch_create": (i, [vp, u32, u32, i, sz, sz, C.POINTER(vp)]),
+        "sk_resampler_batch_destroy": (None, [vp]),
+        "sk_resampler_batch_out_cap": (sz, [vp]),
+        "sk_resampler_batch_pending": (sz, [vp]),
+        "sk_resampler_batch_last_index": (C.c_double, [vp]),
+        "sk_resampler_batch_process_dev": (i, [vp, vp, sz, sz, sz, vp, sz, sz, psz]),
+        "sk_resampler_batch_flush_dev": (i, [vp, vp, sz, sz, psz]),
         "sk_normalize_batch_plan": (i, [vp, u32, u32, sz, i, psz]),
         "sk_normalize_batch_dev": (i, [vp, C.POINTER(BatchDesc)]),
         "sk_normalize_batch": (i, [vp, C.POINTER(BatchDesc)]),
@@ -377,6 +386,10 @@ class Context:
         return Resampler(self, in_rate, out_rate, channels, chunk)
 
     # -- G.726 ADPCM
+    def resampler_batch(self, in_rate, out_rate, channels, n_streams, max_push=4096):
+        """N lock-step StreamingResamplers with device-resident state (sk_resampler_batch_*)"""
+        return ResamplerBatch(self, in_rate, out_rate, channels, n_streams, max_push)
+
     def g726_state(self):
         st = np.zeros(24, np.int32)
         self.L.sk_g726_state_init(_p(st))
@@ -461,6 +474,51 @@ class Normalizer48k:
         n = C.c_size_t()
         self.ctx._ck(self.ctx.L.sk_norm48k_finish(self.h, _p(l), _p(r), cap, C.byref(n)))
         return l[:n.value], r[:n.value]
+
+
+class ResamplerBatch:
+    """sk_resampler_batch: StreamingResampler::process / flush for n_streams streams at once, torch CUDA tensors in and out
+    (planar f32 [n_streams][channels][frames])."""
+
+    def __init__(self, ctx, in_rate, out_rate, channels, n_streams, max_push):
+        self.ctx, self.channels, self.n_streams = ctx, channels, n_streams
+        h = C.c_void_p()
+        ctx._ck(ctx.L.sk_resampler_batch_create(ctx.h, in_rate, out_rate, channels, n_streams, max_push, C.byref(h)))
+        self.h = h
+        self.out_max = int(ctx.L.sk_resampler_batch_out_cap(h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.L.sk_resampler_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def pending(self):
+        return int(self.ctx.L.sk_resampler_batch_pending(self.h))
+
+    @property
+    def last_index(self):
+        return float(self.ctx.L.sk_resampler_batch_last_index(self.h))
+
+    def process_dev(self, x, out):
+        """x: [n_streams, channels, frames] f32 CUDA tensor; out: [n_streams, channels, >= out_max]; returns frames produced"""
+        assert x.dim() == 3 and x.stride(2) == 1 and out.stride(2) == 1 and out.shape[2] >= self.out_max
+        n = C.c_size_t(0)
+        self.ctx._ck(self.ctx.L.sk_resampler_batch_process_dev(self.h, C.c_void_p(x.data_ptr()), x.stride(0), x.stride(1), x.shape[2],
+                                                              C.c_void_p(out.data_ptr()), out.stride(0), out.stride(1), C.byref(n)))
+        return n.value
+
+    def flush_dev(self, out):
+        assert out.stride(2) == 1 and out.shape[2] >= self.out_max
+        n = C.c_size_t(0)
+        self.ctx._ck(self.ctx.L.sk_resampler_batch_flush_dev(self.h, C.c_void_p(out.data_ptr()), out.stride(0), out.stride(1), C.byref(n)))
+        return n.value
 
 
 class Resampler:

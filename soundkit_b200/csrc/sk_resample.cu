@@ -1058,3 +1058,214 @@ extern "C" int sk_resampler_process_partial(sk_resampler* r, const float* const*
     if (frames > r->chunk) frames = r->chunk;
     return resampler_run(r, in_or_null, in_or_null ? frames : 0, out, n_out);
 }
+
+// ================================================================================================
+// C ABI: batched stateful streaming resampler — N StreamingResamplers in lock step
+// ================================================================================================
+// soundkit-decoder/src/lib.rs:1917-2060: `StreamingResampler { resampler: SincFixedIn(chunk 4096), accum, accum_start }`.
+// One handle carries that state for n_streams live streams on the device: per (stream, channel) lane a row
+// [2 * SINC_LEN history | pending input]; the f64 index of rubato's walk is data independent, so ONE host-side walk serves
+// every stream of the batch.  A process call appends the pushed frames, runs every whole 4096-frame chunk that is pending in
+// ONE launch for all streams (the chunks' outputs are contiguous, like StreamingResampler::process returning its pushes), and
+// moves the new history + remainder to the front of the second row buffer (ping-pong: no overlapping copy).
+struct sk_resampler_batch {
+    sk_ctx* ctx;
+    uint32_t in_rate, out_rate;
+    double ratio;
+    int channels;
+    size_t n_streams, max_push, row;   // row = 2 * SINC_LEN + STREAM_CHUNK + max_push floats per lane
+    float* d_rows[2] = {nullptr, nullptr};
+    int cur = 0;
+    size_t pending = 0;                // frames waiting behind the history in d_rows[cur]
+    double last_index;
+    sk_plan plan;                      // per call (general ratios: arrays re-uploaded per call)
+    size_t plan_cap = 0;
+};
+
+extern "C" int sk_resampler_batch_create(sk_ctx* ctx, uint32_t in_rate, uint32_t out_rate, int channels, size_t n_streams, size_t max_push_frames,
+                                         sk_resampler_batch** out) {
+    if (!ctx || !out) return SK_E_ARG;
+    *out = nullptr;
+    if (!in_rate) SK_FAIL(ctx, SK_E_ARG, "Input sample rate must be > 0");
+    if (!out_rate) SK_FAIL(ctx, SK_E_ARG, "Output sample rate must be > 0");
+    if (channels <= 0 || channels > 255) SK_FAIL(ctx, SK_E_ARG, "Channel count must be > 0");
+    if (!n_streams || !max_push_frames) SK_FAIL(ctx, SK_E_ARG, "n_streams and max_push_frames must be > 0");
+    if (max_push_frames > ((size_t)1 << 26) || n_streams * (size_t)channels > ((size_t)1 << 30)) SK_FAIL(ctx, SK_E_ARG, "batch too large");
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    sk_resampler_batch* b = new (std::nothrow) sk_resampler_batch();
+    if (!b) SK_FAIL(ctx, SK_E_ALLOC, "out of memory");
+    b->ctx = ctx; b->in_rate = in_rate; b->out_rate = out_rate; b->ratio = (double)out_rate / (double)in_rate;
+    b->channels = channels; b->n_streams = n_streams; b->max_push = max_push_frames;
+    b->row = sk_round_up(2 * SINC_LEN + STREAM_CHUNK + max_push_frames, 4);
+    b->last_index = -(double)(SINC_LEN / 2);
+    const size_t bytes = n_streams * (size_t)channels * b->row * sizeof(float);
+    for (int i = 0; i < 2; i++) {
+        if (cudaMalloc((void**)&b->d_rows[i], bytes) != cudaSuccess) {
+            cudaGetLastError();
+            sk_resampler_batch_destroy(b);
+            SK_FAIL(ctx, SK_E_ALLOC, "device allocation of %zu bytes failed", bytes);
+        }
+    }
+    // SincFixedIn::new zero-fills its buffer: the initial history
+    cudaMemsetAsync(b->d_rows[0], 0, bytes, ctx->stream);
+    int step;
+    b->plan.integer_step = integer_step_of(in_rate, out_rate, &step);
+    b->plan.step = b->plan.integer_step ? step : 0;
+    int rc = get_sinc_table(ctx, in_rate, out_rate, nullptr, nullptr);
+    if (rc) { sk_resampler_batch_destroy(b); return rc; }
+    *out = b;
+    return SK_OK;
+}
+
+extern "C" void sk_resampler_batch_destroy(sk_resampler_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    for (int i = 0; i < 2; i++)
+        if (b->d_rows[i]) cudaFree(b->d_rows[i]);
+    if (b->plan.d_i0) cudaFree(b->plan.d_i0);
+    if (b->plan.d_s0) cudaFree(b->plan.d_s0);
+    if (b->plan.d_frac) cudaFree(b->plan.d_frac);
+    delete b;
+}
+
+// frames per channel one process / flush call can produce at most (every call's `out` rows must hold this many)
+extern "C" size_t sk_resampler_batch_out_cap(const sk_resampler_batch* b) {
+    if (!b) return 0;
+    const size_t chunks = (STREAM_CHUNK + b->max_push) / STREAM_CHUNK;
+    return chunks * (size_t)((double)STREAM_CHUNK * b->ratio * 2.0 + 10.0);
+}
+extern "C" size_t sk_resampler_batch_pending(const sk_resampler_batch* b) { return b ? b->pending : 0; }
+extern "C" double sk_resampler_batch_last_index(const sk_resampler_batch* b) { return b ? b->last_index : 0.0; }
+
+// run `chunks` rubato chunks over d_rows[cur] (frames [0, valid) of the pending region are data, the rest reads as zero), write
+// `keep` of the produced frames per lane, advance last_index
+static int batch_run_chunks(sk_resampler_batch* b, size_t chunks, size_t valid, float* out, size_t out_stream_stride, size_t out_ch_stride, size_t drop_tail,
+                            size_t* n_out) {
+    sk_ctx* ctx = b->ctx;
+    sk_plan& p = b->plan;
+    WalkOut w;
+    w.record = !p.integer_step;
+    double last = b->last_index;
+    const double first_last = last;
+    for (size_t c = 0; c < chunks; c++) last = walk_chunk(last, b->ratio, STREAM_CHUNK, (long long)(c * STREAM_CHUNK), w);
+    size_t n = w.count;
+    n = n > drop_tail ? n - drop_tail : 0;
+    p.n_out = n;
+    if (p.integer_step) {
+        p.i0_first = (long long)first_last + p.step;  // idx is an exact integer on this path and advances by `step` across chunk borders
+    } else if (n) {
+        if (n > b->plan_cap) {
+            cudaStreamSynchronize(ctx->stream);
+            if (p.d_i0) cudaFree(p.d_i0);
+            if (p.d_s0) cudaFree(p.d_s0);
+            if (p.d_frac) cudaFree(p.d_frac);
+            p.d_i0 = nullptr; p.d_s0 = nullptr; p.d_frac = nullptr;
+            b->plan_cap = 0;
+            const size_t cap = n + n / 8 + 64;
+            SK_CUDA(ctx, cudaMalloc((void**)&p.d_i0, cap * sizeof(int32_t)));
+            SK_CUDA(ctx, cudaMalloc((void**)&p.d_s0, cap));
+            SK_CUDA(ctx, cudaMalloc((void**)&p.d_frac, cap * sizeof(float)));
+            b->plan_cap = cap;
+        }
+        int rc;
+        if ((rc = sk_h2d(ctx, p.d_i0, w.i0.data(), n * sizeof(int32_t)))) return rc;
+        if ((rc = sk_h2d(ctx, p.d_s0, w.s0.data(), n))) return rc;
+        if ((rc = sk_h2d(ctx, p.d_frac, w.frac.data(), n * sizeof(float)))) return rc;
+        p.max_step3 = 0;
+        for (size_t i = 0; i + 3 < n; i++) p.max_step3 = std::max(p.max_step3, w.i0[i + 3] - w.i0[i]);
+        // tile mapping of the one-output-per-thread kernel (batches below 64 lanes): same rule as the batch plans
+        const uint32_t g = gcd_u32(b->in_rate, b->out_rate);
+        const uint32_t L = b->out_rate / g;
+        auto window_for = [&](int period) {
+            int mw = 0;
+            const size_t tile = (size_t)period * 32;
+            for (size_t a = 0; a < n; a += tile) mw = std::max(mw, w.i0[std::min(n, a + tile) - 1] - w.i0[a] + SINC_LEN + 2);
+            return mw;
+        };
+        p.period = 8;
+        if (L >= 8 && L <= 512 && window_for((int)L) <= kGenMaxWindow) p.period = (int)L;
+        p.max_window = window_for(p.period);
+        p.period2 = 0;
+    }
+    if (n) {
+        SrcDesc src;
+        memset(&src, 0, sizeof(src));
+        src.base = (const uint8_t*)b->d_rows[b->cur];
+        src.stream_stride = (long long)((size_t)b->channels * b->row * sizeof(float));
+        src.lane_stride = (long long)(b->row * sizeof(float));
+        src.width = 0; src.channels = b->channels; src.scale = 1.0f;
+        src.origin = 2 * SINC_LEN; src.valid_lo = -(long long)(2 * SINC_LEN); src.valid_hi = (long long)valid;
+        OutDesc dst;
+        dst.base = out; dst.stream_stride = (long long)out_stream_stride; dst.lane_stride = (long long)out_ch_stride; dst.mix = SK_MIX_NONE;
+        dst.n_out = (long long)n;
+        int rc = run_plan(ctx, src, dst, &p, b->in_rate, b->out_rate, b->n_streams, b->channels);
+        if (rc) return rc;
+    }
+    b->last_index = last;
+    if (n_out) *n_out = n;
+    return SK_OK;
+}
+
+// new history (the last 2 * SINC_LEN frames consumed) + the unconsumed remainder -> front of the other row buffer
+static int batch_carry(sk_resampler_batch* b, size_t consumed, size_t total) {
+    sk_ctx* ctx = b->ctx;
+    const size_t lanes = b->n_streams * (size_t)b->channels;
+    const size_t keep = 2 * SINC_LEN + (total - consumed);
+    SK_CUDA(ctx, cudaMemcpy2DAsync(b->d_rows[b->cur ^ 1], b->row * sizeof(float), b->d_rows[b->cur] + consumed, b->row * sizeof(float), keep * sizeof(float), lanes,
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
+    b->cur ^= 1;
+    b->pending = total - consumed;
+    return SK_OK;
+}
+
+// StreamingResampler::process (soundkit-decoder/src/lib.rs:1970-2015) for every stream of the batch: in[s][c][0 .. frames) are
+// device f32 planes (strides in floats); out[s][c][0 .. *n_out) receives what the reference's returned pushes concatenate to
+extern "C" int sk_resampler_batch_process_dev(sk_resampler_batch* b, const float* in, size_t in_stream_stride, size_t in_ch_stride, size_t frames, float* out,
+                                              size_t out_stream_stride, size_t out_ch_stride, size_t* n_out) {
+    if (!b) return SK_E_ARG;
+    sk_ctx* ctx = b->ctx;
+    if (n_out) *n_out = 0;
+    if (frames > b->max_push) SK_FAIL(ctx, SK_E_ARG, "push of %zu frames exceeds max_push_frames %zu", frames, b->max_push);
+    if (!frames) return SK_OK;
+    if (!in || !out) SK_FAIL(ctx, SK_E_ARG, "null buffer");
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    // append behind the pending frames: one 2-D copy per channel plane set
+    float* row0 = b->d_rows[b->cur] + 2 * SINC_LEN + b->pending;
+    if (in_ch_stride * (size_t)b->channels == in_stream_stride || b->channels == 1 || b->n_streams == 1) {
+        // lanes are equally spaced in the source: a single 2-D copy
+        const size_t lane_pitch = b->channels == 1 ? in_stream_stride : in_ch_stride;
+        SK_CUDA(ctx, cudaMemcpy2DAsync(row0, b->row * sizeof(float), in, lane_pitch * sizeof(float), frames * sizeof(float), b->n_streams * (size_t)b->channels,
+                                       cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        for (int c = 0; c < b->channels; c++)
+            SK_CUDA(ctx, cudaMemcpy2DAsync(row0 + (size_t)c * b->row, (size_t)b->channels * b->row * sizeof(float), in + (size_t)c * in_ch_stride,
+                                           in_stream_stride * sizeof(float), frames * sizeof(float), b->n_streams, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    const size_t total = b->pending + frames;
+    const size_t chunks = total / STREAM_CHUNK;
+    if (!chunks) { b->pending = total; return SK_OK; }
+    int rc = batch_run_chunks(b, chunks, chunks * STREAM_CHUNK, out, out_stream_stride, out_ch_stride, 0, n_out);
+    if (rc) return rc;
+    return batch_carry(b, chunks * STREAM_CHUNK, total);
+}
+
+// StreamingResampler::flush (soundkit-decoder/src/lib.rs:2017-2059): a pending remainder is zero padded to one chunk and the
+// padding's share of the output (round(padded * out / in) frames) is dropped; with nothing pending one chunk of zeros is run
+extern "C" int sk_resampler_batch_flush_dev(sk_resampler_batch* b, float* out, size_t out_stream_stride, size_t out_ch_stride, size_t* n_out) {
+    if (!b) return SK_E_ARG;
+    sk_ctx* ctx = b->ctx;
+    if (n_out) *n_out = 0;
+    if (!out) SK_FAIL(ctx, SK_E_ARG, "null buffer");
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t remaining = b->pending;
+    const size_t lanes = b->n_streams * (size_t)b->channels;
+    // the zero padding becomes part of the next history: make it real
+    SK_CUDA(ctx, cudaMemset2DAsync(b->d_rows[b->cur] + 2 * SINC_LEN + remaining, b->row * sizeof(float), 0, (STREAM_CHUNK - remaining) * sizeof(float), lanes,
+                                   ctx->stream));
+    size_t trim = 0;
+    if (remaining > 0) trim = (size_t)llround(((double)(STREAM_CHUNK - remaining) * (double)b->out_rate) / (double)b->in_rate);
+    int rc = batch_run_chunks(b, 1, STREAM_CHUNK, out, out_stream_stride, out_ch_stride, trim, n_out);
+    if (rc) return rc;
+    return batch_carry(b, STREAM_CHUNK, STREAM_CHUNK);
+}

@@ -230,3 +230,30 @@ def test_general_ratio_many_lanes_bit_exact(oracle, rates, semantics):
         assert want.shape == (2, n_out)
         assert np.array_equal(_bits(got[s]), _bits(want)), f"stream {s} differs"
     print(f"[many lanes {i}->{o} {semantics}] fallback outputs {fb} of {S * 2 * n_out}")
+
+
+def _rubato_cases():
+    import glob
+    import os
+    from conftest import GOLDEN
+    return sorted(glob.glob(os.path.join(GOLDEN, "rubato", "*.out.f32")))
+
+
+@pytest.mark.skipif(not _rubato_cases(), reason="no rubato 0.14.1 dump under tests/golden/rubato (needs a Rust toolchain: see its README)")
+@pytest.mark.parametrize("path", _rubato_cases() or ["none"])
+def test_cuda_kernels_against_real_rubato_dump(ctx, path):
+    """the CUDA path against real rubato 0.14.1 output (rust/rubato-dump): north-star contract 1e-5 / 120 dB; reports bit-equality"""
+    import json
+    meta = json.load(open(path.replace(".out.f32", ".json")))
+    ch = meta["channels"]
+    x = np.fromfile(path.replace(".out.f32", ".in.f32"), "<f4").reshape(ch, -1)
+    want = np.fromfile(path, "<f4").reshape(ch, -1)
+    inter = np.ascontiguousarray(x.T).reshape(-1)
+    sem = capi.SEM_ONESHOT if meta["semantics"] == "oneshot" else capi.SEM_STREAMING
+    got = ctx.normalize_stream(inter.view(np.uint8), 32, capi.FMT_FLOAT, False, ch, capi.MODE_A, meta["in_rate"], meta["out_rate"], sem, capi.MIX_NONE)
+    assert got.shape == want.shape
+    err = np.max(np.abs(got.astype(np.float64) - want))
+    noise = np.sum((got.astype(np.float64) - want) ** 2)
+    snr = np.inf if noise == 0 else 10 * np.log10(np.sum(want.astype(np.float64) ** 2) / noise)
+    assert err <= 1e-5 and snr >= 120.0, (err, snr)
+    print("bit-identical to rubato:", bool(np.array_equal(_bits(got), _bits(want))))
