@@ -297,6 +297,26 @@ int  sk_g726_decode_batch_dev(sk_ctx*, int bits, int packing, const uint8_t* in,
 int  sk_g726_encode_batch_dev(sk_ctx*, int bits, int packing, int in_kind, const void* in, size_t in_stride, size_t n_streams, size_t n,
                               uint8_t* out, size_t out_stride, int32_t* state);
 
+/* ------------------------------------------------------------------ G.722 sub-band ADPCM */
+/* soundkit-g722/src/lib.rs:1-230 over `ezk-g722 0.1.1` libg722::{Decoder, Encoder}::new(Bitrate::Mode1_64000, false, false):
+ * ITU-T G.722 mode 1 (64 kbit/s), 16 kHz mono: one code byte <-> two samples.  The codec state (both band predictors + the
+ * 24-tap QMF delay line) is SK_G722_STATE_INTS int32 words, all zero at reset — the crate starts both bands from a zero scale
+ * factor, which is what the reference's golden WAV pins (see sk_g722.cu).  The Rust G722Encoder keeps an odd pending sample
+ * (:10-13, 83-117) and G722Decoder has no pending state; both stay in the host layer and hand whole pairs / bytes to these calls. */
+#define SK_G722_STATE_INTS 68
+void sk_g722_state_init(int32_t* state);
+/* G722Decoder::decode_{i16,i32,f32} (:161-232): out gets bytes * 2 elements */
+int  sk_g722_decode(sk_ctx*, int32_t* state, const uint8_t* in, size_t bytes, int out_kind, void* out);
+/* G722Encoder::encode_{i16,i32} on whole sample pairs (:83-122): n must be even, out gets n / 2 bytes */
+int  sk_g722_encode(sk_ctx*, int32_t* state, int in_kind, const void* in, size_t n, uint8_t* out);
+/* batched, device resident: n_streams independent streams (one thread per stream); in_stride / out_stride in bytes for code
+ * buffers and in ELEMENTS for sample buffers; state = [n_streams][SK_G722_STATE_INTS] device words carried across calls, or NULL
+ * to start every stream from the reset state and discard it */
+int  sk_g722_decode_batch_dev(sk_ctx*, const uint8_t* in, size_t in_stride, size_t n_streams, size_t bytes, int out_kind, void* out,
+                              size_t out_stride, int32_t* state);
+int  sk_g722_encode_batch_dev(sk_ctx*, int in_kind, const void* in, size_t in_stride, size_t n_streams, size_t n, uint8_t* out,
+                              size_t out_stride, int32_t* state);
+
 /* ------------------------------------------------------------------ 48 kHz stereo normalizer */
 /* StreamingStereo48kNormalizer (soundkit/src/audio_pipeline.rs:256-394): decoder-convention conversion, mono
  * duplicated / first two channels, finite_pcm clamp, 2-tap linear interpolation to 48 kHz over the whole-stream

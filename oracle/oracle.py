@@ -393,6 +393,31 @@ class G726:
         return None if n == ERR else out[:n]
 
 
+class G722:
+    """G.722 64 kbit/s restatement (g722.c): one object = one stream's codec state"""
+
+    def __init__(self):
+        L = lib()
+        L.sko_g722_decode.restype = C.c_size_t
+        L.sko_g722_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.sko_g722_encode.restype = C.c_size_t
+        L.sko_g722_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        self.state = np.zeros(114, np.int32)
+        L.sko_g722_state_init(_ptr(self.state))
+
+    def decode(self, data):
+        d = _bytes(data)
+        out = np.empty(d.size * 2, np.int16)
+        n = lib().sko_g722_decode(_ptr(self.state), _ptr(d), d.size, _ptr(out))
+        return out[:n]
+
+    def encode(self, samples):
+        s = np.ascontiguousarray(samples, np.int16)
+        out = np.empty(s.size // 2 + 1, np.uint8)
+        n = lib().sko_g722_encode(_ptr(self.state), _ptr(s), s.size, _ptr(out))
+        return out[:n]
+
+
 class Normalizer48k:
     """StreamingStereo48kNormalizer restatement (soundkit/src/audio_pipeline.rs:256-394).  push/finish return
     (left, right) float32 arrays (empty = Ok(None)) or raise ValueError(code) for the reference's Err arms."""

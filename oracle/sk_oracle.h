@@ -172,6 +172,12 @@ int sko_norm48k_push(sko_norm48k*, const uint8_t* data, size_t bytes, int bits, 
                      float* left, float* right, size_t cap, size_t* n_out);
 int sko_norm48k_finish(sko_norm48k*, float* left, float* right, size_t cap, size_t* n_out);
 
+/* ---- 8(f) next row 4': G.722 64 kbit/s sub-band ADPCM (soundkit-g722/src/lib.rs:1-230 over ezk-g722 0.1.1), g722.c ---- */
+#define SKO_G722_STATE_INTS 114
+void   sko_g722_state_init(int32_t* state);
+size_t sko_g722_decode(int32_t* state, const uint8_t* in, size_t bytes, int16_t* out);
+size_t sko_g722_encode(int32_t* state, const int16_t* in, size_t n, uint8_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,7 @@ FLAT_OPS = ("i16le_to_f32", "s16le_to_i16", "s16be_to_i16", "s16le_to_i32", "s24
 FLAT_OP = {name: i for i, name in enumerate(FLAT_OPS)}
 G726_GROUP = {2: (4, 1), 3: (8, 3), 4: (2, 1), 5: (8, 5)}  # code bits -> (samples, bytes) per group
 G726_LEFT, G726_RIGHT = 0, 1
+G722_STATE_INTS = 68
 
 EXPORTS = (
     "sk_abi_version", "sk_ctx_create", "sk_ctx_destroy", "sk_last_error", "sk_ctx_set_stream", "sk_ctx_reset_stream",
@@ -46,6 +47,7 @@ EXPORTS = (
     "sk_norm48k_output_frames", "sk_norm48k_source_sample_rate", "sk_norm48k_source_channels", "sk_norm48k_max_output",
     "sk_normalize48k_out_frames", "sk_normalize48k_batch_dev",
     "sk_g726_state_init", "sk_g726_decode", "sk_g726_encode", "sk_g726_decode_batch_dev", "sk_g726_encode_batch_dev",
+    "sk_g722_state_init", "sk_g722_decode", "sk_g722_encode", "sk_g722_decode_batch_dev", "sk_g722_encode_batch_dev",
 )
 
 
@@ -150,6 +152,11 @@ def load():
         "sk_g726_encode": (i, [vp, i, i, vp, i, vp, sz, vp]),
         "sk_g726_decode_batch_dev": (i, [vp, i, i, vp, sz, sz, sz, i, vp, sz, vp]),
         "sk_g726_encode_batch_dev": (i, [vp, i, i, i, vp, sz, sz, sz, vp, sz, vp]),
+        "sk_g722_state_init": (None, [vp]),
+        "sk_g722_decode": (i, [vp, vp, vp, sz, i, vp]),
+        "sk_g722_encode": (i, [vp, vp, i, vp, sz, vp]),
+        "sk_g722_decode_batch_dev": (i, [vp, vp, sz, sz, sz, i, vp, sz, vp]),
+        "sk_g722_encode_batch_dev": (i, [vp, i, vp, sz, sz, sz, vp, sz, vp]),
     }
     for name in EXPORTS:
         fn = getattr(L, name)  # AttributeError if the header and the library disagree
@@ -417,6 +424,33 @@ class Context:
     def g726_encode_batch_dev(self, bits, packing, kind, d_in, in_stride, n_streams, n, d_out, out_stride, d_state=None):
         self._ck(self.L.sk_g726_encode_batch_dev(self.h, bits, packing, kind, _p(d_in), in_stride, n_streams, n, _p(d_out), out_stride,
                                                  _p(d_state)))
+
+    # -- G.722 (codec state: numpy int32[G722_STATE_INTS], all zero at reset)
+    def g722_state(self):
+        st = np.zeros(G722_STATE_INTS, np.int32)
+        self.L.sk_g722_state_init(_p(st))
+        return st
+
+    def g722_decode(self, state, data, kind=KIND_I16):
+        d = _u8(data)
+        out = np.empty(d.size * 2, {KIND_I16: np.int16, KIND_I32: np.int32, KIND_F32: np.float32}[kind])
+        self._ck(self.L.sk_g722_decode(self.h, _p(state), _p(d), d.size, kind, _p(out)))
+        return out
+
+    def g722_encode(self, state, samples):
+        s = np.ascontiguousarray(samples)
+        kind = KIND_I16 if s.dtype == np.int16 else KIND_I32
+        out = np.empty(s.size // 2, np.uint8)
+        self._ck(self.L.sk_g722_encode(self.h, _p(state), kind, _p(s), s.size, _p(out)))
+        return out
+
+    def g722_decode_batch_dev(self, d_in, in_stride, n_streams, nbytes, kind, d_out, out_stride, d_state=None):
+        self._ck(self.L.sk_g722_decode_batch_dev(self.h, C.c_void_p(d_in.data_ptr()), in_stride, n_streams, nbytes, kind, C.c_void_p(d_out.data_ptr()),
+                                                 out_stride, C.c_void_p(d_state.data_ptr()) if d_state is not None else None))
+
+    def g722_encode_batch_dev(self, kind, d_in, in_stride, n_streams, n, d_out, out_stride, d_state=None):
+        self._ck(self.L.sk_g722_encode_batch_dev(self.h, kind, C.c_void_p(d_in.data_ptr()), in_stride, n_streams, n, C.c_void_p(d_out.data_ptr()),
+                                                 out_stride, C.c_void_p(d_state.data_ptr()) if d_state is not None else None))
 
     # -- 48 kHz stereo normalizer (StreamingStereo48kNormalizer)
     def normalizer48k(self):

@@ -201,6 +201,40 @@ PYBIND11_MODULE(_host, m) {
                 auto b = to_bytes(in); std::vector<float> out(cap); size_t n = d.decode_f32(b.data(), b.size(), out.data(), cap, fec); out.resize(n); return arr(out); });
     }
 
+    // ---- soundkit_g722
+    {
+        auto g2 = m.def_submodule("g722");
+        using namespace soundkit_g722;
+        g2.attr("G722_SAMPLE_RATE") = G722_SAMPLE_RATE;
+        g2.attr("G722_CHANNELS") = G722_CHANNELS;
+        py::class_<G722Encoder>(g2, "G722Encoder")
+            .def(py::init<>())
+            .def(py::init<uint32_t, uint32_t, uint32_t, uint32_t, uint32_t>())
+            .def_static("new_64k", &G722Encoder::new_64k)
+            .def("reset", &G722Encoder::reset)
+            .def("encode_i16", [](G722Encoder& e, const std::vector<int16_t>& in, size_t cap) {
+                std::vector<uint8_t> out(cap); size_t n = e.encode_i16(in.data(), in.size(), out.data(), cap); out.resize(n);
+                return py::bytes((const char*)out.data(), out.size()); })
+            .def("encode_i32", [](G722Encoder& e, const std::vector<int32_t>& in, size_t cap) {
+                std::vector<uint8_t> out(cap); size_t n = e.encode_i32(in.data(), in.size(), out.data(), cap); out.resize(n);
+                return py::bytes((const char*)out.data(), out.size()); })
+            .def("encode_to_vec", [](G722Encoder& e, const std::vector<int16_t>& in) {
+                std::vector<uint8_t> out; e.encode_to_vec(in, out); return py::bytes((const char*)out.data(), out.size()); })
+            .def("flush_to_vec", [](G722Encoder& e) { std::vector<uint8_t> out; e.flush_to_vec(out); return py::bytes((const char*)out.data(), out.size()); })
+            .def("flush_into", [](G722Encoder& e, size_t cap) { std::vector<uint8_t> out(cap); size_t n = e.flush_into(out.data(), cap); out.resize(n);
+                return py::bytes((const char*)out.data(), out.size()); });
+        py::class_<G722Decoder>(g2, "G722Decoder")
+            .def(py::init<>())
+            .def_static("new_64k", &G722Decoder::new_64k)
+            .def("sample_rate", &G722Decoder::sample_rate).def("channels", &G722Decoder::channels)
+            .def("decode_i16", [](G722Decoder& d, const py::buffer& in, size_t cap, bool fec) {
+                auto b = to_bytes(in); std::vector<int16_t> out(cap); size_t n = d.decode_i16(b.data(), b.size(), out.data(), cap, fec); out.resize(n); return arr(out); })
+            .def("decode_i32", [](G722Decoder& d, const py::buffer& in, size_t cap, bool fec) {
+                auto b = to_bytes(in); std::vector<int32_t> out(cap); size_t n = d.decode_i32(b.data(), b.size(), out.data(), cap, fec); out.resize(n); return arr(out); })
+            .def("decode_f32", [](G722Decoder& d, const py::buffer& in, size_t cap, bool fec) {
+                auto b = to_bytes(in); std::vector<float> out(cap); size_t n = d.decode_f32(b.data(), b.size(), out.data(), cap, fec); out.resize(n); return arr(out); });
+    }
+
     // ---- soundkit_decoder output stage
     auto d = m.def_submodule("decoder");
     using namespace soundkit_decoder;

@@ -567,6 +567,90 @@ private:
 }  // namespace soundkit_g726
 
 // ---- soundkit-decoder output-conversion stage (soundkit-decoder/src/lib.rs) ---------------------------------------
+namespace soundkit_g722 {  // soundkit-g722/src/lib.rs
+using soundkit::Error;
+using soundkit::Gpu;
+constexpr uint32_t G722_SAMPLE_RATE = 16000;  // :6
+constexpr uint8_t G722_CHANNELS = 1;          // :7
+inline size_t max_encoded_len(size_t input_samples) { return (input_samples + 1) / 2; }  // :234-236
+
+class G722Encoder {  // :9-129, impl soundkit::audio_packet::Encoder; the odd pending sample stays here
+public:
+    static G722Encoder new_64k() { return G722Encoder(); }
+    G722Encoder() { sk_g722_state_init(state_); }
+    // Encoder::new(sample_rate, bits_per_sample, channels, frame_size, bitrate), :68-76: every argument ignored
+    G722Encoder(uint32_t, uint32_t, uint32_t, uint32_t, uint32_t) : G722Encoder() {}
+    void init() {}
+    void reset() { sk_g722_state_init(state_); has_pending_ = false; }  // :124-128
+    size_t encode_i16(const int16_t* input, size_t n, uint8_t* output, size_t cap) {  // :83-117
+        const size_t total = n + (has_pending_ ? 1 : 0);
+        const size_t complete = total - (total % 2), required = complete / 2;
+        if (cap < required) throw Error("Output buffer too small for G.722 encode: need " + std::to_string(required) + ", have " + std::to_string(cap));
+        if (total < 2) {
+            if (!has_pending_ && n) { pending_ = input[0]; has_pending_ = true; }
+            return 0;
+        }
+        std::vector<int16_t> samples;
+        samples.reserve(complete + 1);
+        if (has_pending_) { samples.push_back(pending_); has_pending_ = false; }
+        samples.insert(samples.end(), input, input + n);
+        if (samples.size() % 2) { pending_ = samples.back(); has_pending_ = true; samples.pop_back(); }
+        Gpu::check(sk_g722_encode(Gpu::ctx(), state_, SK_KIND_I16, samples.data(), samples.size(), output));
+        return samples.size() / 2;
+    }
+    size_t encode_i32(const int32_t* input, size_t n, uint8_t* output, size_t cap) {  // :119-122
+        std::vector<int16_t> s(n);
+        for (size_t i = 0; i < n; i++) s[i] = (int16_t)(input[i] >> 16);
+        return encode_i16(s.data(), n, output, cap);
+    }
+    size_t encode_to_vec(const std::vector<int16_t>& input, std::vector<uint8_t>& output) {  // :23-31
+        const size_t start = output.size();
+        std::vector<uint8_t> scratch(max_encoded_len(input.size() + (has_pending_ ? 1 : 0)));
+        const size_t w = encode_i16(input.data(), input.size(), scratch.data(), scratch.size());
+        output.insert(output.end(), scratch.begin(), scratch.begin() + w);
+        return output.size() - start;
+    }
+    size_t flush_into(uint8_t* output, size_t cap) {  // :33-46: the pending sample is paired with a zero
+        if (!has_pending_) return 0;
+        if (cap == 0) throw Error("Output buffer too small for G.722 flush: need 1, have 0");
+        const int16_t pair[2] = {pending_, 0};
+        has_pending_ = false;
+        Gpu::check(sk_g722_encode(Gpu::ctx(), state_, SK_KIND_I16, pair, 2, output));
+        return 1;
+    }
+    size_t flush_to_vec(std::vector<uint8_t>& output) {  // :48-54
+        const size_t start = output.size();
+        output.resize(start + 1, 0);
+        const size_t w = flush_into(output.data() + start, 1);
+        output.resize(start + w);
+        return w;
+    }
+private:
+    int32_t state_[SK_G722_STATE_INTS];
+    int16_t pending_ = 0;
+    bool has_pending_ = false;
+};
+
+class G722Decoder {  // :131-232, impl soundkit::audio_packet::Decoder (fec ignored)
+public:
+    static G722Decoder new_64k() { return G722Decoder(); }
+    G722Decoder() { sk_g722_state_init(state_); }
+    uint32_t sample_rate() const { return G722_SAMPLE_RATE; }
+    uint8_t channels() const { return G722_CHANNELS; }
+    size_t decode_i16(const uint8_t* in, size_t n, int16_t* out, size_t cap, bool) { return run(in, n, out, cap, SK_KIND_I16); }
+    size_t decode_i32(const uint8_t* in, size_t n, int32_t* out, size_t cap, bool) { return run(in, n, out, cap, SK_KIND_I32); }
+    size_t decode_f32(const uint8_t* in, size_t n, float* out, size_t cap, bool) { return run(in, n, out, cap, SK_KIND_F32); }
+private:
+    size_t run(const uint8_t* in, size_t n, void* out, size_t cap, int kind) {
+        const size_t required = n * 2;
+        if (cap < required) throw Error("Output buffer too small for G.722 decode: need " + std::to_string(required) + ", have " + std::to_string(cap));
+        if (n) Gpu::check(sk_g722_decode(Gpu::ctx(), state_, in, n, kind, out));
+        return required;
+    }
+    int32_t state_[SK_G722_STATE_INTS];
+};
+}  // namespace soundkit_g722
+
 namespace soundkit_decoder {
 using soundkit::AudioData;
 using soundkit::EncodingFlag;

@@ -109,6 +109,10 @@ def main():
     for r in ("16", "24", "32", "40"):
         put(f"g726_{r}.g726", rd(f"testdata/g726/{NAME}_{r}.g726"))
         put(f"g726_{r}.decoded.s16le", wav_payload(os.path.join(REF, f"golden/g726/{NAME}_{r}.decoded.wav")))
+    # G.722 fixture and the WAV the reference's own decoder wrote (soundkit-g722/src/lib.rs:330-360): pins the sub-band ADPCM
+    # decoder restatement bit for bit, including the crate's zero reset state
+    put("g722.g722", rd(f"testdata/g722/{NAME}.g722"))
+    put("g722.decoded.s16le", wav_payload(os.path.join(REF, f"golden/g722/{NAME}.decoded.wav")))
 
     endian = {}
     for name, kind, bps, be in (("pcm-s16be.caf", "s16", 2, True), ("pcm-s24le.caf", "s24", 3, False),

@@ -546,3 +546,69 @@ def test_apply_output_options_mid_stream_errors_and_surround(oracle):
             want += oracle.f32_channels_to_bytes(oracle.downmix_channels(part, 2), 24, 0).tobytes()
     assert all(f.bits_per_sample() == 24 and f.channel_count() == 2 and f.sampling_rate() == 24000 for f in frames)
     assert len(got) == len(want)
+
+
+# ---------------------------------------------------------------------------------------------- soundkit_g722 (8f row 4)
+G2 = H.g722
+
+
+def g722_samples():  # soundkit-g722/src/lib.rs:238-245
+    idx = np.arange(161, dtype=np.float32)
+    phase = idx / np.float32(160.0) * np.float32(2.0 * math.pi) * np.float32(3.0)
+    return (np.sin(phase).astype(np.float32) * np.float32(12000.0)).astype(np.int16).tolist()
+
+
+def test_g722_encoder_buffer_checks_and_pending_sample_need_no_device():  # :83-100, 33-46: checked before the ABI is crossed
+    e = G2.G722Encoder.new_64k()
+    with pytest.raises(H.SoundkitError, match=r"Output buffer too small for G\.722 encode: need 2, have 1"):
+        e.encode_i16([1, 2, 3, 4], 1)
+    assert e.encode_i16([7], 0) == b""           # a single sample is kept pending, nothing is encoded
+    assert e.encode_i16([], 0) == b""
+    d = G2.G722Decoder.new_64k()
+    assert (d.sample_rate(), d.channels()) == (16000, 1)
+    with pytest.raises(H.SoundkitError, match=r"Output buffer too small for G\.722 decode: need 6, have 5"):
+        d.decode_i16(bytes(3), 5, False)
+    e2 = G2.G722Encoder(16000, 16, 1, 320, 64000)  # Encoder::new ignores every argument (:68-76)
+    assert e2.flush_to_vec() == b""
+
+
+@pytest.mark.gpu
+def test_g722_streaming_encoder_matches_padded_whole_encode():  # :246-268
+    x = g722_samples()
+    padded = x + [0]
+    whole = G2.G722Encoder.new_64k().encode_i16(padded, len(padded) // 2)
+    enc = G2.G722Encoder.new_64k()
+    chunked = b""
+    for i in range(0, len(x), 5):
+        chunked += enc.encode_i16(x[i:i + 5], 8)
+    chunked += enc.flush_to_vec()
+    assert chunked == whole and len(whole) == 81
+    with pytest.raises(H.SoundkitError, match=r"Output buffer too small for G\.722 flush: need 1, have 0"):
+        e = G2.G722Encoder.new_64k()
+        e.encode_i16([5], 0)
+        e.flush_into(0)
+
+
+@pytest.mark.gpu
+def test_g722_streaming_decoder_matches_whole_decode_and_trait_outputs():  # :270-328
+    x = g722_samples()
+    enc = G2.G722Encoder.new_64k()
+    encoded = enc.encode_to_vec(x) + enc.flush_to_vec()
+    whole = G2.G722Decoder.new_64k().decode_i16(encoded, len(encoded) * 2, False)
+    dec = G2.G722Decoder.new_64k()
+    chunked = np.concatenate([dec.decode_i16(encoded[i:i + 3], 6, False) for i in range(0, len(encoded), 3)])
+    assert np.array_equal(chunked, whole)
+    i32 = G2.G722Decoder.new_64k().decode_i32(encoded, len(encoded) * 2, False)
+    f32 = G2.G722Decoder.new_64k().decode_f32(encoded, len(encoded) * 2, False)
+    assert np.array_equal(i32, whole.astype(np.int32) << 16)
+    assert np.max(np.abs(f32 - whole.astype(np.float32) / np.float32(32768.0))) < np.finfo(np.float32).eps
+
+
+@pytest.mark.gpu
+def test_g722_decode_fixture_golden():  # :330-360: 127-byte chunks into a 254-sample scratch
+    raw = golden("g722.g722")
+    want = np.frombuffer(golden("g722.decoded.s16le"), "<i2")
+    dec = G2.G722Decoder.new_64k()
+    got = np.concatenate([dec.decode_i16(raw[i:i + 127], 254, False) for i in range(0, len(raw), 127)])
+    assert got.size == len(raw) * 2 and np.any(got != 0)
+    assert np.array_equal(got, want)
