@@ -33,6 +33,21 @@ ENDIAN_HASHES = {  # LE-canonical payload hashes asserted by the reference tests
 }
 
 
+def aifc_ssnd(path):
+    """sound data of an AIFF-C file: FORM/AIFC chunk walk, SSND body after its offset / blockSize words"""
+    b = open(path, "rb").read()
+    assert b[:4] == b"FORM" and b[8:12] == b"AIFC"
+    pos = 12
+    while pos + 8 <= len(b):
+        cid, size = b[pos:pos + 4], struct.unpack(">I", b[pos + 4:pos + 8])[0]
+        body = b[pos + 8:pos + 8 + size]
+        if cid == b"SSND":
+            off = struct.unpack(">I", body[:4])[0]
+            return body[8 + off:]
+        pos += 8 + size + (size & 1)
+    raise ValueError("no SSND chunk in " + path)
+
+
 def caf_payload(path):
     b = open(path, "rb").read()
     assert b[:4] == b"caff"
@@ -114,6 +129,17 @@ def main():
     put("g722.g722", rd(f"testdata/g722/{NAME}.g722"))
     put("g722.decoded.s16le", wav_payload(os.path.join(REF, f"golden/g722/{NAME}.decoded.wav")))
 
+    # AIFF-C mu-law / A-law (soundkit-aiff/src/lib.rs:529-540 decodes the SSND payload with audio-codec-algorithms' decode_ulaw /
+    # decode_alaw): the payloads of testdata/aifc/stream-{ulaw,alaw}.aifc are byte-identical to the raw G.711 fixtures above, whose
+    # decodes the reference holds as golden WAVs -> no second copy, the identity is recorded
+    aifc = {}
+    for law in ("ulaw", "alaw"):
+        payload = aifc_ssnd(os.path.join(REF, f"testdata/aifc/stream-{law}.aifc"))
+        raw = rd(f"testdata/g711_{law}/{NAME}.{law}")
+        assert payload == raw, law
+        aifc[f"stream-{law}.aifc"] = {"ssnd_sha256": hashlib.sha256(payload).hexdigest(), "same_bytes_as": f"g711_{law}.{law}",
+                                      "decoded_golden": f"g711_{law}.decoded.s16le"}
+
     endian = {}
     for name, kind, bps, be in (("pcm-s16be.caf", "s16", 2, True), ("pcm-s24le.caf", "s24", 3, False),
                                 ("pcm-s32be.caf", "s32", 4, True), ("pcm-f32le.caf", "f32", 4, False)):
@@ -134,7 +160,7 @@ def main():
         endian[out] = {"kind": kind, "bytes_per_sample": bps, "big_endian": be, "le_sha256": ENDIAN_HASHES[kind]}
 
     with open(os.path.join(HERE, "MANIFEST.json"), "w") as f:
-        json.dump({"files": files, "endian_payloads": endian}, f, indent=1, sort_keys=True)
+        json.dump({"files": files, "endian_payloads": endian, "aifc_g711": aifc}, f, indent=1, sort_keys=True)
     print(f"wrote {len(files)} fixtures")
 
 

@@ -492,3 +492,23 @@ def test_g722_encoder_streaming_and_round_trip(oracle):
     r = oracle.G722().decode(oracle.G722().encode(y)).astype(np.float64)
     c = np.corrcoef(y[2000:15000 - 22].astype(np.float64), r[2022:15000])[0, 1]
     assert c > 0.98, c
+
+
+# ---------------------------------------------------------------------------------------------- AIFF-C mu-law / A-law
+def test_aifc_g711_payloads_are_the_g711_fixtures_and_standard_tables_agree(oracle):
+    """soundkit-aiff/src/lib.rs:529-540 decodes AIFF-C 'ulaw' / 'alaw' sound data with audio-codec-algorithms' decode_ulaw /
+    decode_alaw (the ITU-T G.711 tables), not with soundkit-g711.  Two facts make the device G.711 decoder the drop-in for it:
+    (1) the SSND payloads of testdata/aifc/stream-{ulaw,alaw}.aifc are byte-identical to the raw G.711 fixtures (recorded by
+    make_golden.py), whose decodes the reference holds as golden WAVs; (2) an independent implementation of the standard tables
+    (CPython's audioop, itself Sun's g711.c) equals soundkit-g711's decoder on all 256 codes of both laws."""
+    man = json.load(open(os.path.join(GOLDEN, "MANIFEST.json")))["aifc_g711"]
+    for law, name in ((0, "ulaw"), (1, "alaw")):
+        m = man[f"stream-{name}.aifc"]
+        raw = golden(m["same_bytes_as"])
+        assert hashlib.sha256(raw).hexdigest() == m["ssnd_sha256"]
+        want = np.frombuffer(golden(m["decoded_golden"]), "<i2")
+        assert np.array_equal(oracle.g711_decode(law, raw), want)
+    audioop = pytest.importorskip("audioop", reason="removed from CPython 3.13")
+    codes = np.arange(256, dtype=np.uint8)
+    assert np.array_equal(np.frombuffer(audioop.ulaw2lin(codes.tobytes(), 2), "<i2"), oracle.g711_decode(0, codes))
+    assert np.array_equal(np.frombuffer(audioop.alaw2lin(codes.tobytes(), 2), "<i2"), oracle.g711_decode(1, codes))
