@@ -149,6 +149,11 @@ int sk_deinterleave(sk_ctx*, int kind, const uint8_t* in, size_t bytes, int chan
                     size_t* frames);
 /* interleave_vecs_i16 (audio_bytes.rs:250-262): planar [channels][frames] i16 -> LE bytes */
 int sk_interleave_i16(sk_ctx*, const int16_t* planar, int channels, size_t frames, uint8_t* out);
+/* WavStreamEncoder::push_planar_{i16,i32,f32} (soundkit/src/wav.rs:444-494; also PcmData -> bytes in push, :496-540): planar
+ * [channels][frames] elements of elem_bytes = 2 (i16) or 4 (i32 / f32) -> interleaved little-endian frames.  A bit copy (i32
+ * samples and NaN payloads pass unchanged); validation (format, channel count, reserve_chunk) stays in the host layer. */
+int sk_interleave_planar(sk_ctx*, int elem_bytes, const void* planar, int channels, size_t frames, uint8_t* out);
+int sk_interleave_planar_dev(sk_ctx*, int elem_bytes, const void* planar, int channels, size_t frames, uint8_t* out);
 /* stereo_to_mono_{take_left,avg} (audio_bytes.rs:317-373): avg != 0 -> ((l + r) / 2) truncating */
 int sk_stereo_to_mono_i16(sk_ctx*, int avg, const int16_t* in, size_t n, int16_t* out);
 

@@ -35,7 +35,7 @@ EXPORTS = (
     "sk_ctx_launch_count", "sk_ctx_set_batch_slab_bytes", "sk_ctx_resample_fallback_outputs", "sk_ctx_measure_ffma_peak", "sk_ctx_measure_ffma_peaks", "sk_ctx_poison_shared_memory",
     "sk_g711_decode", "sk_g711_decode_dev", "sk_g711_encode", "sk_g711_encode_dev",
     "sk_pcm_flat_convert", "sk_pcm_flat_convert_dev", "sk_flat_op_widths", "sk_dvd_lpcm_unpack", "sk_dvd_lpcm_unpack_dev",
-    "sk_deinterleave", "sk_interleave_i16",
+    "sk_deinterleave", "sk_interleave_i16", "sk_interleave_planar", "sk_interleave_planar_dev",
     "sk_stereo_to_mono_i16", "sk_pcm_to_planar_f32", "sk_pcm_to_planar_f32_dev", "sk_planar_f32_to_pcm",
     "sk_planar_f32_to_pcm_dev", "sk_pcm_narrow_i16", "sk_mixdown_mono", "sk_mixdown_mono_dev", "sk_downmix_stereo",
     "sk_resampler_create", "sk_resampler_destroy", "sk_resampler_out_max", "sk_resampler_last_index",
@@ -108,6 +108,8 @@ def load():
         "sk_dvd_lpcm_unpack_dev": (i, [vp, vp, sz, i, i, vp]),
         "sk_deinterleave": (i, [vp, i, vp, sz, i, vp, psz]),
         "sk_interleave_i16": (i, [vp, vp, i, sz, vp]),
+        "sk_interleave_planar": (i, [vp, i, vp, i, sz, vp]),
+        "sk_interleave_planar_dev": (i, [vp, i, vp, i, sz, vp]),
         "sk_stereo_to_mono_i16": (i, [vp, i, vp, sz, vp]),
         "sk_pcm_to_planar_f32": (i, [vp, vp, sz, i, i, i, i, i, vp, sz, psz]),
         "sk_pcm_to_planar_f32_dev": (i, [vp, vp, sz, sz, sz, i, i, i, i, i, vp, sz]),
@@ -314,6 +316,14 @@ class Context:
         p = np.ascontiguousarray(planar, np.int16)
         out = np.empty(p.size * 2, np.uint8)
         self._ck(self.L.sk_interleave_i16(self.h, _p(p), p.shape[0], p.shape[1], _p(out)))
+        return out
+
+    def interleave_planar(self, planar):
+        """WavStreamEncoder::push_planar_{i16,i32,f32}: [channels][frames] of i16 / i32 / f32 -> interleaved LE bytes (bit copy)"""
+        p = np.ascontiguousarray(planar)
+        assert p.ndim == 2 and p.dtype.itemsize in (2, 4)
+        out = np.empty(p.size * p.dtype.itemsize, np.uint8)
+        self._ck(self.L.sk_interleave_planar(self.h, p.dtype.itemsize, _p(p), p.shape[0], p.shape[1], _p(out)))
         return out
 
     def stereo_to_mono_i16(self, samples, avg):

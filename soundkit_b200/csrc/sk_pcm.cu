@@ -898,6 +898,37 @@ extern "C" int sk_interleave_i16(sk_ctx* ctx, const int16_t* planar, int channel
     return sk_d2h(ctx, out, ctx->d_out, bytes);
 }
 
+// WavStreamEncoder::push_planar_{i16,i32,f32} (soundkit/src/wav.rs:444-494): planar [channels][frames] elements of 2 or 4 bytes ->
+// interleaved little-endian frames.  A bit copy: 4-byte elements take the PCMFloat interleaver (no arithmetic touches the words, so
+// i32 samples and NaN payloads pass unchanged), 2-byte elements the i16 interleaver.
+extern "C" int sk_interleave_planar_dev(sk_ctx* ctx, int elem_bytes, const void* planar, int channels, size_t frames, uint8_t* out) {
+    if (!ctx) return SK_E_ARG;
+    if (elem_bytes != 2 && elem_bytes != 4) SK_FAIL(ctx, SK_E_ARG, "planar elements must be 2 or 4 bytes wide, got %d", elem_bytes);
+    if (channels <= 0 || channels > 255) SK_FAIL(ctx, SK_E_ARG, "Channel count must be > 0");
+    if (!frames) return SK_OK;
+    if (!planar || !out) SK_FAIL(ctx, SK_E_ARG, "null buffer");
+    if (elem_bytes == 4) return sk_planar_f32_to_pcm_dev(ctx, (const float*)planar, frames, channels, 32, SK_FMT_FLOAT, out);
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    interleave_i16_kernel<<<grid_for(ctx, frames * channels, 256), 256, 0, ctx->stream>>>((const int16_t*)planar, channels, frames, (int16_t*)out);
+    SK_LAUNCH_CHECK(ctx);
+    return SK_OK;
+}
+extern "C" int sk_interleave_planar(sk_ctx* ctx, int elem_bytes, const void* planar, int channels, size_t frames, uint8_t* out) {
+    if (!ctx) return SK_E_ARG;
+    if (elem_bytes != 2 && elem_bytes != 4) SK_FAIL(ctx, SK_E_ARG, "planar elements must be 2 or 4 bytes wide, got %d", elem_bytes);
+    if (channels <= 0 || channels > 255) SK_FAIL(ctx, SK_E_ARG, "Channel count must be > 0");
+    if (!frames) return SK_OK;
+    if (!planar || !out) SK_FAIL(ctx, SK_E_ARG, "null buffer");
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = frames * (size_t)channels * (size_t)elem_bytes;
+    int rc;
+    if ((rc = sk_ensure_dev_in(ctx, bytes))) return rc;
+    if ((rc = sk_ensure_dev_out(ctx, bytes))) return rc;
+    if ((rc = sk_h2d(ctx, ctx->d_in, planar, bytes))) return rc;
+    if ((rc = sk_interleave_planar_dev(ctx, elem_bytes, ctx->d_in, channels, frames, (uint8_t*)ctx->d_out))) return rc;
+    return sk_d2h(ctx, out, ctx->d_out, bytes);
+}
+
 __global__ void stereo_to_mono_kernel(const uint32_t* __restrict__ in, size_t frames, int avg, int16_t* __restrict__ out) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < frames; i += (size_t)gridDim.x * blockDim.x) {
         uint32_t fr = in[i];

@@ -898,3 +898,19 @@ def test_resamplers_do_not_read_unstaged_shared_memory(oracle, pattern):
     assert np.array_equal(np.concatenate([gl, fl]).view(np.uint32), wl.view(np.uint32))
     assert np.array_equal(np.concatenate([gr, fr]).view(np.uint32), wr.view(np.uint32))
     c.close()
+
+
+@pytest.mark.parametrize("dtype", [np.int16, np.int32, np.float32])
+@pytest.mark.parametrize("channels,frames", [(1, 0), (1, 5), (2, 4096), (2, 100003), (3, 1000), (6, 777)])
+def test_push_planar_interleave_is_a_bit_copy(ctx, dtype, channels, frames):
+    """WavStreamEncoder::push_planar_{i16,i32,f32} (soundkit/src/wav.rs:444-494): out[(f * ch + c)] = planar[c * frames + f], little
+    endian; i32 values and float NaN payloads must survive untouched"""
+    if dtype == np.float32:
+        bits = RNG.integers(0, 2 ** 32, (channels, frames), dtype=np.uint64).astype(np.uint32)  # every bit pattern incl. NaNs / Infs
+        planar = bits.view(np.float32)
+    else:
+        info = np.iinfo(dtype)
+        planar = RNG.integers(info.min, info.max + 1, (channels, frames), dtype=np.int64).astype(dtype)
+    got = ctx.interleave_planar(planar)
+    want = np.ascontiguousarray(planar.T).view(np.uint8).reshape(-1)
+    assert np.array_equal(got, want)
