@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--streams", type=int, default=32, help="streams per GPU per step (one wave)")
     ap.add_argument("--seconds", type=float, default=600.0, help="stream length in seconds")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary kernel measurements")
-    ap.add_argument("--extras", default=None, help="comma list of extras groups to run (g711,convert,bytes,flat,g726,norm48k,resample,latency,stream)")
+    ap.add_argument("--extras", default=None, help="comma list of extras groups to run (g711,convert,bytes,flat,g726,g722,norm48k,resample,latency,stream)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     return ap.parse_args()
 
@@ -283,6 +283,16 @@ def extras(ctx, torch, peaks, only=None):
         b, m = timed(lambda: ctx.g726_encode_batch_dev(4, 0, capi.KIND_I16, pcm, n, S, n, codes, n // 2), reps=3)
         res["g726_32k_encode_i16"] = {"Msamples/s": S * n / b / 1e6, "GB/s": S * n * 2.5 / b / 1e9, "streams": S, "median": {"Msamples/s": S * n / m / 1e6}}
         del codes, pcm
+    if want("g722"):
+        # G.722 64 kbit/s decode/encode, 65 536 wideband telephony streams x 1 s (one thread per stream; latency bound)
+        S, nb = 65536, 8000
+        codes = torch.randint(0, 256, (S, nb), dtype=torch.uint8, device="cuda")
+        pcm = torch.empty((S, 2 * nb), dtype=torch.int16, device="cuda")
+        b, m = timed(lambda: ctx.g722_decode_batch_dev(codes, nb, S, nb, capi.KIND_I16, pcm, 2 * nb), reps=3)
+        res["g722_64k_decode_i16"] = {"Msamples/s": S * 2 * nb / b / 1e6, "GB/s": S * nb * 5 / b / 1e9, "streams": S, "median": {"Msamples/s": S * 2 * nb / m / 1e6}}
+        b, m = timed(lambda: ctx.g722_encode_batch_dev(capi.KIND_I16, pcm, 2 * nb, S, 2 * nb, codes, nb), reps=3)
+        res["g722_64k_encode_i16"] = {"Msamples/s": S * 2 * nb / b / 1e6, "GB/s": S * nb * 5 / b / 1e9, "streams": S, "median": {"Msamples/s": S * 2 * nb / m / 1e6}}
+        del codes, pcm
     if want("norm48k"):
         # StreamingStereo48kNormalizer, 64 whole streams x 60 s s16le stereo 44.1 kHz -> f32 stereo 48 kHz
         S, frames, rate = 64, 2646000, 44100
@@ -298,7 +308,7 @@ def extras(ctx, torch, peaks, only=None):
         # common downsampling case 44.1k -> 16k).  P = 2: both interpolation products, 1027 flop per output sample.
         for in_rate, out_rate, sem, tag in ((44100, 48000, capi.SEM_ONESHOT, ""), (44100, 48000, capi.SEM_STREAMING, "_streaming"),
                                             (44100, 16000, capi.SEM_ONESHOT, "")):
-            S, frames = 16, 2646000
+            S, frames = 64, 2646000  # 64 streams x 2 channels = 128 lanes (configs[3] is 4096 streams: lane columns, no period structure needed)
             n_out = ctx.batch_plan(in_rate, out_rate, frames, sem)
             x = (torch.rand((S, frames * 2), device="cuda") - 0.5)
             o = torch.empty((S, 2, n_out), dtype=torch.float32, device="cuda")
@@ -524,7 +534,7 @@ def run_ours(args):
             del raw, out, h_in, h_out
             torch.cuda.empty_cache()
             barrier()
-            groups = only if only is not None else ["g711", "convert", "bytes", "flat", "g726", "norm48k", "resample", "stream", "latency"]
+            groups = only if only is not None else ["g711", "convert", "bytes", "flat", "g726", "g722", "norm48k", "resample", "stream", "latency"]
             mine = extras(ctx, torch, peaks, [x for x in groups if rank == 0 or x != "latency"])
         except Exception as e:  # extras must never cost the headline line
             mine = {"error": repr(e)}
