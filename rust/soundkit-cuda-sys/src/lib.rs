@@ -7,6 +7,7 @@ use std::os::raw::{c_char, c_double, c_float, c_int, c_void};
 
 #[repr(C)] pub struct sk_ctx { _private: [u8; 0] }
 #[repr(C)] pub struct sk_resampler { _private: [u8; 0] }
+#[repr(C)] pub struct sk_resampler_batch { _private: [u8; 0] }
 
 pub const SK_OK: c_int = 0;
 pub const SK_E_ARG: c_int = -1;
@@ -43,6 +44,7 @@ pub enum sk_flat_op {
 
 #[repr(C)] pub struct sk_norm48k { _private: [u8; 0] }
 pub const SK_G726_STATE_INTS: usize = 24;
+pub const SK_G722_STATE_INTS: usize = 68;
 
 #[repr(C)] #[derive(Clone, Copy, Debug)]
 pub struct sk_resample_params {
@@ -67,6 +69,8 @@ extern "C" {
     pub fn sk_ctx_reset_stream(ctx: *mut sk_ctx) -> c_int;
     pub fn sk_ctx_synchronize(ctx: *mut sk_ctx) -> c_int;
     pub fn sk_ctx_launch_count(ctx: *const sk_ctx) -> u64;
+    pub fn sk_ctx_set_batch_slab_bytes(ctx: *mut sk_ctx, bytes: usize) -> c_int;
+    pub fn sk_ctx_resample_fallback_outputs(ctx: *mut sk_ctx, count: *mut u64) -> c_int;
     pub fn sk_ctx_measure_ffma_peak(ctx: *mut sk_ctx, tflops: *mut c_double) -> c_int;
     pub fn sk_ctx_measure_ffma_peaks(ctx: *mut sk_ctx, scalar: *mut c_double, packed: *mut c_double) -> c_int;
     pub fn sk_ctx_poison_shared_memory(ctx: *mut sk_ctx, pattern: u32) -> c_int;
@@ -81,6 +85,8 @@ extern "C" {
     pub fn sk_flat_op_widths(op: c_int, in_width: *mut c_int, out_width: *mut c_int) -> c_int;
     pub fn sk_deinterleave(ctx: *mut sk_ctx, kind: c_int, input: *const u8, bytes: usize, channels: c_int, out: *mut c_void, frames: *mut usize) -> c_int;
     pub fn sk_interleave_i16(ctx: *mut sk_ctx, planar: *const i16, channels: c_int, frames: usize, out: *mut u8) -> c_int;
+    pub fn sk_interleave_planar(ctx: *mut sk_ctx, elem_bytes: c_int, planar: *const c_void, channels: c_int, frames: usize, out: *mut u8) -> c_int;
+    pub fn sk_interleave_planar_dev(ctx: *mut sk_ctx, elem_bytes: c_int, planar: *const c_void, channels: c_int, frames: usize, out: *mut u8) -> c_int;
     pub fn sk_stereo_to_mono_i16(ctx: *mut sk_ctx, avg: c_int, input: *const i16, n: usize, out: *mut i16) -> c_int;
     pub fn sk_pcm_to_planar_f32(ctx: *mut sk_ctx, input: *const u8, bytes: usize, bits: c_int, fmt: c_int, big_endian: c_int, channels: c_int,
                                 scale_mode: c_int, out: *mut c_float, frames_cap: usize, frames: *mut usize) -> c_int;
@@ -102,6 +108,18 @@ extern "C" {
     pub fn sk_resampler_process_partial(r: *mut sk_resampler, input_or_null: *const *const c_float, frames: usize, out: *const *mut c_float,
                                         n_out: *mut usize) -> c_int;
     pub fn sk_resampler_copy_table(r: *const sk_resampler, out65536: *mut c_float) -> c_int;
+
+    // N StreamingResamplers in lock step, device-resident state (soundkit-decoder/src/lib.rs:1917-2060)
+    pub fn sk_resampler_batch_create(ctx: *mut sk_ctx, in_rate: u32, out_rate: u32, channels: c_int, n_streams: usize, max_push_frames: usize,
+                                     out: *mut *mut sk_resampler_batch) -> c_int;
+    pub fn sk_resampler_batch_destroy(b: *mut sk_resampler_batch);
+    pub fn sk_resampler_batch_out_cap(b: *const sk_resampler_batch) -> usize;
+    pub fn sk_resampler_batch_pending(b: *const sk_resampler_batch) -> usize;
+    pub fn sk_resampler_batch_last_index(b: *const sk_resampler_batch) -> c_double;
+    pub fn sk_resampler_batch_process_dev(b: *mut sk_resampler_batch, input: *const c_float, in_stream_stride: usize, in_ch_stride: usize, frames: usize,
+                                          out: *mut c_float, out_stream_stride: usize, out_ch_stride: usize, n_out: *mut usize) -> c_int;
+    pub fn sk_resampler_batch_flush_dev(b: *mut sk_resampler_batch, out: *mut c_float, out_stream_stride: usize, out_ch_stride: usize,
+                                        n_out: *mut usize) -> c_int;
 
     pub fn sk_normalize_batch_plan(ctx: *mut sk_ctx, in_rate: u32, out_rate: u32, frames: usize, semantics: c_int, n_out: *mut usize) -> c_int;
     pub fn sk_normalize_batch_dev(ctx: *mut sk_ctx, desc: *const sk_batch_desc) -> c_int;
@@ -126,6 +144,15 @@ extern "C" {
                                     bytes: usize, out_kind: c_int, out: *mut c_void, out_stride: usize, state: *mut i32) -> c_int;
     pub fn sk_g726_encode_batch_dev(ctx: *mut sk_ctx, bits: c_int, packing: c_int, in_kind: c_int, input: *const c_void, in_stride: usize,
                                     n_streams: usize, n: usize, out: *mut u8, out_stride: usize, state: *mut i32) -> c_int;
+
+    // G.722 64 kbit/s (soundkit-g722/src/lib.rs over ezk-g722): explicit 68-word codec state, all zero at reset
+    pub fn sk_g722_state_init(state: *mut i32);
+    pub fn sk_g722_decode(ctx: *mut sk_ctx, state: *mut i32, input: *const u8, bytes: usize, out_kind: c_int, out: *mut c_void) -> c_int;
+    pub fn sk_g722_encode(ctx: *mut sk_ctx, state: *mut i32, in_kind: c_int, input: *const c_void, n: usize, out: *mut u8) -> c_int;
+    pub fn sk_g722_decode_batch_dev(ctx: *mut sk_ctx, input: *const u8, in_stride: usize, n_streams: usize, bytes: usize, out_kind: c_int,
+                                    out: *mut c_void, out_stride: usize, state: *mut i32) -> c_int;
+    pub fn sk_g722_encode_batch_dev(ctx: *mut sk_ctx, in_kind: c_int, input: *const c_void, in_stride: usize, n_streams: usize, n: usize,
+                                    out: *mut u8, out_stride: usize, state: *mut i32) -> c_int;
 
     // StreamingStereo48kNormalizer (soundkit/src/audio_pipeline.rs:256-394)
     pub fn sk_norm48k_create(ctx: *mut sk_ctx, out: *mut *mut sk_norm48k) -> c_int;

@@ -72,3 +72,31 @@ fn stereo_to_mono(input: &[i16], avg: bool) -> Vec<i16> {
 }
 pub fn stereo_to_mono_take_left(input: &[i16]) -> Vec<i16> { stereo_to_mono(input, false) }  // :317
 pub fn stereo_to_mono_avg(input: &[i16]) -> Vec<i16> { stereo_to_mono(input, true) }         // :344
+
+// ---- the remaining items of soundkit/src/audio_bytes.rs -------------------------------------------------------------
+/// `i16_to_i16le` (:17-23): on a little-endian host this is the identity on bytes — the one conversion of the module that
+/// moves no arithmetic at all, so it stays a host copy (a PCIe round trip would only add latency).
+pub fn i16_to_i16le(data: &[i16]) -> Vec<u8> {
+    let mut bytes = Vec::with_capacity(data.len() * 2);
+    for value in data { bytes.extend(&value.to_le_bytes()); }
+    bytes
+}
+/// `s24le_to_i32_sample` (:312-315): a single sample, scalar by definition (callers that have a buffer use `s24le_to_i32`).
+pub fn s24le_to_i32_sample(sample_bytes: [u8; 3]) -> i32 {
+    let sample = i32::from_le_bytes([sample_bytes[0], sample_bytes[1], sample_bytes[2], 0]);
+    (sample << 8) >> 8
+}
+/// `stereo_to_mono_inplace_take_left` (:331-342): device result copied back over the front half of the caller's buffer
+pub fn stereo_to_mono_inplace_take_left(samples: &mut [i16]) -> &mut [i16] {
+    let mono = stereo_to_mono(samples, false);
+    let frames = mono.len();
+    samples[..frames].copy_from_slice(&mono);
+    &mut samples[..frames]
+}
+/// `stereo_to_mono_inplace_avg` (:360-373)
+pub fn stereo_to_mono_inplace_avg(samples: &mut [i16]) -> &mut [i16] {
+    let mono = stereo_to_mono(samples, true);
+    let frames = mono.len();
+    samples[..frames].copy_from_slice(&mono);
+    &mut samples[..frames]
+}

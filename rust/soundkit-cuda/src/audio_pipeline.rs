@@ -31,6 +31,75 @@ pub fn downsample_audio(bits_per_sample: u8, channel_count: u8, input_rate: u32,
     })
 }
 
+// ---- the free functions of soundkit/src/audio_pipeline.rs:17-131, 415-436 ----------------------------------------------
+fn flat_vec<I, O: Default + Clone>(op: sys::sk_flat_op, input: &[I]) -> Vec<O> {
+    let mut out = vec![O::default(); input.len()];
+    if input.is_empty() { return out; }
+    let mut n = 0usize;
+    with_ctx(|ctx| check(ctx, unsafe {
+        sys::sk_pcm_flat_convert(ctx, op as i32, input.as_ptr().cast(), std::mem::size_of_val(input), out.as_mut_ptr().cast(), &mut n)
+    })).expect("soundkit-cuda flat conversion");
+    out.truncate(n);
+    out
+}
+/// `(clamp(x, -1, 1) * 32767.0) as i16` (:17-27) == f32le_to_i16 on the samples' own little-endian bytes
+pub fn vec_f32_to_i16(input: Vec<f32>) -> Vec<i16> { flat_vec(sys::sk_flat_op::F32LE_TO_I16, &input) }
+/// `value as f32 / 32768.0` (:29-38)
+pub fn vec_i16_to_f32(input: Vec<i16>) -> Vec<f32> { flat_vec(sys::sk_flat_op::I16LE_TO_F32, &input) }
+/// `value as f32 / 2147483647.0` — the literal rounds to 2^31 in f32 (:40-50)
+pub fn vec_i32_to_f32(input: Vec<i32>) -> Vec<f32> { flat_vec(sys::sk_flat_op::S32LE_TO_F32, &input) }
+
+/// `audio_to_f32_channels` (:74-98), soundkit convention ("mode A": always little-endian, 24-bit / 2^31, no NaN scrub).
+/// Takes the fields of `AudioData` so the crate does not depend on soundkit; the caller passes `audio.data()` etc.
+pub fn audio_to_f32_channels(bits_per_sample: u8, channel_count: u8, is_float: bool, data: &[u8]) -> Result<Vec<Vec<f32>>, String> {
+    let channels = channel_count as usize;
+    if channels == 0 { return Err("Channel count must be > 0".to_string()); }
+    let fmt = if bits_per_sample == 32 && is_float { sys::SK_FMT_FLOAT } else { sys::SK_FMT_SIGNED };
+    if !(bits_per_sample == 16 || bits_per_sample == 24 || bits_per_sample == 32) {
+        return Err("deserialize_audio failed: unsuporrted type".to_string());      // sic, :71 and :91
+    }
+    let frames = data.len() / (bits_per_sample as usize / 8 * channels);
+    let mut flat = vec![0f32; frames.max(1) * channels];
+    let mut got = 0usize;
+    with_ctx(|ctx| check(ctx, unsafe {
+        sys::sk_pcm_to_planar_f32(ctx, data.as_ptr(), data.len(), bits_per_sample as i32, fmt, 0, channels as i32, sys::SK_MODE_A,
+                                  flat.as_mut_ptr(), frames.max(1), &mut got)
+    }))?;
+    Ok((0..channels).map(|c| flat[c * frames.max(1)..c * frames.max(1) + got].to_vec()).collect())
+}
+
+/// `mixdown_to_mono_f32` (:105-131): `(((0 + c0) + c1) + ...) * (1 / n)`
+pub fn mixdown_to_mono_f32(channels: &[Vec<f32>]) -> Result<Vec<f32>, String> {
+    if channels.is_empty() { return Ok(Vec::new()); }
+    if channels.len() == 1 { return Ok(channels[0].clone()); }
+    let sample_count = channels[0].len();
+    if channels.iter().any(|channel| channel.len() != sample_count) { return Err("channel length mismatch".to_string()); }
+    if sample_count == 0 { return Ok(Vec::new()); }
+    let planar: Vec<f32> = channels.iter().flat_map(|c| c.iter().copied()).collect();
+    let mut mono = vec![0f32; sample_count];
+    with_ctx(|ctx| check(ctx, unsafe {
+        sys::sk_mixdown_mono(ctx, planar.as_ptr(), sample_count, channels.len() as i32, sys::SK_MIX_SUM_THEN_SCALE, mono.as_mut_ptr())
+    }))?;
+    Ok(mono)
+}
+/// `audio_to_mono_f32` (:100-103)
+pub fn audio_to_mono_f32(bits_per_sample: u8, channel_count: u8, is_float: bool, data: &[u8]) -> Result<Vec<f32>, String> {
+    mixdown_to_mono_f32(&audio_to_f32_channels(bits_per_sample, channel_count, is_float, data)?)
+}
+
+/// `f32s_to_le_bytes` / `f32s_from_le_bytes` (:415-436): bit copies on a little-endian host — no arithmetic to offload
+pub fn f32s_to_le_bytes(samples: &[f32]) -> Vec<u8> {
+    let mut bytes = Vec::with_capacity(std::mem::size_of_val(samples));
+    for sample in samples { bytes.extend_from_slice(&sample.to_le_bytes()); }
+    bytes
+}
+pub fn f32s_from_le_bytes(bytes: &[u8]) -> Result<Vec<f32>, String> {
+    if bytes.len() % std::mem::size_of::<f32>() != 0 {
+        return Err(format!("invalid f32le byte length {}; expected multiple of 4", bytes.len()));
+    }
+    Ok(bytes.chunks_exact(4).map(|c| f32::from_le_bytes([c[0], c[1], c[2], c[3]])).collect())
+}
+
 /// One bounded block of canonical 48 kHz stereo PCM (soundkit/src/audio_pipeline.rs:234-248).
 #[derive(Debug)]
 pub struct Stereo48kBlock { pub left: Vec<f32>, pub right: Vec<f32> }

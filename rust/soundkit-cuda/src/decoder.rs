@@ -82,8 +82,11 @@ pub fn f32_channels_to_bytes(channels: &[Vec<f32>], bits_per_sample: u8, pcm_flo
 }
 
 /// `unpack_dvd_lpcm` (:750-804): 16-bit = byte swap, 20/24-bit = the DVD group layout → s24/s32 LE as the reference emits
-pub fn unpack_dvd_lpcm(packed: &[u8], bits: u8, channels: u8, out_bytes: usize) -> Result<Vec<u8>, String> {
-    let mut out = vec![0u8; out_bytes];
+/// The output has exactly the input's byte length (the C side writes `packed.len()` bytes): the buffer is sized here, not by
+/// the caller, so a wrong size can never reach the device.
+pub fn unpack_dvd_lpcm(packed: &[u8], bits: u8, channels: u8) -> Result<Vec<u8>, String> {
+    let mut out = vec![0u8; packed.len()];
+    if packed.is_empty() { return Ok(out); }
     with_ctx(|ctx| check(ctx, unsafe { sys::sk_dvd_lpcm_unpack(ctx, packed.as_ptr(), packed.len(), bits as i32, channels as i32, out.as_mut_ptr()) }))?;
     Ok(out)
 }
@@ -165,5 +168,45 @@ impl StreamingResampler {
             if !res.is_empty() && !res[0].is_empty() { outputs.push(res); }
         }
         Ok(outputs)
+    }
+}
+
+
+/// N `StreamingResampler`s in lock step (`sk_resampler_batch_*`): the per-stream rubato history and the pending input stay on the
+/// device between pushes, every push of the whole batch is one kernel launch.  `input` / `output` are DEVICE pointers to planar
+/// f32 (`[stream][channel][frame]`, strides in floats) owned by the caller — a serving front-end keeps its streams resident.
+pub struct StreamingResamplerBatch { handle: *mut sys::sk_resampler_batch, pub out_cap: usize }
+impl Drop for StreamingResamplerBatch { fn drop(&mut self) { unsafe { sys::sk_resampler_batch_destroy(self.handle) } } }
+impl StreamingResamplerBatch {
+    pub fn new(input_sample_rate: u32, output_sample_rate: u32, channels: usize, n_streams: usize, max_push_frames: usize) -> Result<Self, String> {
+        if input_sample_rate == 0 { return Err("Input sample rate must be > 0".to_string()); }       // apply_output_options' strings (:3330-3370)
+        if output_sample_rate == 0 { return Err("Output sample rate must be > 0".to_string()); }
+        if channels == 0 { return Err("Channel count must be > 0".to_string()); }
+        with_ctx(|ctx| {
+            let mut h = std::ptr::null_mut();
+            check(ctx, unsafe {
+                sys::sk_resampler_batch_create(ctx, input_sample_rate, output_sample_rate, channels as i32, n_streams, max_push_frames, &mut h)
+            }).map_err(|e| format!("Failed to create resampler: {e}"))?;
+            Ok(Self { handle: h, out_cap: unsafe { sys::sk_resampler_batch_out_cap(h) } })
+        })
+    }
+    /// # Safety
+    /// `input` must address `frames` readable floats per (stream, channel) at the given strides and `output` `out_cap` writable
+    /// floats per (stream, channel), both in device memory of the context's device.
+    pub unsafe fn process_dev(&mut self, input: *const f32, in_stream_stride: usize, in_ch_stride: usize, frames: usize, output: *mut f32,
+                              out_stream_stride: usize, out_ch_stride: usize) -> Result<usize, String> {
+        let mut n = 0usize;
+        with_ctx(|ctx| check(ctx, sys::sk_resampler_batch_process_dev(self.handle, input, in_stream_stride, in_ch_stride, frames, output,
+                                                                         out_stream_stride, out_ch_stride, &mut n))
+            .map_err(|e| format!("Resample failed: {e}")))?;
+        Ok(n)
+    }
+    /// # Safety
+    /// as `process_dev`
+    pub unsafe fn flush_dev(&mut self, output: *mut f32, out_stream_stride: usize, out_ch_stride: usize) -> Result<usize, String> {
+        let mut n = 0usize;
+        with_ctx(|ctx| check(ctx, sys::sk_resampler_batch_flush_dev(self.handle, output, out_stream_stride, out_ch_stride, &mut n))
+            .map_err(|e| format!("Resample flush failed: {e}")))?;
+        Ok(n)
     }
 }

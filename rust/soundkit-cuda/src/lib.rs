@@ -8,10 +8,13 @@ use std::cell::RefCell;
 use std::ffi::CStr;
 
 pub mod audio_bytes;
+pub mod audio_packet;
 pub mod audio_pipeline;
 pub mod decoder;
 pub mod g711;
+pub mod g722;
 pub mod g726;
+pub mod wav;
 
 /// One `sk_ctx` per thread: the reference runs one worker thread per `DecodePipeline`
 /// (soundkit-decoder/src/lib.rs:2764) and contexts are thread-confined.
