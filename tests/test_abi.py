@@ -66,3 +66,17 @@ def test_flat_op_widths_table():
                            "f32le": 4, "f32be": 4, "u8": 1}[src]
         assert b.value == (2 if name.endswith(("i16", "s16")) else 4)
     assert L.sk_flat_op_widths(99, None, None) == capi.E_ARG
+
+
+def test_rust_sys_crate_binds_every_declared_symbol():
+    """the Rust `-sys` crate cannot be compiled here (no cargo): at least its extern block must name exactly the header's symbols,
+    and the state-size constants must agree with the header"""
+    src = open(os.path.join(ROOT, "rust", "soundkit-cuda-sys", "src", "lib.rs")).read()
+    bound = sorted(set(re.findall(r"pub fn (sk_[a-z0-9_]+)\s*\(", src)))
+    assert bound == declared_symbols()
+    hdr = open(os.path.join(ROOT, "include", "soundkit_cuda.h")).read()
+    for name in ("SK_G726_STATE_INTS", "SK_G722_STATE_INTS"):
+        c = int(re.search(rf"#define {name} (\d+)", hdr).group(1))
+        r = int(re.search(rf"pub const {name}: usize = (\d+);", src).group(1))
+        assert c == r, name
+    assert capi.G722_STATE_INTS == int(re.search(r"#define SK_G722_STATE_INTS (\d+)", hdr).group(1))
