@@ -108,7 +108,7 @@ __device__ __forceinline__ float reduce8_rotated(const unsigned long long (&acc)
 __device__ __forceinline__ bool g3_nonfinite(float v) { return (__float_as_uint(v) & 0x7f800000u) == 0x7f800000u; }
 
 // the per-output arithmetic for one output of the lane whose staged window starts at `wc` (frame w0)
-__device__ __forceinline__ float g3_exact(const float* wc, int w0, const int32_t* __restrict__ pi0, const uint8_t* __restrict__ ps0, long long n,
+__device__ __noinline__ float g3_exact(const float* wc, int w0, const int32_t* __restrict__ pi0, const uint8_t* __restrict__ ps0, long long n,
                                           const float* __restrict__ table, float fr) {
     const int i0o = pi0[n], s0o = ps0[n];
     int s1 = s0o + 1, d = 0;
@@ -173,10 +173,14 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
             for (int c = warp; c < geo.C; c += kG3Warps) {
                 const uint8_t* sp = s_col_src[c];
                 float* d = win + (size_t)c * geo.col_stride;
-                for (int i = q; i < count; i += 32) {
-                    if (sp && i >= lo && i < hi) cp_async4(d + i, sp + (long long)i * fstride);
-                    else d[i] = 0.0f;
-                }
+                const int lo_c = sp ? lo : count, hi_c = sp ? hi : count;  // a missing lane is all zeros
+                for (int i = q; i < lo_c; i += 32) d[i] = 0.0f;
+                // first i >= lo_c with i == q (mod 32); 32-bit byte offsets (a window is far below 2 GB)
+                int i = q + ((max(lo_c - q, 0) + 31) & ~31);
+                const uint32_t dst0 = smem_u32(d);
+                for (; i < hi_c; i += 32)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst0 + 4u * (uint32_t)i), "l"(sp + (uint32_t)i * (uint32_t)fstride) : "memory");
+                for (; i < count; i += 32) d[i] = 0.0f;
             }
             cp_async_wait_all();
             if (!raw_float) {
@@ -388,6 +392,14 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
             make_ref(i0n, s0n, cur);
             stage_taps(cur);
         }
+        // the finish step's frac values: requested now (L1 hits after the prefetch), consumed after the exchange
+        float frv[A][kLanes ? 1 : 2];
+#pragma unroll
+        for (int bb = 0; bb < (kLanes ? 1 : 2); bb++) {
+            const int rb = col_first(bb) + ph0;
+#pragma unroll
+            for (int a = 0; a < A; a++) frv[a][bb] = pfrac[min(rb + a, nt - 1)];
+        }
         float P0[A][2], P1[A][2];  // the two products of the 4 outputs of the 2 columns this thread finishes (slots 0, 1)
 #pragma unroll
         for (int a = 0; a < A; a++)
@@ -438,7 +450,7 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
                 for (int a = 0; a < A; a++) {
                     y[a] = 0.0f;
                     if (a < nv) {
-                        const float fr = pfrac[rb + a];
+                        const float fr = frv[a][kLanes ? 0 : bb];
                         y[a] = __fadd_rn(P0[a][bb], __fmul_rn(fr, __fsub_rn(P1[a][bb], P0[a][bb])));  // interp_lin
                         if (!f || g3_nonfinite(y[a])) { y[a] = g3_exact(wc, w0, pi0, ps0, rb + a, table, fr); redo++; }
                     }
@@ -490,7 +502,7 @@ int sk_launch_gen3(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk
     const int mlen = SINC_LEN + dmax <= 264 ? 264 : (SINC_LEN + dmax <= 272 ? 272 : 0);
     if (!mlen) return 1;                                        // steep downsampling ratios: the padded walk would waste too much; gen2 / gen serve them
     g.tap_stride = mlen;
-    const int smem_budget = 200 * 1024;
+    const int smem_budget = 224 * 1024;
     const int taps_bytes = kG3Warps * kG3Rows * g.tap_stride * (int)sizeof(float);
     const int over = (g.tap_stride - SINC_LEN) + 8 + 4;         // overshoot of the padded walk past the last real window word
     if (lanes_only) {
