@@ -107,6 +107,13 @@ uint64_t sk_ctx_launch_count(const sk_ctx* ctx);
 /* input bytes per slab of the host-pointer batch pipeline (sk_normalize_batch keeps three slabs of this size plus their
  * outputs on the device; default 256 MiB).  Smaller slabs bound the device footprint, larger ones amortise launches. */
 int  sk_ctx_set_batch_slab_bytes(sk_ctx* ctx, size_t bytes);
+/* Arithmetic of the general-ratio (non-integer) resampler.  BIT_EXACT (default): every output is rubato's p0 + frac (p1 - p0) with
+ * its 8-lane accumulation order, bit-identical to the CPU restatement.  FAST (opt-in): batches of >= 64 (stream, channel) lanes
+ * are convolved against the interpolated row h_s + frac (h_{s+1} - h_s) — one product per output, half the work; results stay
+ * within the north-star contract (max-abs 1e-5 of full scale, SNR >= 120 dB) but are not bit-identical.  Integer ratios (48 -> 16
+ * kHz ...) and everything else are unaffected. */
+enum sk_resample_mode { SK_RESAMPLE_BIT_EXACT = 0, SK_RESAMPLE_FAST = 1 };
+int  sk_ctx_set_resample_mode(sk_ctx* ctx, int mode);
 /* Diagnostic: how many output samples of the general-ratio resampler so far left the tiled fast path and were computed by the
  * per-output exact path (non-uniform table rows inside a warp tile, ragged tile ends).  Results are identical either way;
  * the parity tests report and bound the share.  Synchronises the context's stream. */

@@ -30,6 +30,8 @@ pub const SK_MIX_SUM_THEN_SCALE: c_int = 1;
 pub const SK_MIX_SCALE_THEN_SUM: c_int = 2;
 pub const SK_SEM_ONESHOT: c_int = 0;
 pub const SK_SEM_STREAMING: c_int = 1;
+pub const SK_RESAMPLE_BIT_EXACT: c_int = 0;
+pub const SK_RESAMPLE_FAST: c_int = 1;
 
 /// `enum sk_flat_op`: the flat functions of `soundkit/src/audio_bytes.rs`
 #[repr(C)] #[derive(Clone, Copy, Debug, PartialEq, Eq)]
@@ -70,6 +72,7 @@ extern "C" {
     pub fn sk_ctx_synchronize(ctx: *mut sk_ctx) -> c_int;
     pub fn sk_ctx_launch_count(ctx: *const sk_ctx) -> u64;
     pub fn sk_ctx_set_batch_slab_bytes(ctx: *mut sk_ctx, bytes: usize) -> c_int;
+    pub fn sk_ctx_set_resample_mode(ctx: *mut sk_ctx, mode: c_int) -> c_int;
     pub fn sk_ctx_resample_fallback_outputs(ctx: *mut sk_ctx, count: *mut u64) -> c_int;
     pub fn sk_ctx_measure_ffma_peak(ctx: *mut sk_ctx, tflops: *mut c_double) -> c_int;
     pub fn sk_ctx_measure_ffma_peaks(ctx: *mut sk_ctx, scalar: *mut c_double, packed: *mut c_double) -> c_int;

@@ -20,6 +20,7 @@ FMT_SIGNED, FMT_FLOAT = 0, 1
 MODE_A, MODE_B = 0, 1
 MIX_NONE, MIX_SUM_THEN_SCALE, MIX_SCALE_THEN_SUM = 0, 1, 2
 SEM_ONESHOT, SEM_STREAMING = 0, 1
+RESAMPLE_BIT_EXACT, RESAMPLE_FAST = 0, 1
 FLAT_OPS = ("i16le_to_f32", "s16le_to_i16", "s16be_to_i16", "s16le_to_i32", "s24le_to_i32", "s24le_to_i16",
             "s24be_to_i16", "s32le_to_i32", "s32be_to_i32", "s32le_to_s24", "s32be_to_s24", "s32le_to_f32",
             "s32be_to_f32", "s32le_to_i16", "s32be_to_i16", "f32le_to_i16", "f32be_to_i16", "f32le_to_i32",
@@ -32,7 +33,7 @@ G722_STATE_INTS = 68
 EXPORTS = (
     "sk_abi_version", "sk_ctx_create", "sk_ctx_destroy", "sk_last_error", "sk_ctx_set_stream", "sk_ctx_reset_stream",
     "sk_ctx_synchronize",
-    "sk_ctx_launch_count", "sk_ctx_set_batch_slab_bytes", "sk_ctx_resample_fallback_outputs", "sk_ctx_measure_ffma_peak", "sk_ctx_measure_ffma_peaks", "sk_ctx_poison_shared_memory",
+    "sk_ctx_launch_count", "sk_ctx_set_batch_slab_bytes", "sk_ctx_set_resample_mode", "sk_ctx_resample_fallback_outputs", "sk_ctx_measure_ffma_peak", "sk_ctx_measure_ffma_peaks", "sk_ctx_poison_shared_memory",
     "sk_g711_decode", "sk_g711_decode_dev", "sk_g711_encode", "sk_g711_encode_dev",
     "sk_pcm_flat_convert", "sk_pcm_flat_convert_dev", "sk_flat_op_widths", "sk_dvd_lpcm_unpack", "sk_dvd_lpcm_unpack_dev",
     "sk_deinterleave", "sk_interleave_i16", "sk_interleave_planar", "sk_interleave_planar_dev",
@@ -93,6 +94,7 @@ def load():
         "sk_ctx_synchronize": (i, [vp]),
         "sk_ctx_launch_count": (C.c_uint64, [vp]),
         "sk_ctx_set_batch_slab_bytes": (i, [vp, sz]),
+        "sk_ctx_set_resample_mode": (i, [vp, i]),
         "sk_ctx_resample_fallback_outputs": (i, [vp, C.POINTER(C.c_uint64)]),
         "sk_ctx_measure_ffma_peak": (i, [vp, C.POINTER(C.c_double)]),
         "sk_ctx_measure_ffma_peaks": (i, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -235,6 +237,10 @@ class Context:
     def set_batch_slab_bytes(self, nbytes):
         """input bytes per slab of the host-pointer batch pipeline (normalize_batch_host)"""
         self._ck(self.L.sk_ctx_set_batch_slab_bytes(self.h, nbytes))
+
+    def set_resample_mode(self, fast):
+        """general-ratio resampler arithmetic: False = bit-exact (default), True = the opt-in tolerance mode (1e-5 / 120 dB)"""
+        self._ck(self.L.sk_ctx_set_resample_mode(self.h, RESAMPLE_FAST if fast else RESAMPLE_BIT_EXACT))
 
     def resample_fallback_outputs(self):
         """outputs of the general-ratio resampler that took the per-output exact path so far (synchronises)"""

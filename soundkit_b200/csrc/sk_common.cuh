@@ -41,6 +41,7 @@ struct sk_ctx {
     void* d_res = nullptr;   size_t d_res_cap = 0;     // result planes of sk_normalize_stream (grow-only; no per-call cudaMalloc)
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};     // pinned-stage slot events of sk_h2d / sk_d2h (created once)
     size_t batch_slab_bytes = (size_t)256 << 20;      // input bytes per slab of the sk_normalize_batch pipeline (sk_ctx_set_batch_slab_bytes)
+    bool resample_fast = false;                       // sk_ctx_set_resample_mode: opt-in tolerance mode of the general-ratio resampler
     bool disable_gen3 = false;                        // diagnostic (SK_DISABLE_GEN3=1): general ratios use the older 2 x 2 tile kernel
     unsigned long long* d_stats = nullptr;            // [0] outputs of the general-ratio resampler that took the per-output exact path
 };

@@ -82,6 +82,13 @@ extern "C" int sk_ctx_set_batch_slab_bytes(sk_ctx* ctx, size_t bytes) {
     return SK_OK;
 }
 
+extern "C" int sk_ctx_set_resample_mode(sk_ctx* ctx, int mode) {
+    if (!ctx) return SK_E_ARG;
+    if (mode != SK_RESAMPLE_BIT_EXACT && mode != SK_RESAMPLE_FAST) SK_FAIL(ctx, SK_E_ARG, "unknown resample mode %d", mode);
+    ctx->resample_fast = mode == SK_RESAMPLE_FAST;
+    return SK_OK;
+}
+
 int sk_ensure_stats(sk_ctx* ctx) {
     if (ctx->d_stats) return SK_OK;
     SK_CUDA(ctx, cudaMalloc((void**)&ctx->d_stats, 8 * sizeof(unsigned long long)));

@@ -153,6 +153,8 @@ static int finalize_general_plan(sk_ctx* ctx, sk_plan* p, uint32_t in_rate, uint
     p->n_out = w.i0.size();
     p->max_step3 = 0;
     for (size_t n = 0; n + 3 < p->n_out; n++) p->max_step3 = std::max(p->max_step3, w.i0[n + 3] - w.i0[n]);
+    p->max_step7 = 0;
+    for (size_t n = 0; n + 7 < p->n_out; n++) p->max_step7 = std::max(p->max_step7, w.i0[n + 7] - w.i0[n]);
     const uint32_t g = gcd_u32(in_rate, out_rate);
     const uint32_t L = out_rate / g;
     auto window_for = [&](int period) {
@@ -1174,6 +1176,8 @@ static int batch_run_chunks(sk_resampler_batch* b, size_t chunks, size_t valid, 
         if ((rc = sk_h2d(ctx, p.d_frac, w.frac.data(), n * sizeof(float)))) return rc;
         p.max_step3 = 0;
         for (size_t i = 0; i + 3 < n; i++) p.max_step3 = std::max(p.max_step3, w.i0[i + 3] - w.i0[i]);
+        p.max_step7 = 0;
+        for (size_t i = 0; i + 7 < n; i++) p.max_step7 = std::max(p.max_step7, w.i0[i + 7] - w.i0[i]);
         // tile mapping of the one-output-per-thread kernel (batches below 64 lanes): same rule as the batch plans
         const uint32_t g = gcd_u32(b->in_rate, b->out_rate);
         const uint32_t L = b->out_rate / g;

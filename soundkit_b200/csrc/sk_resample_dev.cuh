@@ -26,6 +26,7 @@ struct sk_plan {
     int period2 = 0;         // resample_gen2_kernel: outputs per period (a multiple of L), 0 = kernel not applicable
     int max_window2 = 0;     // largest input window of a 64-period tile
     int max_step3 = -1;      // general plans: largest i0[n + 3] - i0[n] (window advance inside a group of 4 consecutive outputs)
+    int max_step7 = -1;      // ... and i0[n + 7] - i0[n] (groups of 8 outputs: the tolerance-mode kernel)
     uint64_t last_use = 0;   // plan cache clock value of the last lookup (least recently used plans are evicted first)
 };
 

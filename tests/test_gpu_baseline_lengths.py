@@ -257,3 +257,60 @@ def test_cuda_kernels_against_real_rubato_dump(ctx, path):
     snr = np.inf if noise == 0 else 10 * np.log10(np.sum(want.astype(np.float64) ** 2) / noise)
     assert err <= 1e-5 and snr >= 120.0, (err, snr)
     print("bit-identical to rubato:", bool(np.array_equal(_bits(got), _bits(want))))
+
+
+@pytest.mark.parametrize("rates", [(44100, 48000), (44100, 16000), (48000, 44100), (8000, 16000), (32000, 48000), (22050, 16000)])
+@pytest.mark.parametrize("semantics", ["oneshot", "streaming"])
+def test_fast_resample_mode_stays_inside_the_north_star_contract(oracle, rates, semantics):
+    """sk_ctx_set_resample_mode(SK_RESAMPLE_FAST): one product against the interpolated table row per output instead of rubato's
+    two — opt-in, lane columns only.  Gate: max-abs <= 1e-5 of full scale and SNR >= 120 dB against the bit-exact kernel AND against
+    the CPU oracle, full-scale noise and near-Nyquist tones; batches below 64 lanes must stay bit-exact even with the mode on."""
+    import torch
+    i, o = rates
+    S, frames = 40, 50021
+    rng = np.random.default_rng(i + o)
+    t = np.arange(frames) / i
+    x = rng.uniform(-1.0, 1.0, (S, frames, 2)).astype(np.float32)
+    x[1, :, 0] = 0.99 * np.sin(2 * np.pi * 0.47 * min(i, o) * t)
+    x[1, :, 1] = 0.99 * np.sin(2 * np.pi * 997.0 * t)
+    x = x.reshape(S, -1)
+    sem = capi.SEM_ONESHOT if semantics == "oneshot" else capi.SEM_STREAMING
+    c = capi.Context(0)
+    c.use_torch_stream()
+    try:
+        n_out = c.batch_plan(i, o, frames, sem)
+        xd = torch.from_numpy(x).cuda()
+        res = {}
+        for fast in (False, True):
+            c.set_resample_mode(fast)
+            od = torch.zeros((S, 2, n_out), dtype=torch.float32, device="cuda")
+            d = capi.BatchDesc(xd.data_ptr(), xd.stride(0) * 4, S, frames, 32, capi.FMT_FLOAT, 0, 2, capi.MODE_A, i, o, sem, capi.MIX_NONE,
+                               od.data_ptr(), 2 * n_out, n_out)
+            c.normalize_batch_dev(d)
+            torch.cuda.synchronize()
+            res[fast] = od.cpu().numpy()
+        # fewer than 64 lanes: the fast kernel does not apply, the result is the bit-exact one
+        od = torch.zeros((3, 2, n_out), dtype=torch.float32, device="cuda")
+        d = capi.BatchDesc(xd.data_ptr(), xd.stride(0) * 4, 3, frames, 32, capi.FMT_FLOAT, 0, 2, capi.MODE_A, i, o, sem, capi.MIX_NONE,
+                           od.data_ptr(), 2 * n_out, n_out)
+        c.normalize_batch_dev(d)
+        torch.cuda.synchronize()
+        small = od.cpu().numpy()
+    finally:
+        c.close()
+    exact, fast = res[False].astype(np.float64), res[True].astype(np.float64)
+    assert np.array_equal(_bits(small), _bits(res[False][:3]))
+    err = np.max(np.abs(exact - fast))
+    snr = 10 * np.log10(np.sum(exact ** 2) / max(np.sum((exact - fast) ** 2), 1e-300))
+    assert err <= 1e-5 and snr >= 120.0, (err, snr)
+    for s in (0, 1, 39):
+        if semantics == "oneshot":
+            want = oracle.downsample_audio(x[s].view(np.uint8), 32, 1, 2, i, o)
+        else:
+            st = oracle.Stream(i, o, 2)
+            want = np.concatenate([st.process(np.ascontiguousarray(x[s].reshape(-1, 2).T)), st.flush()], axis=1)
+        assert np.array_equal(_bits(res[False][s]), _bits(want))
+        w = want.astype(np.float64)
+        assert np.max(np.abs(w - fast[s])) <= 1e-5
+        assert 10 * np.log10(np.sum(w ** 2) / max(np.sum((w - fast[s]) ** 2), 1e-300)) >= 120.0
+    print(f"[fast mode {i}->{o} {semantics}] max-abs {err:.2e}, SNR {snr:.1f} dB vs the bit-exact kernel")

@@ -16,6 +16,7 @@ def main():
     ctx.use_torch_stream()
     sizes = [int(a) for a in sys.argv[1:]] or [16, 64, 256]
     reps = int(os.environ.get("KB_REPS", "3"))
+    ctx.set_resample_mode(os.environ.get("KB_FAST", "0") == "1")
     out = {}
     for in_rate, out_rate in ((44100, 48000), (44100, 16000)):
         for S in sizes:
