@@ -85,15 +85,24 @@ __device__ __forceinline__ bool stage_window(const SrcDesc& s, long long stream,
                                              float* win0, float* win1) {
     bool big = false;
     if (s.width == 0) {
+        // planar f32 (the stateful resamplers' device rows): 4-byte cp.async per sample — any alignment, every copy of the window in
+        // flight at once, no register round trip — then the fetching thread checks its own elements for huge / non-finite values
         const float* p0 = reinterpret_cast<const float*>(s.base + stream * s.stream_stride + (long long)lane0 * s.lane_stride);
         const float* p1 = reinterpret_cast<const float*>(s.base + stream * s.stream_stride + (long long)(lane0 + 1) * s.lane_stride);
         for (int i = threadIdx.x; i < count; i += NTHREADS) {
             const long long f = w0 + i;
             const bool ok = f >= s.valid_lo && f < s.valid_hi;
-            float a = ok ? __ldg(p0 + f + s.origin) : 0.0f;
-            float b = (ok && lane1_valid) ? __ldg(p1 + f + s.origin) : 0.0f;
-            big |= ((__float_as_uint(a) & 0x7f800000u) >= 0x78000000u) | ((__float_as_uint(b) & 0x7f800000u) >= 0x78000000u);
-            win0[i] = a; if (win1) win1[i] = b;
+            if (ok) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(win0 + i)), "l"(p0 + f + s.origin) : "memory");
+            else win0[i] = 0.0f;
+            if (win1) {
+                if (ok && lane1_valid) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(win1 + i)), "l"(p1 + f + s.origin) : "memory");
+                else win1[i] = 0.0f;
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        for (int i = threadIdx.x; i < count; i += NTHREADS) {
+            big |= (__float_as_uint(win0[i]) & 0x7f800000u) >= 0x78000000u;
+            if (win1) big |= (__float_as_uint(win1[i]) & 0x7f800000u) >= 0x78000000u;
         }
     } else {
         const uint8_t* sbase = s.base + stream * s.stream_stride;
