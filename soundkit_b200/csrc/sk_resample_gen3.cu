@@ -202,19 +202,28 @@ __device__ __forceinline__ void g3_stage_tile(const SrcDesc& src, const OutDesc&
 
 }
 
-// XVEC == 4: lane columns only (P == 1, C == 64): every column shares every plan entry, windows and group bases are 16-byte
-// aligned (LDS.128 input loads).  XVEC == 1: period columns (P > 1): scalar input loads, per-column plan entries checked
+// XVEC == 4 / 8: lane columns only (P == 1, C == 64): every column shares every plan entry, windows and group bases are 16-byte
+// aligned (vector input loads).  XVEC == 1: period columns (P > 1): scalar input loads, per-column plan entries checked
 // against the group's reference entries.
+// XVEC == 8 is the QUAD form: the 8 accumulator lanes of an output are split over FOUR threads (q, q + 8, q + 16, q + 24) that
+// share 8 columns; quarter hh walks words m + 2 hh, m + 2 hh + 1 of every 8-word block, so every load is an LDS.64 and a thread
+// tile is 8 tap rows x 8 columns: 16 x 8 bytes arrive in registers per 64 FFMA2 instead of 12 x 16 (the register tile is
+// square, which minimises operand bytes per FMA for 64 accumulator pairs).  tools/ub/ub_lds_split.cu measures the walk alone:
+// shared-memory loads cost by the bytes they return to the register file, not by wavefronts — LDS.128 twice an LDS.64 whatever
+// the address pattern — and the quad walk runs 1.10x the pair walk.
 template <int XVEC, int MLEN>
 __global__ void __launch_bounds__(kG3Threads, 1)
 resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant__ OutDesc dst, const __grid_constant__ Gen3Geom geo,
                      const int32_t* __restrict__ pi0, const uint8_t* __restrict__ ps0, const float* __restrict__ pfrac,
                      const float* __restrict__ table, const float* __restrict__ table4, int lanes_per_stream, unsigned long long* __restrict__ stats) {
-    constexpr int A = kG3A, B = kG3B;
-    constexpr bool kLanes = XVEC == 4;
+    constexpr bool kLanes = XVEC >= 4, kQuad = XVEC == 8;
+    constexpr int A = kG3A, B = kQuad ? 8 : kG3B;
+    constexpr int NP = kQuad ? 1 : 2;   // accumulator pairs (of the thread's 2 or 4 virtual lanes) per product
+    constexpr int HW = kQuad ? 2 : 4;   // words of every 8-word block this thread walks
     extern __shared__ __align__(16) float g3_smem[];
     __shared__ const uint8_t* s_col_src[kG3Cols];  // per lane of this CTA: first sample of the lane (channel plane for planar sources); null = no lane
     __shared__ float* s_col_dst[kG3Cols];          // output row of the lane
+    __shared__ __align__(8) unsigned long long s_tap_bar[kG3Warps];  // per warp: completion of its 8 bulk row copies
     constexpr int TS = MLEN;  // words per staged row == length of the (fully unrolled) tap walk
     float* taps_all = g3_smem;                                   // [warps][8 rows][TS]
     float* win = g3_smem + kG3Warps * kG3Rows * TS;              // [C][col_stride]
@@ -232,6 +241,9 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
     // be staged data)
     const int count = min(geo.span, pi0[nt - 1] - w0 + SINC_LEN + 2 + (TS - SINC_LEN) + 8);
 
+    const uint32_t tap_bar = smem_u32(&s_tap_bar[warp]);
+    if (q == 0) { mbar_init(tap_bar, 1); mbar_fence_init(); }  // visible to every lane after the barriers of the tile prologue
+    uint32_t tap_phase = 0;
     g3_stage_tile(src, dst, geo, n0, lane0, w0, count, lanes_per_stream, win, s_col_src, s_col_dst);
 
     // ---- this thread's four columns.  The two half-warps share the 64 columns of the warp: lane pair (ql, ql + 16) owns columns
@@ -240,16 +252,20 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
     // anyway, and every tap register feeds 4 columns: 32 shared-memory wavefronts per 64 FFMA2 per thread.  Each thread keeps
     // the two columns it will finish in slots 0-1 and its partner's in slots 2-3 (slot b = column (b ^ 2 hh)), so the exchange
     // after the walk needs no selects.  column j -> (lane c = j % C, period k = j / C)
-    const int ql = q & 15, hh = q >> 4;
-    // slot b of this thread = column j = ql + 16 (b ^ 2 hh) -> lane c = j % C of the CTA, period k = j / C of the tile
-    auto col_lane = [&](int b) { return (ql + 16 * (b ^ (2 * hh))) & (geo.C - 1); };
-    auto col_first = [&](int b) { return kLanes ? 0 : ((ql + 16 * (b ^ (2 * hh))) >> geo.log2c) * geo.period; };  // first output of the period
+    // Quad form: threads (ql, hh = 0..3) share columns ql + 8 n (n < 8); slot b = column n = b ^ 2 hh, so a thread's own two
+    // columns (n = 2 hh, 2 hh + 1) sit in slots 0-1, those of its second-step partner (hh ^ 1) in 2-3 and those of the
+    // first-step partner's pair (hh ^ 2, hh ^ 3) in 4-7: both exchange steps send and receive the same slot numbers.
+    constexpr int CW = kQuad ? 8 : 16;  // threads that own distinct columns
+    const int ql = q & (CW - 1), hh = q / CW;
+    // slot b of this thread = column j = ql + CW (b ^ 2 hh) -> lane c = j % C of the CTA, period k = j / C of the tile
+    auto col_lane = [&](int b) { return (ql + CW * (b ^ (2 * hh))) & (geo.C - 1); };
+    auto col_first = [&](int b) { return kLanes ? 0 : ((ql + CW * (b ^ (2 * hh))) >> geo.log2c) * geo.period; };  // first output of the period
     unsigned col_ok = 0;  // bit = slot: the lane exists
 #pragma unroll
     for (int b = 0; b < B; b++) col_ok |= (lane0 + col_lane(b) < geo.n_lanes ? 1u : 0u) << b;
     const float* xcol[B];  // window of each slot's lane, + this half's word offset
 #pragma unroll
-    for (int b = 0; b < B; b++) xcol[b] = win + (size_t)col_lane(b) * geo.col_stride + 4 * hh;
+    for (int b = 0; b < B; b++) xcol[b] = win + (size_t)col_lane(b) * geo.col_stride + HW * hh;
 
     // Reference plan entries of a group (period 0 of the tile; entries clamped at ragged ends are masked later), packed:
     //   base = window start of output 0 (moved down to a 16-byte boundary for the LDS.128 form: the taps shift up instead),
@@ -280,9 +296,13 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
             r.dp |= (unsigned)min(255, max(0, i0v[a] - i0v[0] + fix)) << (8 * a);
         }
     };
-    // stage the 8 shifted rows of a group (warp private): 16-byte cp.async from the pre-shifted table copies
+    // stage the 8 shifted rows of a group (warp private): one TMA bulk copy per row from the pre-shifted table copies (16-byte
+    // aligned slices of MLEN words), issued by lane 0 and completed on the warp's mbarrier — ~40 instructions in one lane
+    // instead of ~350 in every lane for 16-byte cp.async loops.  The caller has synchronised the warp after its last read
+    // of the rows.
     auto stage_taps = [&](const GroupRef& r) {
-        if (!ref_ok(r)) return;
+        if (!ref_ok(r) || q != 0) return;
+        mbar_expect_tx(tap_bar, kG3Rows * MLEN * (uint32_t)sizeof(float));
 #pragma unroll
         for (int a = 0; a < A; a++)
 #pragma unroll
@@ -291,8 +311,7 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
                 const int row = p == 0 ? s0 : ((s0 + 1) & (OVERSAMPLING - 1));
                 const int d = shift_of(r, a, p), sh = d & 3;
                 const float* grow = table4 + ((size_t)(sh * OVERSAMPLING + row)) * kG3RowLen + (kG3PadL - (d - sh));
-                float* t = T + (a * 2 + p) * TS;
-                for (int v = q; v < MLEN / 4; v += 32) cp_async16(t + 4 * v, grow + 4 * v);
+                tma_load_1d(smem_u32(T + (a * 2 + p) * TS), grow, MLEN * (uint32_t)sizeof(float), tap_bar);
             }
     };
 
@@ -325,7 +344,7 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
             xoff[0] = cur.base - w0;
             const bool f = cur_ok && xoff[0] >= 0 && xoff[0] + MLEN <= count;
             if (!f) xoff[0] = 0;
-            follows = f ? 0xfu : 0u;
+            follows = f ? 0xffu : 0u;
         } else {
 #pragma unroll
             for (int b = 0; b < B; b++) {
@@ -356,40 +375,42 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
 #pragma unroll
             for (int p = 0; p < 2; p++) rot_odd |= (unsigned)(shift_of(cur, a, p) & 1) << (a * 2 + p);
 
-        cp_async_wait_all();  // this group's rows
+        if (cur_ok) { mbar_wait(tap_bar, tap_phase); tap_phase ^= 1u; }  // this group's rows
         __syncwarp();
-        unsigned long long acc[A][B][2][2];  // [output][slot][product][pair of this half's 4 virtual lanes]
+        unsigned long long acc[A][B][2][NP];  // [output][slot][product][pair of this thread's 4 (2: quad form) virtual lanes]
         if (cur_ok) {
             // ---- the packed FIR walk over this half-warp's words
             const float* xb[B];
 #pragma unroll
             for (int b = 0; b < B; b++) xb[b] = xcol[b] + xoff[kLanes ? 0 : b];
-            const float* Th = T + 4 * hh;
+            const float* Th = T + HW * hh;
 #pragma unroll
-            for (int i = 0; i < A * B * 4; i++) (&acc[0][0][0][0])[i] = 0ull;
+            for (int i = 0; i < A * B * 2 * NP; i++) (&acc[0][0][0][0])[i] = 0ull;
 #pragma unroll
             for (int m = 0; m < MLEN; m += 8) {
-                unsigned long long xp[B][2];
+                unsigned long long xp[B][NP];
 #pragma unroll
                 for (int b = 0; b < B; b++) {
-                    if (kLanes) {
-                        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xp[b][0]), "=l"(xp[b][1]) : "r"(smem_u32(xb[b] + m)));
+                    if constexpr (kQuad) {
+                        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(xp[b][0]) : "r"(smem_u32(xb[b] + m)));
+                    } else if constexpr (kLanes) {
+                        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xp[b][0]), "=l"(xp[b][NP - 1]) : "r"(smem_u32(xb[b] + m)));
                     } else {
                         xp[b][0] = pack2(xb[b][m], xb[b][m + 1]);
-                        xp[b][1] = pack2(xb[b][m + 2], xb[b][m + 3]);
+                        xp[b][NP - 1] = pack2(xb[b][m + 2], xb[b][m + 3]);
                     }
                 }
 #pragma unroll
                 for (int a = 0; a < A; a++)
 #pragma unroll
                     for (int p = 0; p < 2; p++) {
-                        unsigned long long t0, t1;
-                        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(t0), "=l"(t1) : "r"(smem_u32(Th + (a * 2 + p) * TS + m)));
+                        unsigned long long t[NP];
+                        if constexpr (kQuad) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(t[0]) : "r"(smem_u32(Th + (a * 2 + p) * TS + m)));
+                        else asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(t[0]), "=l"(t[NP - 1]) : "r"(smem_u32(Th + (a * 2 + p) * TS + m)));
 #pragma unroll
-                        for (int b = 0; b < B; b++) {
-                            ffma2(acc[a][b][p][0], xp[b][0], t0);
-                            ffma2(acc[a][b][p][1], xp[b][1], t1);
-                        }
+                        for (int b = 0; b < B; b++)
+#pragma unroll
+                            for (int k = 0; k < NP; k++) ffma2(acc[a][b][p][k], xp[b][k], t[k]);
                     }
             }
         }
@@ -414,7 +435,41 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
         for (int a = 0; a < A; a++)
 #pragma unroll
             for (int bb = 0; bb < 2; bb++) { P0[a][bb] = 0.0f; P1[a][bb] = 0.0f; }
-        if (cur_ok) {
+        if constexpr (kQuad) {
+            if (cur_ok) {
+                // ---- exchange and reduce, quad form.  Step 1 (partner lane ^ 16 = quarter hh ^ 2, which holds virtual lanes
+                // v_{i+4} of this thread's v_i): send slots 4-7, receive the partner's 4-7 = this thread's slots 0-3, leaving
+                // (s_i, s_{i+1}) = (v_i + v_{i+4}, v_{i+1} + v_{i+5}), i = 2 (hh & 1).  Step 2 (partner lane ^ 8 = quarter hh ^ 1,
+                // which holds the other two s of the same columns): send slots 2-3, receive the partner's = this thread's
+                // slots 0-1.  rubato's tree adds s pairs (0,1), (2,3) for an even rotation and (1,2), (3,0) for an odd one;
+                // with own (m0, m1) and received (r0, r1) that is (m0 + m1) + (r0 + r1) or (m1 + r0) + (r1 + m0) for either
+                // value of hh & 1, because every addition commutes bit for bit.
+#pragma unroll
+                for (int a = 0; a < A; a++)
+#pragma unroll
+                    for (int p = 0; p < 2; p++) {
+                        float s[4][2];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const unsigned long long recv = __shfl_xor_sync(0xffffffffu, acc[a][4 + k][p][0], 16);
+                            float m0, m1, r0, r1;
+                            unpack2(acc[a][k][p][0], m0, m1);
+                            unpack2(recv, r0, r1);
+                            s[k][0] = __fadd_rn(m0, r0); s[k][1] = __fadd_rn(m1, r1);
+                        }
+                        const bool odd = ((rot_odd >> (a * 2 + p)) & 1u) != 0;
+#pragma unroll
+                        for (int bb = 0; bb < 2; bb++) {
+                            const float r0 = __shfl_xor_sync(0xffffffffu, s[2 + bb][0], 8), r1 = __shfl_xor_sync(0xffffffffu, s[2 + bb][1], 8);
+                            const float m0 = s[bb][0], m1 = s[bb][1];
+                            const float t0 = odd ? __fadd_rn(m1, r0) : __fadd_rn(m0, m1);
+                            const float t1 = odd ? __fadd_rn(r1, m0) : __fadd_rn(r0, r1);
+                            const float r = __fadd_rn(t0, t1);
+                            if (p == 0) P0[a][bb] = r; else P1[a][bb] = r;
+                        }
+                    }
+            }
+        } else if (cur_ok) {
             // ---- exchange and reduce: this thread holds virtual lanes 4 hh .. 4 hh + 3 of all four slots and finishes slots 0, 1;
             // its partner (lane ^ 16) holds the other four lanes and finishes this thread's slots 2, 3 (its own 0, 1).
             // s_i = v_i + v_{i+4} pairs one value of each half and additions commute, so the halves need no ordering.
@@ -427,9 +482,9 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
                         float s4[4];
 #pragma unroll
                         for (int k = 0; k < 2; k++) {
-                            const unsigned long long recv = __shfl_xor_sync(0xffffffffu, acc[a][2 + bb][p][k], 16);
+                            const unsigned long long recv = __shfl_xor_sync(0xffffffffu, acc[a][2 + bb][p][k & (NP - 1)], 16);
                             float m0, m1, r0, r1;
-                            unpack2(acc[a][bb][p][k], m0, m1);
+                            unpack2(acc[a][bb][p][k & (NP - 1)], m0, m1);
                             unpack2(recv, r0, r1);
                             s4[2 * k] = __fadd_rn(m0, r0); s4[2 * k + 1] = __fadd_rn(m1, r1);
                         }
@@ -454,17 +509,18 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
                 const int cl = col_lane(bb);
                 const float* wc = win + (size_t)cl * geo.col_stride;
                 float y[A];
-                int redo = 0;
+                unsigned redo = 0;  // bit a: output a goes to the per-output arithmetic (rare: one branch for the whole column)
 #pragma unroll
                 for (int a = 0; a < A; a++) {
-                    y[a] = 0.0f;
-                    if (a < nv) {
-                        const float fr = frv[a][kLanes ? 0 : bb];
-                        y[a] = __fadd_rn(P0[a][bb], __fmul_rn(fr, __fsub_rn(P1[a][bb], P0[a][bb])));  // interp_lin
-                        if (!f || g3_nonfinite(y[a])) { y[a] = g3_exact(wc, w0, pi0, ps0, rb + a, table, fr); redo++; }
-                    }
+                    y[a] = __fadd_rn(P0[a][bb], __fmul_rn(frv[a][kLanes ? 0 : bb], __fsub_rn(P1[a][bb], P0[a][bb])));  // interp_lin
+                    redo |= ((a < nv && (!f || g3_nonfinite(y[a]))) ? 1u : 0u) << a;
                 }
-                if (redo) atomicAdd(stats, (unsigned long long)redo);
+                if (redo) {
+#pragma unroll
+                    for (int a = 0; a < A; a++)
+                        if ((redo >> a) & 1u) y[a] = g3_exact(wc, w0, pi0, ps0, rb + a, table, frv[a][kLanes ? 0 : bb]);
+                    atomicAdd(stats, (unsigned long long)__popc(redo));
+                }
                 float* op = s_col_dst[cl] + rb;
                 if (nv == A && ((((uintptr_t)op) & 15) == 0)) {
                     *reinterpret_cast<float4*>(op) = make_float4(y[0], y[1], y[2], y[3]);
@@ -476,7 +532,6 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
             }
         }
     }
-    cp_async_wait_all();
 }
 
 // ================================================================================================
@@ -762,8 +817,10 @@ int sk_launch_gen3(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk
         int rc;
         if (fast) rc = mlen == 272 ? launch_gen3_fast_t<272>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem)
                                    : launch_gen3_fast_t<288>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem);
-        else if (g.xvec) rc = mlen == 264 ? launch_gen3_t<4, 264>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem)
+        else if (g.xvec && getenv("SK_GEN3_PAIR")) rc = mlen == 264 ? launch_gen3_t<4, 264>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem)
                                      : launch_gen3_t<4, 272>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem);
+        else if (g.xvec) rc = mlen == 264 ? launch_gen3_t<8, 264>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem)
+                                     : launch_gen3_t<8, 272>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem);
         else rc = mlen == 264 ? launch_gen3_t<1, 264>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem)
                               : launch_gen3_t<1, 272>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem);
         if (rc) return rc;
