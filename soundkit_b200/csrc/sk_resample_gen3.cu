@@ -1,4 +1,5 @@
-// sk_resample_gen3.cu — general-ratio polyphase FIR, third form: 4 outputs x 2 columns per thread, packed FFMA2, shifted tap rows.
+// sk_resample_gen3.cu — general-ratio polyphase FIR, third form: 4 consecutive outputs x 64 columns per warp, packed FFMA2 against
+// shifted tap rows, the 8 accumulator lanes of an output split over 4 (lane columns) or 2 (period columns) threads.
 //
 // Same arithmetic contract as resample_gen2_kernel (sk_resample.cu): every output is rubato's
 //     p0 + frac * (p1 - p0),   p_k = 8 lane accumulators (lane l owns taps l, l+8, ... with fused multiply-adds in tap order)
@@ -7,22 +8,24 @@
 // (soundkit/src/audio_pipeline.rs:474-491, soundkit-decoder/src/lib.rs:1939-2031).
 //
 // Why a third form.  The 2 x 2 tile of gen2 spends 13-14 shared-memory wavefronts per 32 FFMA (LSU-bound at ~0.57 of the FMA
-// peak, measured 0.28).  Here a thread owns A = 4 CONSECUTIVE outputs (n .. n+3) of B = 2 COLUMNS:
+// peak, measured 0.28).  Here a warp owns A = 4 CONSECUTIVE outputs (n .. n+3) of 64 COLUMNS:
 //   * a column is an independent input window that shares the group's table rows: another (stream, channel) lane of the batch
 //     and/or the same lane one or more whole phase periods later.  With >= 64 lanes in a batch (BASELINE configs[3]: 4096
 //     streams x 2 channels) columns are simply lanes, every plan entry is shared exactly and the period structure of the
 //     ratio is not needed at all; smaller batches fill the 64 columns with periods of the same lane (the gen2 idea);
 //   * the windows of 4 consecutive outputs overlap almost completely, so ONE pass over the input words x[m] serves all four:
 //     output a needs tap j = m - d_a, where d_a is its window offset inside the group.  The warp stages its 8 table rows
-//     (4 outputs x 2 interpolation products) in shared memory SHIFTED by d_a and zero padded: T_a[m] = h_a[m - d_a].  Every
-//     output then consumes the same (x[m], x[m+1]) register pair against (T_a[m], T_a[m+1]) with one packed FFMA2;
+//     (4 outputs x 2 interpolation products) in shared memory SHIFTED by d_a and zero padded: T_a[m] = h_a[m - d_a] (TMA bulk
+//     copies from word-shifted copies of the table).  Every output then consumes the same (x[m], x[m+1]) register pair
+//     against (T_a[m], T_a[m+1]) with one packed FFMA2;
 //   * accumulators are indexed by m & 7 ("virtual lanes", compile time).  Rubato's lane of tap j is j & 7 = (m - d_a) & 7, a
 //     rotation by d_a & 7 that is undone in the reduction: the tree pairs lane l with l + 4 — a rotation-invariant pairing —
 //     and then sums adjacent pairs, which depends on the parity of the rotation only (two selects per product).
 //     Zero-padded taps add x * 0 to an accumulator that can never be -0: an exact no-op for finite x; tiles that stage
-//     non-finite or huge (>= 2^113) floats take the per-output path instead.
-// Per 4 input words and warp: 2 LDS.128 of inputs + 8 broadcast LDS.128 of taps feed 32 FFMA2 (64 FMA lanes-pairs):
-// 10 shared-memory instructions / 16 wavefronts per 32 FFMA2 instead of 13-14 per 32 scalar FFMA.
+//     non-finite or huge (>= 2^113) floats take the per-output path instead;
+//   * the 8 virtual lanes of every output are split over a lane quad (pair, for period columns) that shares 8 (4) columns, and
+//     exchanged with shuffles after the walk: a thread tile is 8 tap rows x 8 columns of accumulator pairs (128 registers),
+//     fed by 16 LDS.64 per 64 FFMA2.
 //
 // Lanes whose own plan entries differ from the group's reference entries (possible only for period columns, where the f64
 // index walk lands within rounding of a table-row boundary for some periods but not others) recompute their outputs with the
@@ -42,6 +45,12 @@ constexpr int kG3Rows = 2 * kG3A;
 constexpr int kG3PadL = 32;                       // largest staged shift (multiple of 4)
 constexpr int kG3RowLen = kG3PadL + 288 + 4;      // 324 words: the longest tap walk (288) starting at any offset <= kG3PadL, + the shift
 
+// The tap walk is NOT fully unrolled.  264 words = 33 blocks x (64 FFMA2 + 16 LDS) is 42 KB of straight-line code; streamed through
+// the instruction cache it caps a scheduler at ~0.45 issued instructions per clock whatever the instruction mix
+// (tools/ub/ub_lds_split.cu: ncu stall reason no_instructions, walk alone 41-45 TFLOP/s fully unrolled, 54-56 as a loop of
+// 3-11 blocks).  The walk therefore runs as a short loop of g3_walk_unroll<MLEN>() blocks that stays resident.
+// (A trip count that is not a multiple of the unroll factor gets a compiler-generated remainder loop.)
+template <int MLEN> __host__ __device__ constexpr int g3_walk_unroll() { return (MLEN / 8) % 12 == 0 ? 12 : 11; }
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -202,9 +211,10 @@ __device__ __forceinline__ void g3_stage_tile(const SrcDesc& src, const OutDesc&
 
 }
 
-// XVEC == 4 / 8: lane columns only (P == 1, C == 64): every column shares every plan entry, windows and group bases are 16-byte
+// XVEC == 8: lane columns only (P == 1, C == 64): every column shares every plan entry, windows and group bases are 16-byte
 // aligned (vector input loads).  XVEC == 1: period columns (P > 1): scalar input loads, per-column plan entries checked
-// against the group's reference entries.
+// against the group's reference entries; the accumulator lanes are split over lane PAIRS (q, q + 16; 4 columns per thread,
+// LDS.128 tap loads).
 // XVEC == 8 is the QUAD form: the 8 accumulator lanes of an output are split over FOUR threads (q, q + 8, q + 16, q + 24) that
 // share 8 columns; quarter hh walks words m + 2 hh, m + 2 hh + 1 of every 8-word block, so every load is an LDS.64 and a thread
 // tile is 8 tap rows x 8 columns: 16 x 8 bytes arrive in registers per 64 FFMA2 instead of 12 x 16 (the register tile is
@@ -216,7 +226,7 @@ __global__ void __launch_bounds__(kG3Threads, 1)
 resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant__ OutDesc dst, const __grid_constant__ Gen3Geom geo,
                      const int32_t* __restrict__ pi0, const uint8_t* __restrict__ ps0, const float* __restrict__ pfrac,
                      const float* __restrict__ table, const float* __restrict__ table4, int lanes_per_stream, unsigned long long* __restrict__ stats) {
-    constexpr bool kLanes = XVEC >= 4, kQuad = XVEC == 8;
+    constexpr bool kLanes = XVEC == 8, kQuad = kLanes;
     constexpr int A = kG3A, B = kQuad ? 8 : kG3B;
     constexpr int NP = kQuad ? 1 : 2;   // accumulator pairs (of the thread's 2 or 4 virtual lanes) per product
     constexpr int HW = kQuad ? 2 : 4;   // words of every 8-word block this thread walks
@@ -279,22 +289,29 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
         for (int a = 0; a < A; a++) dmax = max(dmax, shift_of(r, a, 1));
         return SINC_LEN + dmax <= MLEN && dmax <= kG3PadL;
     };
-    auto load_ref = [&](int ph0, int (&i0v)[A], int (&s0v)[A]) {
+    // raw plan entries of a group: the four window starts and the four subindices packed as GroupRef::s0p packs them — one
+    // 128-bit and one 32-bit load when the group is whole and aligned, clamped scalar loads at ragged ends
+    auto load_ref = [&](int ph0, int (&i0v)[A], unsigned& s0p) {
+        static_assert(A == 4, "vector form of the plan loads");
+        if (ph0 + A <= min(geo.period, nt) && ((reinterpret_cast<uintptr_t>(pi0 + ph0) & 15) | (reinterpret_cast<uintptr_t>(ps0 + ph0) & 3)) == 0) {
+            const int4 v = __ldg(reinterpret_cast<const int4*>(pi0 + ph0));
+            i0v[0] = v.x; i0v[1] = v.y; i0v[2] = v.z; i0v[3] = v.w;
+            s0p = __ldg(reinterpret_cast<const unsigned*>(ps0 + ph0));
+        } else {
+            s0p = 0;
 #pragma unroll
-        for (int a = 0; a < A; a++) {
-            const int nr = min(min(ph0 + a, geo.period - 1), nt - 1);
-            i0v[a] = pi0[nr];
-            s0v[a] = ps0[nr];
+            for (int a = 0; a < A; a++) {
+                const int nr = min(min(ph0 + a, geo.period - 1), nt - 1);
+                i0v[a] = pi0[nr];
+                s0p |= (unsigned)ps0[nr] << (8 * a);
+            }
         }
     };
-    auto make_ref = [&](const int (&i0v)[A], const int (&s0v)[A], GroupRef& r) {
+    auto make_ref = [&](const int (&i0v)[A], unsigned s0p, GroupRef& r) {
         const int fix = kLanes ? ((i0v[0] - w0) & 3) : 0;
-        r.base = i0v[0] - fix; r.s0p = 0; r.dp = 0;
+        r.base = i0v[0] - fix; r.s0p = s0p; r.dp = 0;
 #pragma unroll
-        for (int a = 0; a < A; a++) {
-            r.s0p |= (unsigned)s0v[a] << (8 * a);
-            r.dp |= (unsigned)min(255, max(0, i0v[a] - i0v[0] + fix)) << (8 * a);
-        }
+        for (int a = 0; a < A; a++) r.dp |= (unsigned)min(255, max(0, i0v[a] - i0v[0] + fix)) << (8 * a);
     };
     // stage the 8 shifted rows of a group (warp private): one TMA bulk copy per row from the pre-shifted table copies (16-byte
     // aligned slices of MLEN words), issued by lane 0 and completed on the warp's mbarrier — ~40 instructions in one lane
@@ -321,17 +338,21 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
     const int groups = min((geo.period + A - 1) / A, (nt + A - 1) / A);  // groups that exist in period 0 (later periods start later still)
     GroupRef cur = {0, 0u, 0u};
     if (warp < groups) {
-        int i0v[A], s0v[A];
-        load_ref(warp * A, i0v, s0v);
-        make_ref(i0v, s0v, cur);
+        int i0v[A];
+        unsigned s0p;
+        load_ref(warp * A, i0v, s0p);
+        make_ref(i0v, s0p, cur);
         stage_taps(cur);
     }
     for (int g = warp; g < groups; g += kG3Warps) {
         const int ph0 = g * A;
         const bool have_next = g + kG3Warps < groups;
-        if (have_next) {  // pull the next group's plan entries into L1 now (no registers held across the walk)
-            const int nr = min((g + kG3Warps) * A, nt - 1);
-            prefetch_l1(pi0 + nr); prefetch_l1(ps0 + nr);
+        int i0n[A] = {0, 0, 0, 0};  // the next group's raw plan entries: requested now, consumed after the walk (five registers across it)
+        unsigned s0n = 0;
+        constexpr bool kCarry = kLanes;  // period columns hold per-column offsets across the walk: no registers to spare there
+        if (have_next) {
+            if constexpr (kCarry) load_ref((g + kG3Warps) * A, i0n, s0n);
+            else { const int nr = min((g + kG3Warps) * A, nt - 1); prefetch_l1(pi0 + nr); prefetch_l1(ps0 + nr); }
         }
         const bool cur_ok = ref_ok(cur);
         const int fix = (int)(cur.dp & 255u);  // shift of output 0, product 0 == the alignment fix
@@ -386,15 +407,13 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
             const float* Th = T + HW * hh;
 #pragma unroll
             for (int i = 0; i < A * B * 2 * NP; i++) (&acc[0][0][0][0])[i] = 0ull;
-#pragma unroll
+#pragma unroll(kLanes ? g3_walk_unroll<MLEN>() : MLEN / 8)
             for (int m = 0; m < MLEN; m += 8) {
                 unsigned long long xp[B][NP];
 #pragma unroll
                 for (int b = 0; b < B; b++) {
                     if constexpr (kQuad) {
                         asm volatile("ld.shared.b64 %0, [%1];" : "=l"(xp[b][0]) : "r"(smem_u32(xb[b] + m)));
-                    } else if constexpr (kLanes) {
-                        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xp[b][0]), "=l"(xp[b][NP - 1]) : "r"(smem_u32(xb[b] + m)));
                     } else {
                         xp[b][0] = pack2(xb[b][m], xb[b][m + 1]);
                         xp[b][NP - 1] = pack2(xb[b][m + 2], xb[b][m + 3]);
@@ -417,8 +436,7 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
         // ---- the rows are consumed: request the next group's while this one is finished
         __syncwarp();
         if (have_next) {
-            int i0n[A], s0n[A];
-            load_ref((g + kG3Warps) * A, i0n, s0n);
+            if constexpr (!kCarry) load_ref((g + kG3Warps) * A, i0n, s0n);
             make_ref(i0n, s0n, cur);
             stage_taps(cur);
         }
@@ -430,6 +448,7 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
 #pragma unroll
             for (int a = 0; a < A; a++) frv[a][bb] = pfrac[min(rb + a, nt - 1)];
         }
+        float* const dst_row[2] = {s_col_dst[col_lane(0)], s_col_dst[col_lane(1)]};  // requested ahead of the exchange, used by the stores
         float P0[A][2], P1[A][2];  // the two products of the 4 outputs of the 2 columns this thread finishes (slots 0, 1)
 #pragma unroll
         for (int a = 0; a < A; a++)
@@ -521,7 +540,7 @@ resample_gen3_kernel(const __grid_constant__ SrcDesc src, const __grid_constant_
                         if ((redo >> a) & 1u) y[a] = g3_exact(wc, w0, pi0, ps0, rb + a, table, frv[a][kLanes ? 0 : bb]);
                     atomicAdd(stats, (unsigned long long)__popc(redo));
                 }
-                float* op = s_col_dst[cl] + rb;
+                float* op = dst_row[bb] + rb;
                 if (nv == A && ((((uintptr_t)op) & 15) == 0)) {
                     *reinterpret_cast<float4*>(op) = make_float4(y[0], y[1], y[2], y[3]);
                 } else {
@@ -644,7 +663,7 @@ resample_gen3_fast_kernel(const __grid_constant__ SrcDesc src, const __grid_cons
             unsigned long long acc[A][B][2];
 #pragma unroll
             for (int i = 0; i < A * B * 2; i++) (&acc[0][0][0])[i] = 0ull;
-#pragma unroll
+#pragma unroll(g3_walk_unroll<MLEN>())
             for (int m = 0; m < MLEN; m += 8) {
                 unsigned long long xp[B][2];
 #pragma unroll
@@ -817,8 +836,6 @@ int sk_launch_gen3(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const sk
         int rc;
         if (fast) rc = mlen == 272 ? launch_gen3_fast_t<272>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem)
                                    : launch_gen3_fast_t<288>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem);
-        else if (g.xvec && getenv("SK_GEN3_PAIR")) rc = mlen == 264 ? launch_gen3_t<4, 264>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem)
-                                     : launch_gen3_t<4, 272>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem);
         else if (g.xvec) rc = mlen == 264 ? launch_gen3_t<8, 264>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem)
                                      : launch_gen3_t<8, 272>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem);
         else rc = mlen == 264 ? launch_gen3_t<1, 264>(ctx, s2, d2, g2, plan, d_table, d_table4, lanes_per_stream, grid, smem)

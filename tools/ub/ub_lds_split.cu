@@ -60,7 +60,7 @@ static void run_lds(const char* name) {
 // ---- (2) the walk.  SPLIT = 2: lane pair, 4 columns x 4 outputs x 2 products x 4 virtual lanes per thread (LDS.128);
 //                     SPLIT = 4: lane quad, 8 columns x 4 outputs x 2 products x 2 virtual lanes per thread (LDS.64).
 constexpr int MLEN = 264, ROWS = 8, TS = MLEN, CSTRIDE = 548;  // CSTRIDE / 4 odd
-template <int SPLIT, int LOADS>
+template <int SPLIT, int LOADS, int UNROLL>
 __global__ void __launch_bounds__(256, 1) walk_k(float* sink, int groups) {
     extern __shared__ __align__(16) float sm[];
     float* taps = sm;                     // [8 warps][8 rows][TS]
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256, 1) walk_k(float* sink, int groups) {
             for (int i = 0; i < 64; i++) (&acc[0][0][0][0])[i] = 0ull;
             const int xo = (g & 7) * 4;
             unsigned long long xp[4][2], tt[8][2];
-#pragma unroll
+#pragma unroll UNROLL
             for (int m = 0; m < MLEN; m += 8) {
 #pragma unroll
                 for (int b = 0; b < 4; b++) if (LOADS == 2 || m == 0) asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xp[b][0]), "=l"(xp[b][1]) : "r"(smem_u32(xb[b] + xo + m)));
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256, 1) walk_k(float* sink, int groups) {
             for (int i = 0; i < 64; i++) (&acc[0][0][0])[i] = 0ull;
             const int xo = (g & 7) * 4;
             unsigned long long xp[8], tt[8];
-#pragma unroll
+#pragma unroll UNROLL
             for (int m = 0; m < MLEN; m += 8) {
 #pragma unroll
                 for (int b = 0; b < 8; b++) if (LOADS == 2 || m == 0) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(xp[b]) : "r"(smem_u32(xb[b] + xo + m)));
@@ -126,25 +126,84 @@ __global__ void __launch_bounds__(256, 1) walk_k(float* sink, int groups) {
     if (total == 0x1234567ull) sink[0] = 1.0f;
 }
 
-template <int SPLIT, int LOADS>
-static void run_walk() {
+template <int SPLIT, int LOADS, int UNROLL = 33>
+static void run_walk(int threads = 256) {
     int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     float* sink; cudaMalloc(&sink, 4);
     const int smem = (8 * ROWS * TS + 64 * CSTRIDE) * 4;
-    cudaFuncSetAttribute(walk_k<SPLIT, LOADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(walk_k<SPLIT, LOADS, UNROLL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const int groups = 400;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e9f;
     for (int rep = 0; rep < 4; rep++) {
         cudaEventRecord(e0);
-        walk_k<SPLIT, LOADS><<<sms, 256, smem>>>(sink, groups);
+        walk_k<SPLIT, LOADS, UNROLL><<<sms, threads, smem>>>(sink, groups);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (rep && ms < best) best = ms;
     }
     // per thread and group: (MLEN / 8) blocks x 64 FFMA2 x 4 flop
-    const double flops = (double)groups * (MLEN / 8) * 64 * 4 * 256 * sms;
-    printf("walk, accumulator lanes split over %d threads, loads in the loop: %s: %.2f TFLOP/s executed (%.3f ms)\n", SPLIT, LOADS == 2 ? "x + taps" : LOADS == 1 ? "taps only" : "none", flops / (best * 1e-3) / 1e12, best);
+    const double flops = (double)groups * (MLEN / 8) * 64 * 4 * threads * sms;
+    printf("walk, unroll %2d blocks, %d warps/SM, accumulator lanes split over %d threads, loads in the loop: %s: %.2f TFLOP/s executed (%.3f ms)\n", UNROLL, threads / 32, SPLIT, LOADS == 2 ? "x + taps" : LOADS == 1 ? "taps only" : "none", flops / (best * 1e-3) / 1e12, best);
+    cudaFree(sink);
+}
+
+// ---- (3) 16 warps per SM, quad split, 4 tap rows (2 outputs x 2 products) x 8 columns per thread: 32 accumulator pairs, <= 128 registers
+template <int UNROLL>
+__global__ void __launch_bounds__(512, 1) walk16_k(float* sink, int groups) {
+    extern __shared__ __align__(16) float sm[];
+    float* taps = sm;                       // [16 warps][4 rows][TS]
+    float* win = sm + 16 * 4 * TS;          // [64 columns][CSTRIDE]
+    for (int i = threadIdx.x; i < 16 * 4 * TS + 64 * CSTRIDE; i += blockDim.x) sm[i] = 1.0f / (float)(1 + (i & 1023));
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, q = threadIdx.x & 31;
+    const float* T = taps + warp * 4 * TS;
+    unsigned long long total = 0;
+    const int ql = q & 7, hq = q >> 3;
+    const float* xb[8];
+    for (int b = 0; b < 8; b++) xb[b] = win + (ql + 8 * (b ^ (2 * hq))) * CSTRIDE + 2 * hq;
+    const float* Th = T + 2 * hq;
+    for (int g = 0; g < groups; g++) {
+        unsigned long long acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 32; i++) (&acc[0][0])[i] = 0ull;
+        const int xo = (g & 7) * 4;
+#pragma unroll UNROLL
+        for (int m = 0; m < MLEN; m += 8) {
+            unsigned long long xp[8];
+#pragma unroll
+            for (int b = 0; b < 8; b++) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(xp[b]) : "r"(smem_u32(xb[b] + xo + m)));
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                unsigned long long t0;
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(t0) : "r"(smem_u32(Th + r * TS + m)));
+#pragma unroll
+                for (int b = 0; b < 8; b++) ffma2(acc[r][b], xp[b], t0);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i++) total ^= (&acc[0][0])[i];
+    }
+    if (total == 0x1234567ull) sink[0] = 1.0f;
+}
+template <int UNROLL>
+static void run_walk16() {
+    int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    float* sink; cudaMalloc(&sink, 4);
+    const int smem = (16 * 4 * TS + 64 * CSTRIDE) * 4;
+    cudaFuncSetAttribute(walk16_k<UNROLL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int groups = 400;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e9f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        walk16_k<UNROLL><<<sms, 512, smem>>>(sink, groups);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep && ms < best) best = ms;
+    }
+    const double flops = (double)groups * (MLEN / 8) * 32 * 4 * 512 * sms;
+    printf("walk, unroll %2d blocks, 16 warps/SM, quad split, 4 rows x 8 columns per thread: %.2f TFLOP/s executed (%.3f ms)\n", UNROLL, flops / (best * 1e-3) / 1e12, best);
     cudaFree(sink);
 }
 
@@ -159,11 +218,10 @@ int main() {
     run_lds<16, 1>("one address per half-warp");
     run_lds<16, 2>("one address per quarter-warp");
     run_lds<16, 3>("32 distinct (512 B)");
-    run_walk<2, 2>();
-    run_walk<4, 2>();
-    run_walk<2, 1>();
-    run_walk<4, 1>();
-    run_walk<2, 0>();
-    run_walk<4, 0>();
+    run_walk<2, 2, 33>(); run_walk<2, 2, 11>(); run_walk<2, 2, 3>(); run_walk<2, 2, 1>();
+    run_walk<4, 2, 33>(); run_walk<4, 2, 11>(); run_walk<4, 2, 3>(); run_walk<4, 2, 1>();
+    run_walk<4, 0, 33>(); run_walk<4, 0, 3>();
+    run_walk<2, 2, 3>(128); run_walk<4, 2, 3>(128); run_walk<4, 0, 3>(128);
+    run_walk16<33>(); run_walk16<11>(); run_walk16<3>();
     return 0;
 }
