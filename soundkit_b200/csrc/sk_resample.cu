@@ -1075,9 +1075,11 @@ struct sk_resampler_batch {
     uint32_t in_rate, out_rate;
     double ratio;
     int channels;
-    size_t n_streams, max_push, row;   // row = 2 * SINC_LEN + STREAM_CHUNK + max_push floats per lane
+    size_t n_streams, max_push, row;   // row = 4 + 2 * SINC_LEN + STREAM_CHUNK + max_push floats per lane
     float* d_rows[2] = {nullptr, nullptr};
     int cur = 0;
+    size_t pad = 0;                    // the history starts at element `pad` (0..3) of a row: integer ratios keep every tile window of the
+                                       // next run on a 16-byte boundary of the row, so the planar TMA kernel can fetch it
     size_t pending = 0;                // frames waiting behind the history in d_rows[cur]
     double last_index;
     sk_plan plan;                      // per call (general ratios: arrays re-uploaded per call)
@@ -1098,7 +1100,7 @@ extern "C" int sk_resampler_batch_create(sk_ctx* ctx, uint32_t in_rate, uint32_t
     if (!b) SK_FAIL(ctx, SK_E_ALLOC, "out of memory");
     b->ctx = ctx; b->in_rate = in_rate; b->out_rate = out_rate; b->ratio = (double)out_rate / (double)in_rate;
     b->channels = channels; b->n_streams = n_streams; b->max_push = max_push_frames;
-    b->row = sk_round_up(2 * SINC_LEN + STREAM_CHUNK + max_push_frames, 4);
+    b->row = sk_round_up(4 + 2 * SINC_LEN + STREAM_CHUNK + max_push_frames, 4);
     b->last_index = -(double)(SINC_LEN / 2);
     const size_t bytes = n_streams * (size_t)channels * b->row * sizeof(float);
     for (int i = 0; i < 2; i++) {
@@ -1199,7 +1201,7 @@ static int batch_run_chunks(sk_resampler_batch* b, size_t chunks, size_t valid, 
         src.stream_stride = (long long)((size_t)b->channels * b->row * sizeof(float));
         src.lane_stride = (long long)(b->row * sizeof(float));
         src.width = 0; src.channels = b->channels; src.scale = 1.0f;
-        src.origin = 2 * SINC_LEN; src.valid_lo = -(long long)(2 * SINC_LEN); src.valid_hi = (long long)valid;
+        src.origin = 2 * SINC_LEN + (long long)b->pad; src.valid_lo = -(long long)(2 * SINC_LEN); src.valid_hi = (long long)valid;
         OutDesc dst;
         dst.base = out; dst.stream_stride = (long long)out_stream_stride; dst.lane_stride = (long long)out_ch_stride; dst.mix = SK_MIX_NONE;
         dst.n_out = (long long)n;
@@ -1211,13 +1213,45 @@ static int batch_run_chunks(sk_resampler_batch* b, size_t chunks, size_t valid, 
     return SK_OK;
 }
 
+// rows x `count` floats between pitched planes, 4 floats per thread (cudaMemcpy2DAsync moves these 16 KB rows at a third of the HBM
+// rate): 128-bit accesses where the row starts allow it, scalar otherwise — coalesced either way
+__global__ void __launch_bounds__(256) rows_copy_kernel(float* __restrict__ dst, size_t dst_pitch, const float* __restrict__ src, size_t src_pitch, size_t count,
+                                                        size_t rows, int vec_ld, int vec_st) {
+    const size_t per_row = (count + 3) / 4;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= per_row * rows) return;
+    const size_t r = i / per_row, c = 4 * (i - r * per_row);
+    const float* sp = src + r * src_pitch + c;
+    float* dp = dst + r * dst_pitch + c;
+    if (c + 4 <= count) {
+        float4 v;
+        if (vec_ld) v = __ldg(reinterpret_cast<const float4*>(sp));
+        else { v.x = __ldg(sp); v.y = __ldg(sp + 1); v.z = __ldg(sp + 2); v.w = __ldg(sp + 3); }
+        if (vec_st) *reinterpret_cast<float4*>(dp) = v;
+        else { dp[0] = v.x; dp[1] = v.y; dp[2] = v.z; dp[3] = v.w; }
+    } else {
+        for (size_t k = c; k < count; k++) dst[r * dst_pitch + k] = __ldg(src + r * src_pitch + k);
+    }
+}
+static int rows_copy(sk_ctx* ctx, float* dst, size_t dst_pitch, const float* src, size_t src_pitch, size_t count, size_t rows) {
+    if (!count || !rows) return SK_OK;
+    const size_t threads = ((count + 3) / 4) * rows;
+    const int vec_ld = ((uintptr_t)src % 16) == 0 && (src_pitch % 4) == 0, vec_st = ((uintptr_t)dst % 16) == 0 && (dst_pitch % 4) == 0;
+    rows_copy_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(dst, dst_pitch, src, src_pitch, count, rows, vec_ld, vec_st);
+    SK_LAUNCH_CHECK(ctx);
+    return SK_OK;
+}
+
 // new history (the last 2 * SINC_LEN frames consumed) + the unconsumed remainder -> front of the other row buffer
 static int batch_carry(sk_resampler_batch* b, size_t consumed, size_t total) {
     sk_ctx* ctx = b->ctx;
     const size_t lanes = b->n_streams * (size_t)b->channels;
     const size_t keep = 2 * SINC_LEN + (total - consumed);
-    SK_CUDA(ctx, cudaMemcpy2DAsync(b->d_rows[b->cur ^ 1], b->row * sizeof(float), b->d_rows[b->cur] + consumed, b->row * sizeof(float), keep * sizeof(float), lanes,
-                                   cudaMemcpyDeviceToDevice, ctx->stream));
+    // integer ratios: the next run's first window frame is (long long)last_index + step - step % 8 before frame 0, i.e. congruent to
+    // last_index modulo 4 — start the history where that lands on a 16-byte boundary
+    const size_t new_pad = b->plan.integer_step ? (size_t)((-(long long)b->last_index) & 3) : 0;
+    if (int rc = rows_copy(ctx, b->d_rows[b->cur ^ 1] + new_pad, b->row, b->d_rows[b->cur] + b->pad + consumed, b->row, keep, lanes)) return rc;
+    b->pad = new_pad;
     b->cur ^= 1;
     b->pending = total - consumed;
     return SK_OK;
@@ -1235,16 +1269,15 @@ extern "C" int sk_resampler_batch_process_dev(sk_resampler_batch* b, const float
     if (!in || !out) SK_FAIL(ctx, SK_E_ARG, "null buffer");
     SK_CUDA(ctx, cudaSetDevice(ctx->device));
     // append behind the pending frames: one 2-D copy per channel plane set
-    float* row0 = b->d_rows[b->cur] + 2 * SINC_LEN + b->pending;
+    float* row0 = b->d_rows[b->cur] + b->pad + 2 * SINC_LEN + b->pending;
     if (in_ch_stride * (size_t)b->channels == in_stream_stride || b->channels == 1 || b->n_streams == 1) {
         // lanes are equally spaced in the source: a single 2-D copy
         const size_t lane_pitch = b->channels == 1 ? in_stream_stride : in_ch_stride;
-        SK_CUDA(ctx, cudaMemcpy2DAsync(row0, b->row * sizeof(float), in, lane_pitch * sizeof(float), frames * sizeof(float), b->n_streams * (size_t)b->channels,
-                                       cudaMemcpyDeviceToDevice, ctx->stream));
+        if (int rc = rows_copy(ctx, row0, b->row, in, lane_pitch, frames, b->n_streams * (size_t)b->channels)) return rc;
     } else {
         for (int c = 0; c < b->channels; c++)
-            SK_CUDA(ctx, cudaMemcpy2DAsync(row0 + (size_t)c * b->row, (size_t)b->channels * b->row * sizeof(float), in + (size_t)c * in_ch_stride,
-                                           in_stream_stride * sizeof(float), frames * sizeof(float), b->n_streams, cudaMemcpyDeviceToDevice, ctx->stream));
+            if (int rc = rows_copy(ctx, row0 + (size_t)c * b->row, (size_t)b->channels * b->row, in + (size_t)c * in_ch_stride, in_stream_stride, frames, b->n_streams))
+                return rc;
     }
     const size_t total = b->pending + frames;
     const size_t chunks = total / STREAM_CHUNK;
@@ -1265,7 +1298,7 @@ extern "C" int sk_resampler_batch_flush_dev(sk_resampler_batch* b, float* out, s
     const size_t remaining = b->pending;
     const size_t lanes = b->n_streams * (size_t)b->channels;
     // the zero padding becomes part of the next history: make it real
-    SK_CUDA(ctx, cudaMemset2DAsync(b->d_rows[b->cur] + 2 * SINC_LEN + remaining, b->row * sizeof(float), 0, (STREAM_CHUNK - remaining) * sizeof(float), lanes,
+    SK_CUDA(ctx, cudaMemset2DAsync(b->d_rows[b->cur] + b->pad + 2 * SINC_LEN + remaining, b->row * sizeof(float), 0, (STREAM_CHUNK - remaining) * sizeof(float), lanes,
                                    ctx->stream));
     size_t trim = 0;
     if (remaining > 0) trim = (size_t)llround(((double)(STREAM_CHUNK - remaining) * (double)b->out_rate) / (double)b->in_rate);

@@ -650,8 +650,145 @@ resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant
 }
 
 // ================================================================================================
+// integer-step kernel v3: persistent CTAs, PLANAR f32 rows fetched by the TMA straight into double-buffered windows
+// ================================================================================================
+// The stateful resamplers (sk_resampler, sk_resampler_batch) keep every (stream, channel) lane as a device row of f32
+// [history | pending input].  No conversion pass is needed for such a source, so the TMA writes the two lanes' windows of tile
+// k + 1 directly into the second window buffer while tile k is convolved; tiles (lane pair x 128 R outputs) are drawn by ticket
+// like the interleaved kernel's.  Requires 16-byte aligned rows and (origin + i0_first - LEAD) % 4 == 0, which the batched
+// handle arranges by choosing where in the row it keeps its history; anything else takes resample_int_kernel.
+template <int STEP> __host__ __device__ constexpr int planar_smem_bytes() { return 4 * tma_lane_stride<STEP>() * (int)sizeof(float) + 64; }
+struct PlanarGeom { int stream; int lane0; int n0; int wa; int c_lo; int c_hi; int lane1; int pad; };  // [c_lo, c_hi): window frames the TMA copies
+
+template <int STEP>
+__global__ void __launch_bounds__(kIntThreads, IntCfg<STEP>::CTAS)
+resample_int_planar_kernel(const __grid_constant__ Taps taps, const __grid_constant__ SrcDesc src, const __grid_constant__ OutDesc dst, long long i0_first,
+                           int lanes_per_stream, unsigned tiles_per_lane, unsigned total_tiles, const float* __restrict__ row1, unsigned* __restrict__ ticket) {
+    constexpr int R = IntCfg<STEP>::R;
+    constexpr int T = int_tile_outputs<STEP>();
+    constexpr int LEAD = tma_lead<STEP>();
+    constexpr int WF = tma_frames<STEP>();
+    constexpr int WS = tma_lane_stride<STEP>();
+    static_assert(((LEAD + STEP * (R - 1)) & 1) == 0 || WF > LEAD + int_window<STEP>(), "stage one more frame for this STEP / R");
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float* wins = reinterpret_cast<float*>(smem_raw);  // [2 buffers][2 lanes][WS]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 4 * WS * sizeof(float));
+    __shared__ PlanarGeom geoms[4];
+    const unsigned pps = (unsigned)(lanes_per_stream + 1) >> 1;  // lane pairs per stream
+
+    // one elected thread: ticket and geometry of the CTA's k-th tile -> geoms[k & 3] (stream = -1: no tile left), then the two
+    // bulk copies of the part of the window that lies inside the row's valid frames, rounded inward to whole 16-byte units
+    auto issue = [&](unsigned k) {
+        const unsigned t = atomicAdd(ticket, 1u);
+        if (t >= total_tiles) { geoms[k & 3].stream = -1; return; }
+        const unsigned pair = t / tiles_per_lane, stream = pair / pps;
+        PlanarGeom g;
+        g.stream = (int)stream; g.lane0 = 2 * (int)(pair - stream * pps); g.lane1 = g.lane0 + 1 < lanes_per_stream;
+        g.n0 = (int)((t - pair * tiles_per_lane) * (unsigned)T);
+        const long long wa = i0_first + (long long)STEP * g.n0 - LEAD;  // first frame of the shared window
+        g.wa = (int)wa;
+        const long long lo = wa > src.valid_lo ? wa : src.valid_lo, hi = wa + WF < src.valid_hi ? wa + WF : src.valid_hi;
+        g.c_lo = (int)((lo - wa + 3) & ~3ll);
+        g.c_hi = hi > wa ? (int)((hi - wa) & ~3ll) : 0;
+        if (g.c_hi < g.c_lo) g.c_hi = g.c_lo;
+        geoms[k & 3] = g;
+        const int buf = (int)(k & 1);
+        const uint32_t bar = smem_u32(&bars[buf]);
+        const uint32_t bytes = (uint32_t)(g.c_hi - g.c_lo) * 4u;
+        // the buffer was read by the FIR and patched at its edges through the generic proxy: order that before the async writes
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, g.lane1 ? 2 * bytes : bytes);
+        if (bytes) {
+            const uint8_t* p0 = src.base + (long long)stream * src.stream_stride + (long long)g.lane0 * src.lane_stride + (wa + g.c_lo + src.origin) * 4;
+            float* w = wins + buf * 2 * WS + g.c_lo;
+            tma_load_1d(smem_u32(w), p0, bytes, bar);
+            if (g.lane1) tma_load_1d(smem_u32(w + WS), p0 + src.lane_stride, bytes, bar);
+        }
+    };
+
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&bars[0]), 1);
+        mbar_init(smem_u32(&bars[1]), 1);
+        mbar_fence_init();
+        issue(0);
+        issue(1);
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 1, b = threadIdx.x >> 1;
+    for (unsigned k = 0;; k++) {
+        const PlanarGeom g = geoms[k & 3];
+        if (g.stream < 0) break;  // tickets are monotonic: nothing was requested for this or any later k
+        const int buf = (int)(k & 1);
+        float* win = wins + buf * 2 * WS;
+        // ---- the frames the bulk copies do not cover (up to 3 at either end of the valid range, everything outside it, all of a
+        // missing second lane): frame by frame, zero outside the row's valid frames
+        {
+            const float* p0 = reinterpret_cast<const float*>(src.base + (long long)g.stream * src.stream_stride + (long long)g.lane0 * src.lane_stride);
+            const int edge = g.c_lo + (WF - g.c_hi), edge1 = g.lane1 ? edge : WF;
+            for (int i = threadIdx.x; i < edge + edge1; i += kIntThreads) {
+                const int l = i >= edge, j = l ? i - edge : i;
+                const int f = (l && !g.lane1) ? j : (j < g.c_lo ? j : g.c_hi + (j - g.c_lo));  // window frame
+                const long long ff = (long long)g.wa + f;
+                float v = 0.0f;
+                if ((!l || g.lane1) && ff >= src.valid_lo && ff < src.valid_hi) v = __ldg(p0 + (l ? src.lane_stride / 4 : 0) + ff + src.origin);
+                win[l * WS + f] = v;
+            }
+        }
+        mbar_wait(smem_u32(&bars[buf]), (k >> 1) & 1);
+        __syncthreads();
+        // ---- huge / non-finite inputs take the exact path
+        bool big = false;
+        for (int i = threadIdx.x; i < 2 * (WF / 4); i += kIntThreads) {
+            const int l = i >= WF / 4, j = l ? i - WF / 4 : i;
+            const uint4 u = *reinterpret_cast<const uint4*>(win + l * WS + 4 * j);
+            big |= ((u.x & 0x7f800000u) >= 0x78000000u) | ((u.y & 0x7f800000u) >= 0x78000000u) | ((u.z & 0x7f800000u) >= 0x78000000u) |
+                   ((u.w & 0x7f800000u) >= 0x78000000u);
+        }
+        const int any_big = __syncthreads_or((int)big);
+
+        // ---- FIR
+        const float* w = win + lane * WS + STEP * R * b;
+        float acc[R][8];
+        fir_core2<STEP, R, LEAD>(w, taps, acc);
+        float y[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) y[r] = reduce8(acc[r]);
+        if (any_big) {  // exact slow path, see resample_int_kernel
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const float p0 = dot256(w + LEAD + STEP * r, row1 - SINC_LEN), p1 = dot256(w + LEAD + STEP * r, row1);
+                y[r] = __fadd_rn(p0, __fmul_rn(0.0f, __fsub_rn(p1, p0)));
+            }
+        }
+        int_epilogue<R, false>(y, dst, g.stream, g.n0, b, lane, g.lane0, g.lane1 != 0);
+        __syncthreads();  // this window buffer is free: request the tile after next into it
+        if (threadIdx.x == 0) issue(k + 2);
+    }
+}
+
+// ================================================================================================
 // host: launchers of the integer-step kernels
 // ================================================================================================
+template <int STEP>
+static int launch_int_planar(sk_ctx* ctx, const Taps& taps, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, const float* d_table, size_t n_streams,
+                             int lanes_per_stream) {
+    constexpr int T = int_tile_outputs<STEP>();
+    constexpr int smem = planar_smem_bytes<STEP>();
+    SK_CUDA(ctx, cudaFuncSetAttribute(resample_int_planar_kernel<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const long long tiles_per_lane = (long long)((plan->n_out + T - 1) / T);
+    const long long total = tiles_per_lane * (long long)((lanes_per_stream + 1) / 2) * (long long)n_streams;
+    const int per_sm = std::max(1, std::min(IntCfg<STEP>::CTAS, (220 * 1024) / smem));
+    const long long grid = std::min<long long>(total, (long long)ctx->num_sms * per_sm);
+    constexpr unsigned kTicketRing = 256;
+    if (!ctx->d_tickets) SK_CUDA(ctx, cudaMalloc((void**)&ctx->d_tickets, kTicketRing * sizeof(unsigned)));
+    unsigned* ticket = ctx->d_tickets + (ctx->ticket_next++ % kTicketRing);
+    SK_CUDA(ctx, cudaMemsetAsync(ticket, 0, sizeof(unsigned), ctx->stream));
+    resample_int_planar_kernel<STEP><<<(unsigned)grid, kIntThreads, smem, ctx->stream>>>(taps, src, dst, plan->i0_first, lanes_per_stream, (unsigned)tiles_per_lane,
+                                                                                       (unsigned)total, d_table + SINC_LEN, ticket);
+    SK_LAUNCH_CHECK(ctx);
+    return SK_OK;
+}
 template <int STEP, int SRCW>
 static int launch_int_tma(sk_ctx* ctx, const Taps& taps, const SrcDesc& src, const OutDesc& dst, const sk_plan* plan, const float* d_table, size_t n_streams) {
     constexpr int T = int_tile_outputs<STEP>();
@@ -712,6 +849,11 @@ static int launch_int(sk_ctx* ctx, const SrcDesc& src, const OutDesc& dst, const
             return launch_int_tma<STEP, 4>(ctx, taps, src, dst, plan, d_table, n_streams);
         }
     }
+    // planar f32 rows (the stateful resamplers), aligned so that every tile window starts on a 16-byte boundary of its row
+    if (src.width == 0 && !dst.pcm_bits && ((uintptr_t)src.base % 16) == 0 && (src.stream_stride % 16) == 0 && (src.lane_stride % 16) == 0 &&
+        ((src.origin + plan->i0_first - tma_lead<STEP>()) & 3) == 0 && plan->i0_first > -(1ll << 30) && plan->i0_first < (1ll << 30) && plan->n_out < (1u << 30) &&
+        (long long)n_streams * ((lanes_per_stream + 1) / 2) * (long long)((plan->n_out + int_tile_outputs<STEP>() - 1) / int_tile_outputs<STEP>()) < (1ll << 31))
+        return launch_int_planar<STEP>(ctx, taps, src, dst, plan, d_table, n_streams, lanes_per_stream);
     constexpr int T = int_tile_outputs<STEP>();
     constexpr int smem = int_smem_bytes<STEP>();
     constexpr bool kPcm = int_step_has_pcm<STEP>();
