@@ -564,7 +564,7 @@ def run_ours(args):
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch, same workload only)
     traffic, traffic_src = None, None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         w = tr["workload"]
         if (w["streams_per_gpu"], w["frames_per_stream"], w["bits"], w["channels"]) == (S, frames, BITS, CHANNELS):
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]  # bytes per launch; algorithmic: BYTES_PER_FRAME * S * n_out

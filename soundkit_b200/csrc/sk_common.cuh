@@ -120,21 +120,20 @@ __device__ __forceinline__ float clamp1(float x) { return x < -1.0f ? -1.0f : (x
 __device__ __forceinline__ bool finite_f(float x) { return (__float_as_uint(x) & 0x7f800000u) != 0x7f800000u; }
 
 // float_sample_to_i16, soundkit-decoder/src/lib.rs:1815-1827: non-finite -> 0, clamp, x < 0 ? x * 32768 : x * 32767 IN F64,
-// f64::round (half away from zero), clamp to i16.  Evaluated here without f64 (the FP64 path made the s16 byte writer the
-// one HBM kernel that was compute bound): |x| * 32768 is exact in f32; |x| * 32767 = a - |x| is taken as the f32
-// difference s plus its exact rounding error (Fast2Sum: err = (a - s) - |x|), so floor(s), the exact fraction s - floor(s)
-// and the sign of err decide the rounding exactly as the f64 product would.  Identical to the f64 rule for every float
-// (checked exhaustively over all exponents that can produce a non-zero result, both signs).
+// f64::round (half away from zero), clamp to i16.  Evaluated with ONE f32 operation that rounds once: round-half-away of
+// |v| is floor(|v| + 0.5), and fma.rm(|x|, c, 2^22 + 0.5) forms |x|*c + 0.5 exactly before its single rounding toward -inf
+// to a multiple of 0.5 (every float in [2^22, 2^23) is one) — flooring a value that was floored to halves is flooring the
+// value itself, so the mantissa >> 1 IS the rounded magnitude (its low 16 bits; the exponent sits above bit 22).  |x| <= 1
+// keeps the magnitude <= 32767 (>= 0) / 32768 (< 0): the reference's final clamp never acts.  No f64, no conversion
+// instruction (history: the FP64 form made the s16 byte writer compute bound; a Fast2Sum f32 form with FRND + F2I still
+// kept the ALU pipe 80 % busy at 0.88 of the HBM rate).  Callers keep the low 16 bits.
 __device__ __forceinline__ int32_t float_sample_to_i16_dev(float s) {
-    const float f = finite_f(s) ? clamp1(s) : 0.0f;
-    const float m = fabsf(f);
-    const float a = __fmul_rn(m, 32768.0f);
-    const bool neg = f < 0.0f;
-    const float sv = neg ? a : __fsub_rn(a, m);
-    const float err = neg ? 0.0f : __fsub_rn(__fsub_rn(a, sv), m);
-    const float t = floorf(sv), fr = __fsub_rn(sv, t);
-    const int r = __float2int_rz(t) + (int)((fr > 0.5f) || (fr == 0.5f && err >= 0.0f));
-    return max(-32768, min(32767, neg ? -r : r));
+    const bool fin = fabsf(s) <= 3.402823466e+38f;       // false for NaN and +-Inf
+    const float m = fin ? fminf(fabsf(s), 1.0f) : 0.0f;
+    const bool neg = s < 0.0f;
+    const float q = __fmaf_rd(m, neg ? 32768.0f : 32767.0f, 4194304.5f);
+    const int r = (int)((__float_as_uint(q) >> 1) & 0xffffu);
+    return neg ? -r : r;
 }
 // audio_bytes.rs:205-220 / decoder lib.rs:3653-3659
 __device__ __forceinline__ int32_t f32_to_s24_dev(float x) {

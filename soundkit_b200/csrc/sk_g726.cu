@@ -53,96 +53,49 @@ template <> struct G726Tab<5> {
 
 // quan(value, &POWER2) (:465-470): first i < 15 with value < 2^i, else 15 == min(bit_length(value), 15), 0 for value <= 0
 __device__ __forceinline__ int g726_quan2(int v) { return v <= 0 ? 0 : min(32 - __clz(v), 15); }
+// PTX shifts clamp their amount to the register width (a C++ shift by 32 is undefined): x << 32 == 0, x >> 32 == 0
+__device__ __forceinline__ uint32_t g726_shl(uint32_t x, int n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n)); return r; }
+__device__ __forceinline__ uint32_t g726_shr(uint32_t x, int n) { uint32_t r; asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n)); return r; }
 
-__device__ __forceinline__ int g726_fmult(int an, int srn) {  // :472-497
-    const int anmag = an > 0 ? an : ((-an) & 0x1FFF);
-    const int anexp = g726_quan2(anmag) - 6;
-    const int anmant = anmag == 0 ? 32 : (anexp >= 0 ? anmag >> anexp : anmag << -anexp);
-    const int wanexp = anexp + ((srn >> 6) & 0x0F) - 13;
-    const int wanmant = (anmant * (srn & 0x3F) + 0x30) >> 4;
-    const int retval = wanexp >= 0 ? ((wanmant << wanexp) & 0x7FFF) : (wanmant >> -wanexp);
-    return ((an ^ srn) < 0) ? -retval : retval;
+// One delay-line entry (dq[i] / sr[i], the `exp << 6 + mantissa` log format of :425-452 with the sign as −0x400) together with
+// the fields every later sample reads from it, decoded once when the entry is made instead of eight times per sample:
+// m8 = mantissa << 8, kk = 30 − exponent, sg = ±1.
+struct G726Tap { int m8, kk, sg; };
+__device__ __forceinline__ G726Tap g726_tap(int raw) {
+    G726Tap t;
+    t.m8 = (raw & 0x3F) << 8; t.kk = 30 - ((raw >> 6) & 0xF); t.sg = (raw >> 31) | 1;
+    return t;
+}
+// the word the reference keeps for an entry (exact for every entry the algorithm itself makes out of a 15-bit magnitude)
+__device__ __forceinline__ int g726_tap_raw(const G726Tap& t) { return ((30 - t.kk) << 6) + (t.m8 >> 8) - (t.sg < 0 ? 0x400 : 0); }
+// log format of a magnitude < 2^15 (0 -> 0x20, :441 / :450) with the sign `neg`
+__device__ __forceinline__ G726Tap g726_tap_of(int mag, bool neg) {
+    const int c = __clz(mag);                                             // 32 for 0
+    const int m = max((int)(g726_shl((uint32_t)mag, c) >> 26), 32);       // the 6 leading bits; 32 for mag == 0
+    G726Tap t;
+    t.m8 = m << 8; t.kk = c - 2; t.sg = neg ? -1 : 1;
+    return t;
 }
 
-struct G726Core { int s[G726_NSTATE]; };
-
-__device__ __forceinline__ int g726_step_size(const G726Core& c) {  // :317-332
-    if (c.s[G_AP] >= 256) return c.s[G_YU];
-    const int y = c.s[G_YL] >> 6, dif = c.s[G_YU] - y, al = c.s[G_AP] >> 2;
-    if (dif > 0) return y + ((dif * al) >> 6);
-    if (dif < 0) return y + ((dif * al + 0x3F) >> 6);
-    return y;
-}
-__device__ __forceinline__ int g726_reconstruct(bool sign, int dqln, int y) {  // :517-536
-    const int dql = dqln + (y >> 2);
-    if (dql < 0) return sign ? -0x8000 : 0;
-    const int dex = (dql >> 7) & 15, dqt = 128 + (dql & 127);
-    const int dq = (dqt << 7) >> (14 - dex);
-    return sign ? dq - 0x8000 : dq;
-}
-// log-format of a magnitude (the `exp << 6 + mantissa` form stored in dq[] / sr[], :425-452)
-__device__ __forceinline__ int g726_logfmt(int mag) { const int e = g726_quan2(mag); return (e << 6) + ((mag << 6) >> e); }
-
-template <bool IS40>
-__device__ __forceinline__ void g726_update(G726Core& c, int y, int wi, int fi, int dq, int sr, int dqsez) {  // :334-462
-    int* s = c.s;
-    const int pk0 = dqsez < 0, mag = dq & 0x7FFF;
-    const int ylint = s[G_YL] >> 15, ylfrac = (s[G_YL] >> 10) & 0x1F;
-    const int thr1 = (32 + ylfrac) << ylint;
-    const int thr2 = ylint > 9 ? (31 << 10) : thr1;
-    const int dqthr = (thr2 + (thr2 >> 1)) >> 1;
-    const bool tr = s[G_TD] != 0 && mag > dqthr;
-    s[G_YU] = max(544, min(5120, y + ((wi - y) >> 5)));
-    s[G_YL] += s[G_YU] + ((-s[G_YL]) >> 6);
-    int a2p = 0;
-    if (tr) {
-        s[G_A0] = 0; s[G_A1] = 0;
-#pragma unroll
-        for (int i = 0; i < 6; i++) s[G_B0 + i] = 0;
-    } else {
-        const int pks1 = pk0 ^ s[G_PK0];
-        a2p = s[G_A1] - (s[G_A1] >> 7);
-        if (dqsez != 0) {
-            const int fa1 = pks1 ? s[G_A0] : -s[G_A0];
-            a2p += fa1 < -8191 ? -0x100 : (fa1 > 8191 ? 0xFF : (fa1 >> 5));
-            if (pk0 ^ s[G_PK1]) a2p = a2p <= -12160 ? -12288 : (a2p >= 12416 ? 12288 : a2p - 0x80);
-            else a2p = a2p <= -12416 ? -12288 : (a2p >= 12160 ? 12288 : a2p + 0x80);
-        }
-        s[G_A1] = a2p;
-        s[G_A0] -= s[G_A0] >> 8;
-        if (dqsez != 0) s[G_A0] += pks1 == 0 ? 192 : -192;
-        const int a1ul = 15360 - a2p;
-        s[G_A0] = max(-a1ul, min(a1ul, s[G_A0]));
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-            s[G_B0 + i] -= s[G_B0 + i] >> (IS40 ? 9 : 8);
-            if (mag != 0) s[G_B0 + i] += ((dq ^ s[G_DQ0 + i]) >= 0) ? 128 : -128;
-        }
-    }
-#pragma unroll
-    for (int i = 5; i >= 1; i--) s[G_DQ0 + i] = s[G_DQ0 + i - 1];
-    s[G_DQ0] = mag == 0 ? (dq >= 0 ? 0x20 : -0x3E0) : (dq >= 0 ? g726_logfmt(mag) : g726_logfmt(mag) - 0x400);
-    s[G_SR1] = s[G_SR0];
-    s[G_SR0] = sr == 0 ? 0x20 : (sr > 0 ? g726_logfmt(sr) : (sr > -32768 ? g726_logfmt(-sr) - 0x400 : -0x3E0));
-    s[G_PK1] = s[G_PK0];
-    s[G_PK0] = pk0;
-    s[G_TD] = tr ? 0 : (a2p < -11776);
-    s[G_DMS] += (fi - s[G_DMS]) >> 5;
-    s[G_DML] += ((fi << 2) - s[G_DML]) >> 7;
-    if (tr) s[G_AP] = 256;
-    else if (y < 1536 || s[G_TD] != 0 || abs((s[G_DMS] << 2) - s[G_DML]) >= (s[G_DML] >> 3)) s[G_AP] += (0x200 - s[G_AP]) >> 4;
-    else s[G_AP] += (-s[G_AP]) >> 4;
+// fmult (:472-497) against a decoded entry.  anexp = bit_length(anmag) − 6 and anmant = the 6 leading bits of anmag (32 for 0);
+// the reference's two-sided shift `wanexp >= 0 ? (wanmant << wanexp) & 0x7FFF : wanmant >> -wanexp` is ONE right shift of
+// wanmant << 12 by 12 − wanexp = kk − floor(log2 anmag) ∈ [2, 31] (no low bit is lost while wanexp >= 0, and the mask is a no-op
+// for the right shifts: wanmant < 2^8); `(anmant·m + 0x30) >> 4 << 12` is `(anmant·(m << 8) + 0x3000) & ~0xFFF`.
+__device__ __forceinline__ int g726_fmult(int an, const G726Tap& t) {
+    const int anmag = an > 0 ? an : (abs(an) & 0x1FFF);
+    const int c = __clz(anmag);
+    const int anmant = max((int)(g726_shl((uint32_t)anmag, c) >> 26), 32);
+    const uint32_t p = (uint32_t)(anmant * t.m8 + 0x3000) & ~0xFFFu;
+    const int r = (int)g726_shr(p, t.kk + c - 31) & 0x7FFF;
+    const int s = (an ^ t.sg) >> 31;
+    return (r ^ s) - s;
 }
 
-// signal estimate shared by both directions: sezi (zeros) and se (zeros + poles); the 8 fmult() are independent
-__device__ __forceinline__ void g726_predict(const G726Core& c, int& sez, int& se) {
-    int sezi = 0;
-#pragma unroll
-    for (int i = 0; i < 6; i++) sezi += g726_fmult(c.s[G_B0 + i] >> 2, c.s[G_DQ0 + i]);
-    const int pole = g726_fmult(c.s[G_A1] >> 2, c.s[G_SR1]) + g726_fmult(c.s[G_A0] >> 2, c.s[G_SR0]);
-    sez = sezi >> 1;
-    se = (sezi + pole) >> 1;
-}
+struct G726Core {
+    int yl, yu, dms, dml, ap, a0, a1, b[6], pk0, pk1, td;
+    G726Tap dq[6], sr[2];
+    int sr_raw[2];  // sr can leave the 16-bit range, its log-format word is then not canonical: kept as the reference holds it
+};
 
 // quan(dln, q_table) (:505): the tables are sorted, so "first index with dln < q[i]" is the number of thresholds <= dln;
 // written against literals (G726Tab<BITS>::q) so the search is NQ compares and adds with no memory access
@@ -157,61 +110,127 @@ template <> __device__ __forceinline__ int g726_qcount<5>(int d) {
            (d >= 445) + (d >= 475) + (d >= 502) + (d >= 528) + (d >= 553);
 }
 
-// tab: shared memory [3][32] = dqln | wi << 5 | fi
-template <int BITS>
-__device__ __forceinline__ int g726_decode_code(G726Core& c, int i, const int* tab) {  // :279-303
-    int sez, se;
-    g726_predict(c, sez, se);
-    const int y = g726_step_size(c);
-    const int dq = g726_reconstruct((i & (1 << (BITS - 1))) != 0, tab[i], y);
-    const int sr = dq < 0 ? se - (dq & (BITS == 5 ? 0x7FFF : 0x3FFF)) : se + dq;
-    g726_update<BITS == 5>(c, y, tab[32 + i], tab[64 + i], dq, sr, sr - se + sez);
-    return max(-32768, min(32767, sr << 2));
-}
-template <int BITS>
-__device__ __forceinline__ int g726_encode_sample(G726Core& c, int sample, const int* tab) {  // :249-277
-    int sez, se;
-    g726_predict(c, sez, se);
-    const int d = (sample >> 2) - se;
-    const int y = g726_step_size(c);
-    // quantize, :499-515: the sorted threshold search is a count of thresholds <= dln, against immediates
-    const int dqm = abs(d);
-    const int e = g726_quan2(dqm >> 1);
-    const int dln = (e << 7) + (((dqm << 7) >> e) & 0x7F) - (y >> 2);
-    const int q = g726_qcount<BITS>(dln);
+// One sample of either direction: encode_sample (:249-277: `in` = the 16-bit sample, returns the code) or decode_code
+// (:279-303: `in` = the code, returns the sample), including update (:334-462).  Written without a data-dependent branch:
+// every lane of a warp is a different stream, so a branch taken by one lane is paid by all 32 (the first version's loop
+// executed 569 instructions per sample, most of them on partially active warps).  tab[code] = {dqln, wi << 5, fi, 0}.
+template <int BITS, bool ENC>
+__device__ __forceinline__ int g726_step(G726Core& s, int in, const int4* tab) {
     constexpr int MASK = (1 << BITS) - 1;
-    const int i = d < 0 ? MASK - q : (q == 0 ? MASK : q);
-    const int dq = g726_reconstruct((i & (1 << (BITS - 1))) != 0, tab[i], y);
-    const int sr = dq < 0 ? se - (dq & (BITS == 5 ? 0x7FFF : 0x3FFF)) : se + dq;
-    g726_update<BITS == 5>(c, y, tab[32 + i], tab[64 + i], dq, sr, sr + sez - se);
-    return i & MASK;
+    // predictor_zero (:305) / predictor_pole (:313): the 8 products are independent of each other
+    int sezi = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) sezi += g726_fmult(s.b[i] >> 2, s.dq[i]);
+    const int pole = g726_fmult(s.a1 >> 2, s.sr[1]) + g726_fmult(s.a0 >> 2, s.sr[0]);
+    const int sez = sezi >> 1, se = (sezi + pole) >> 1;
+    // step_size (:317-332); the rounding term 0x3F applies to negative differences only and dif == 0 adds nothing
+    const int yq = s.yl >> 6, dif = s.yu - yq;
+    const int ymix = yq + ((dif * (s.ap >> 2) + ((dif >> 31) & 0x3F)) >> 6);
+    const int y = s.ap >= 256 ? s.yu : ymix;
+    int code = in;
+    if (ENC) {  // quantize (:499-515)
+        const int d = (in >> 2) - se;
+        const int dqm = abs(d);
+        const int e = g726_quan2(dqm >> 1);
+        const int dln = (e << 7) + (((dqm << 7) >> e) & 0x7F) - (y >> 2);
+        const int q = g726_qcount<BITS>(dln);
+        code = d < 0 ? MASK - q : (q == 0 ? MASK : q);
+    }
+    const int4 row = tab[code];
+    // reconstruct (:517-536): dq = ±mag in sign-magnitude (sign ? mag − 0x8000 : mag)
+    const bool neg = (code & (1 << (BITS - 1))) != 0;
+    const int dql = row.x + (y >> 2);
+    const int mag = dql < 0 ? 0 : (int)g726_shr((uint32_t)(128 + (dql & 127)) << 7, 14 - ((dql >> 7) & 15));
+    const int sr = neg ? se - (mag & (BITS == 5 ? 0x7FFF : 0x3FFF)) : se + mag;
+    const int dqsez = sr - se + sez;
+    // update (:334-462)
+    const int pk0 = dqsez < 0 ? 1 : 0;
+    const int ylint = s.yl >> 15, ylfrac = (s.yl >> 10) & 0x1F;
+    const int thr2 = ylint > 9 ? (31 << 10) : ((32 + ylfrac) << ylint);
+    const bool tr = s.td != 0 && mag > ((thr2 + (thr2 >> 1)) >> 1);
+    const int yu = max(544, min(5120, y + ((row.y - y) >> 5)));
+    s.yl += yu + ((-s.yl) >> 6);
+    s.yu = yu;
+    // pole coefficients: both saturating selects of the reference are clamps (fa1 >> 5 into [-256, 255]; a2p ± 0x80 into ±12288)
+    const bool nz = dqsez != 0;
+    const int pks1 = pk0 ^ s.pk0;
+    int a2p = s.a1 - (s.a1 >> 7);
+    {
+        const int fa1 = pks1 ? s.a0 : -s.a0;
+        const int t = a2p + max(-256, min(255, fa1 >> 5)) + ((pk0 ^ s.pk1) ? -0x80 : 0x80);
+        a2p = nz ? max(-12288, min(12288, t)) : a2p;
+    }
+    const int a1ul = 15360 - a2p;
+    const int a0 = max(-a1ul, min(a1ul, s.a0 - (s.a0 >> 8) + (nz ? (pks1 ? -192 : 192) : 0)));
+    s.a1 = tr ? 0 : a2p;
+    s.a0 = tr ? 0 : a0;
+    // zero coefficients: ±128 by the sign agreement of dq with each delayed dq (none for a zero magnitude)
+    const int gs = mag == 0 ? 0 : (neg ? -128 : 128);
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        const int b = s.b[i] - (s.b[i] >> (BITS == 5 ? 9 : 8)) + gs * s.dq[i].sg;
+        s.b[i] = tr ? 0 : b;
+    }
+#pragma unroll
+    for (int i = 5; i >= 1; i--) s.dq[i] = s.dq[i - 1];
+    s.dq[0] = g726_tap_of(mag, neg);
+    s.sr[1] = s.sr[0];
+    s.sr_raw[1] = s.sr_raw[0];
+    {   // sr in log format (:443-452), literally: sr outside ±32767 makes a mantissa that carries into the exponent field
+        const int x = sr > 0 ? sr : -sr;
+        const int e = g726_quan2(x);
+        const int lf = (e << 6) + ((x << 6) >> e);
+        s.sr_raw[0] = sr == 0 ? 0x20 : (sr > 0 ? lf : (sr > -32768 ? lf - 0x400 : -0x3E0));
+        s.sr[0] = g726_tap(s.sr_raw[0]);
+    }
+    s.pk1 = s.pk0;
+    s.pk0 = pk0;
+    s.td = (!tr && a2p < -11776) ? 1 : 0;
+    s.dms += (row.z - s.dms) >> 5;
+    s.dml += ((row.z << 2) - s.dml) >> 7;
+    const bool fast = y < 1536 || s.td != 0 || abs((s.dms << 2) - s.dml) >= (s.dml >> 3);
+    s.ap = tr ? 256 : s.ap + (((fast ? 0x200 : 0) - s.ap) >> 4);
+    return ENC ? code : max(-32768, min(32767, sr << 2));
 }
 
 // [rate][3][32] = dqln | wi | fi in constant memory (filled from G726Tab on first use); each CTA copies its rate's rows to
-// shared memory because the hot-loop index is a per-lane code (constant memory would serialise divergent indices)
+// shared memory as one 16-byte row per code {dqln, wi << 5, fi, 0} (one LDS.128 per sample; the index is a per-lane code,
+// constant memory would serialise divergent indices)
 __constant__ int g726_c_tab[4][96];
 template <int BITS>
-__device__ __forceinline__ void g726_load_tables(int* tab) {
-    for (int i = threadIdx.x; i < 96; i += blockDim.x) tab[i] = i >= 32 && i < 64 ? g726_c_tab[BITS - 2][i] << 5 : g726_c_tab[BITS - 2][i];
+__device__ __forceinline__ void g726_load_tables(int4* tab) {
+    for (int i = threadIdx.x; i < 32; i += blockDim.x)
+        tab[i] = make_int4(g726_c_tab[BITS - 2][i], g726_c_tab[BITS - 2][32 + i] << 5, g726_c_tab[BITS - 2][64 + i], 0);
     __syncthreads();
 }
-__device__ __forceinline__ void g726_core_default(G726Core& c) {  // Default for G726Core, :214-230
-#pragma unroll
-    for (int i = 0; i < G726_NSTATE; i++) c.s[i] = 0;
-    c.s[G_YL] = 34816; c.s[G_YU] = 544;
-#pragma unroll
-    for (int i = 0; i < 6; i++) c.s[G_DQ0 + i] = 32;
-    c.s[G_SR0] = 32; c.s[G_SR1] = 32;
-}
 __device__ __forceinline__ void g726_core_load(G726Core& c, const int32_t* state, size_t stream) {
-    if (!state) { g726_core_default(c); return; }
+    int r[G726_NSTATE];
+    if (state) {
 #pragma unroll
-    for (int i = 0; i < G726_NSTATE; i++) c.s[i] = state[stream * G726_NSTATE + i];
+        for (int i = 0; i < G726_NSTATE; i++) r[i] = state[stream * G726_NSTATE + i];
+    } else {  // Default for G726Core, :214-230
+#pragma unroll
+        for (int i = 0; i < G726_NSTATE; i++) r[i] = 0;
+        r[G_YL] = 34816; r[G_YU] = 544;
+#pragma unroll
+        for (int i = 0; i < 6; i++) r[G_DQ0 + i] = 32;
+        r[G_SR0] = 32; r[G_SR1] = 32;
+    }
+    c.yl = r[G_YL]; c.yu = r[G_YU]; c.dms = r[G_DMS]; c.dml = r[G_DML]; c.ap = r[G_AP]; c.a0 = r[G_A0]; c.a1 = r[G_A1];
+    c.pk0 = r[G_PK0]; c.pk1 = r[G_PK1]; c.td = r[G_TD];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { c.b[i] = r[G_B0 + i]; c.dq[i] = g726_tap(r[G_DQ0 + i]); }
+    c.sr[0] = g726_tap(r[G_SR0]); c.sr[1] = g726_tap(r[G_SR1]);
+    c.sr_raw[0] = r[G_SR0]; c.sr_raw[1] = r[G_SR1];
 }
 __device__ __forceinline__ void g726_core_store(const G726Core& c, int32_t* state, size_t stream) {
     if (!state) return;
+    int32_t* r = state + stream * G726_NSTATE;
+    r[G_YL] = c.yl; r[G_YU] = c.yu; r[G_DMS] = c.dms; r[G_DML] = c.dml; r[G_AP] = c.ap; r[G_A0] = c.a0; r[G_A1] = c.a1;
+    r[G_PK0] = c.pk0; r[G_PK1] = c.pk1; r[G_TD] = c.td;
 #pragma unroll
-    for (int i = 0; i < G726_NSTATE; i++) state[stream * G726_NSTATE + i] = c.s[i];
+    for (int i = 0; i < 6; i++) { r[G_B0 + i] = c.b[i]; r[G_DQ0 + i] = g726_tap_raw(c.dq[i]); }
+    r[G_SR0] = c.sr_raw[0]; r[G_SR1] = c.sr_raw[1];
 }
 
 // 32 bits of the code stream starting at byte `off` (< bytes); bytes past the end read as 0.  `wordwise`: the stream
@@ -227,11 +246,35 @@ __device__ __forceinline__ uint32_t g726_fetch32(const uint8_t* p, size_t off, s
 
 constexpr int kG726Threads = 128;
 
+// A block of 32 samples is exactly BITS 32-bit words of codes.  The words are held as one multi-word integer `w` (word 0 =
+// the earliest codes; MSB-first packing byte-swaps on load so that the earliest code is the TOP of word 0): the 8 codes of a
+// sub-block are its first 8·BITS bits, then the whole integer moves on by 8·BITS bits with compile-time funnel shifts.
+template <int BITS, int PACKING, int U = 8>
+__device__ __forceinline__ void g726_words_advance(uint32_t (&w)[BITS]) {
+    constexpr int S = U * BITS, WS = S / 32, BS = S % 32;
+#pragma unroll
+    for (int i = 0; i < BITS; i++) {
+        const uint32_t a = i + WS < BITS ? w[i + WS] : 0u, b = i + WS + 1 < BITS ? w[i + WS + 1] : 0u;
+        if (BS == 0) w[i] = a;
+        else w[i] = PACKING == 0 ? __funnelshift_l(b, a, BS) : __funnelshift_r(a, b, BS);
+    }
+}
+template <int BITS, int PACKING>
+__device__ __forceinline__ int g726_code_at(uint64_t cw, int j) {  // cw: first 64 bits of the words (word 0 first)
+    return PACKING == 0 ? (int)(cw >> (64 - (j + 1) * BITS)) & ((1 << BITS) - 1) : (int)(cw >> (j * BITS)) & ((1 << BITS) - 1);
+}
+
+template <int KIND> __device__ __forceinline__ uint32_t g726_out_elem(int v) {  // G726Decoder::decode_{i16,i32,f32}, :821-951
+    if (KIND == SK_KIND_I16) return (uint32_t)v & 0xffffu;
+    if (KIND == SK_KIND_I32) return (uint32_t)v << 16;
+    return __float_as_uint(__fmul_rn((float)v, 1.0f / 32768.0f));
+}
+
 // KIND: output element (sk_kind).  One thread per stream; `bytes` per stream is a whole number of code groups.
 template <int BITS, int PACKING, int KIND>
 __global__ void __launch_bounds__(kG726Threads) g726_decode_kernel(const uint8_t* __restrict__ in, size_t in_stride, size_t n_streams, size_t bytes,
                                                                    void* __restrict__ outv, size_t out_stride, int32_t* __restrict__ state) {
-    __shared__ int tab[96];
+    __shared__ int4 tab[32];
     g726_load_tables<BITS>(tab);
     const size_t stream = (size_t)blockIdx.x * kG726Threads + threadIdx.x;
     if (stream >= n_streams) return;
@@ -240,15 +283,63 @@ __global__ void __launch_bounds__(kG726Threads) g726_decode_kernel(const uint8_t
     const uint8_t* p = in + stream * in_stride;
     const bool wordwise = ((uintptr_t)p & 3) == 0;
     const size_t n = bytes * 8 / BITS;
-    uint64_t res = 0;
-    int navail = 0;
-    size_t off = 0;
     constexpr int OB = KIND == SK_KIND_I16 ? 2 : 4;
     uint8_t* o = reinterpret_cast<uint8_t*>(outv) + stream * out_stride * OB;
     const bool vec = ((uintptr_t)o & 15) == 0;
-    constexpr int PER = 16 / OB;  // samples per 128-bit store
-    uint32_t buf[4];
-    for (size_t k = 0; k < n; k++) {
+#ifndef G726_DEC_SUB
+#define G726_DEC_SUB 8
+#endif
+    constexpr int U = G726_DEC_SUB;  // samples decoded per trip of the resident loop (straight-line code: U x ~310 instructions)
+    // whole 32-sample blocks: the next block's words are requested before the current block is decoded
+    const size_t nblk = wordwise ? n / 32 : 0;
+    const uint32_t* pw = reinterpret_cast<const uint32_t*>(p);
+    uint32_t nx[BITS];
+    if (nblk) {
+#pragma unroll
+        for (int i = 0; i < BITS; i++) nx[i] = __ldg(pw + i);
+    }
+    for (size_t blk = 0; blk < nblk; blk++) {
+        uint32_t w[BITS];
+#pragma unroll
+        for (int i = 0; i < BITS; i++) w[i] = PACKING == 0 ? bswap32(nx[i]) : nx[i];
+        if (blk + 1 < nblk) {
+#pragma unroll
+            for (int i = 0; i < BITS; i++) nx[i] = __ldg(pw + (blk + 1) * BITS + i);
+        }
+        uint8_t* ob = o + blk * 32 * OB;
+#pragma unroll 1
+        for (int sb = 0; sb < 32 / U; sb++) {
+            const uint64_t cw = PACKING == 0 ? ((uint64_t)w[0] << 32 | w[1]) : ((uint64_t)w[1] << 32 | w[0]);
+            uint32_t e[U];
+#pragma unroll
+            for (int j = 0; j < U; j++) e[j] = g726_out_elem<KIND>(g726_step<BITS, false>(c, g726_code_at<BITS, PACKING>(cw, j), tab));
+            if (OB == 2) {
+                uint32_t q[U / 2];
+#pragma unroll
+                for (int j = 0; j < U / 2; j++) q[j] = e[2 * j] | e[2 * j + 1] << 16;
+                if (vec) {
+                    if (U == 8) st_stream_v4(ob + sb * 16, make_uint4(q[0], q[1], q[U / 2 - 2], q[U / 2 - 1]));
+                    else st_stream_v2(ob + sb * 8, make_uint2(q[0], q[1]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < U; j++) reinterpret_cast<uint16_t*>(ob)[sb * U + j] = (uint16_t)(q[j >> 1] >> (16 * (j & 1)));
+                }
+            } else if (vec) {
+#pragma unroll
+                for (int j = 0; j < U; j += 4) st_stream_v4(ob + sb * U * 4 + j * 4, make_uint4(e[j], e[j + 1], e[j + 2], e[j + 3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < U; j++) reinterpret_cast<uint32_t*>(ob)[sb * U + j] = e[j];
+            }
+            g726_words_advance<BITS, PACKING, U>(w);
+        }
+    }
+    // the rest (fewer than 32 samples, or a stream that does not start on a word): a 64-bit bit reservoir, one sample at a time
+    uint64_t res = 0;
+    int navail = 0;
+    size_t off = nblk * 4 * BITS;
+#pragma unroll 1
+    for (size_t k = nblk * 32; k < n; k++) {
         if (navail < BITS) {
             const uint32_t w = g726_fetch32(p, off, bytes, wordwise);
             off += 4;
@@ -260,34 +351,22 @@ __global__ void __launch_bounds__(kG726Threads) g726_decode_kernel(const uint8_t
         if (PACKING == 0) { code = (int)(res >> (64 - BITS)); res <<= BITS; }
         else { code = (int)(res & ((1u << BITS) - 1)); res >>= BITS; }
         navail -= BITS;
-        const int v = g726_decode_code<BITS>(c, code, tab);
-        // G726Decoder::decode_{i16,i32,f32}, :821-951
-        uint32_t e;
-        if (KIND == SK_KIND_I16) e = (uint32_t)v & 0xffffu;
-        else if (KIND == SK_KIND_I32) e = (uint32_t)v << 16;
-        else e = __float_as_uint(__fmul_rn((float)v, 1.0f / 32768.0f));
-        const int slot = (int)(k % PER);
-        if (OB == 2) { if (slot & 1) buf[slot >> 1] |= e << 16; else buf[slot >> 1] = e; }
-        else buf[slot] = e;
-        if (slot == PER - 1 || k + 1 == n) {
-            const size_t first = k - slot;
-            if (vec && slot == PER - 1) st_stream_v4(o + first * OB, make_uint4(buf[0], buf[1], buf[2], buf[3]));
-            else {
-                for (int j = 0; j <= slot; j++) {
-                    if (OB == 2) reinterpret_cast<uint16_t*>(o)[first + j] = (uint16_t)(buf[j >> 1] >> (16 * (j & 1)));
-                    else reinterpret_cast<uint32_t*>(o)[first + j] = buf[j];
-                }
-            }
-        }
+        const uint32_t e = g726_out_elem<KIND>(g726_step<BITS, false>(c, code, tab));
+        if (OB == 2) reinterpret_cast<uint16_t*>(o)[k] = (uint16_t)e;
+        else reinterpret_cast<uint32_t*>(o)[k] = e;
     }
     g726_core_store(c, state, stream);
 }
 
-// KIND: input element, i16 or i32 ((s >> 16) as i16, :735-738).  `n` samples per stream, a whole number of groups.
+template <int KIND> __device__ __forceinline__ int g726_in_sample(const uint8_t* p, size_t k) {  // i32: (s >> 16) as i16, :735-738
+    return KIND == SK_KIND_I16 ? (int)__ldg(reinterpret_cast<const int16_t*>(p) + k) : (int)(int16_t)(__ldg(reinterpret_cast<const int32_t*>(p) + k) >> 16);
+}
+
+// KIND: input element, i16 or i32.  `n` samples per stream, a whole number of groups.
 template <int BITS, int PACKING, int KIND>
 __global__ void __launch_bounds__(kG726Threads) g726_encode_kernel(const void* __restrict__ inv, size_t in_stride, size_t n_streams, size_t n,
                                                                    uint8_t* __restrict__ out, size_t out_stride, int32_t* __restrict__ state) {
-    __shared__ int tab[96];
+    __shared__ int4 tab[32];
     g726_load_tables<BITS>(tab);
     const size_t stream = (size_t)blockIdx.x * kG726Threads + threadIdx.x;
     if (stream >= n_streams) return;
@@ -297,14 +376,66 @@ __global__ void __launch_bounds__(kG726Threads) g726_encode_kernel(const void* _
     const uint8_t* p = reinterpret_cast<const uint8_t*>(inv) + stream * in_stride * IB;
     uint8_t* o = out + stream * out_stride;
     const bool wordwise = ((uintptr_t)o & 3) == 0;
+    const bool vec = ((uintptr_t)p & 15) == 0;
     const size_t bytes = n * BITS / 8;
+    // whole 32-sample blocks = BITS output words, built as one multi-word integer (see g726_words_advance): each sub-block's
+    // 8 codes enter at the far end and the integer moves on, so after four sub-blocks the first codes sit in word 0
+    const size_t nblk = wordwise ? n / 32 : 0;
+    constexpr int NV = IB * 8 / 16;  // 128-bit loads per sub-block
+    uint4 nx[NV];
+    auto fetch = [&](size_t k) {
+        if (vec) {
+#pragma unroll
+            for (int i = 0; i < NV; i++) nx[i] = ld_stream_v4(p + k * IB + i * 16);
+        } else {
+            uint32_t q[NV * 4];
+#pragma unroll
+            for (int j = 0; j < NV * 4; j++) {
+                if (IB == 2) q[j] = (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(p) + k + 2 * j) | (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(p) + k + 2 * j + 1) << 16;
+                else q[j] = __ldg(reinterpret_cast<const uint32_t*>(p) + k + j);
+            }
+#pragma unroll
+            for (int i = 0; i < NV; i++) nx[i] = make_uint4(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]);
+        }
+    };
+    if (nblk) fetch(0);
+    for (size_t blk = 0; blk < nblk; blk++) {
+        uint32_t w[BITS];
+#pragma unroll
+        for (int i = 0; i < BITS; i++) w[i] = 0;
+#pragma unroll 1
+        for (int sb = 0; sb < 4; sb++) {
+            uint32_t q[NV * 4];
+#pragma unroll
+            for (int i = 0; i < NV; i++) { q[4 * i] = nx[i].x; q[4 * i + 1] = nx[i].y; q[4 * i + 2] = nx[i].z; q[4 * i + 3] = nx[i].w; }
+            const size_t knext = blk * 32 + (sb + 1) * 8;
+            if (knext + 8 <= nblk * 32) fetch(knext);
+            uint64_t cw = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int sample = IB == 2 ? (int)(int16_t)(q[j >> 1] >> (16 * (j & 1))) : (int)(int16_t)((int32_t)q[j] >> 16);
+                const uint64_t code = (uint64_t)g726_step<BITS, true>(c, sample, tab);
+                cw |= PACKING == 0 ? code << (8 * BITS - (j + 1) * BITS) : code << (j * BITS);
+            }
+            g726_words_advance<BITS, PACKING>(w);
+            constexpr int S = 8 * BITS, T = 32 * BITS - S;  // the sub-block occupies bits [T, T + S) counted from the first code
+            if (PACKING == 0) {  // MSB first: the last S bits of the integer = the low end of the last words
+                w[BITS - 1] |= (uint32_t)cw;
+                if (S > 32) w[BITS - 2] |= (uint32_t)(cw >> 32);
+            } else {
+                w[T / 32] |= (uint32_t)(cw << (T % 32));
+                if constexpr (T % 32 + S > 32) w[T / 32 + 1] |= (uint32_t)(cw >> (32 - T % 32));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < BITS; i++) reinterpret_cast<uint32_t*>(o)[blk * BITS + i] = PACKING == 0 ? bswap32(w[i]) : w[i];
+    }
     uint64_t res = 0;
     int nbits = 0;
-    size_t off = 0;
-    for (size_t k = 0; k < n; k++) {
-        const int sample = KIND == SK_KIND_I16 ? (int)__ldg(reinterpret_cast<const int16_t*>(p) + k)
-                                               : (int)(int16_t)(__ldg(reinterpret_cast<const int32_t*>(p) + k) >> 16);
-        const uint64_t code = (uint64_t)g726_encode_sample<BITS>(c, sample, tab);
+    size_t off = nblk * 4 * BITS;
+#pragma unroll 1
+    for (size_t k = nblk * 32; k < n; k++) {
+        const uint64_t code = (uint64_t)g726_step<BITS, true>(c, g726_in_sample<KIND>(p, k), tab);
         if (PACKING == 0) res |= code << (64 - BITS - nbits); else res |= code << nbits;
         nbits += BITS;
         while (nbits >= 32 || (k + 1 == n && nbits > 0)) {  // whole words; at the end of the stream also the partial one

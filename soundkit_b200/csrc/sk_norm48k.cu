@@ -186,18 +186,38 @@ __device__ __forceinline__ void n48_frame_raw(const uint8_t* p, bool fb4, float&
 }
 template <int W> __device__ __forceinline__ float n48_scale() { return W == 2 ? 1.0f / 32768.0f : (W == 3 ? 1.0f / 8388608.0f : 4.656612873077393e-10f); }
 
-constexpr int kN48MaxVec = 4;  // 128-bit vectors of one staged run a thread may hold in registers (prefetch of the next stream)
+constexpr int kN48MaxStages = 4;         // staged runs in flight per CTA (ring of shared-memory buffers)
+constexpr int kN48MaxBufBytes = 48 << 10;  // largest run the tiled kernel stages (two stages of it still leave 2 CTAs per SM)
+
+__device__ __forceinline__ uint32_t n48_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void n48_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void n48_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void n48_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void n48_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tN48_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra N48_DONE;\n\tbra N48_WAIT;\n\tN48_DONE:\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
 
 // Outputs of a tile are dealt to threads round-robin (thread t owns outputs t, t + 256, t + 512, t + 768 of the tile):
 // consecutive lanes read consecutive source frames (conflict-free shared-memory reads) and write consecutive floats
-// (one 128-byte line per warp store).  The staged run is double buffered: the global loads of the NEXT stream are in
-// flight while the current stream is interpolated, and there is one barrier per stream.
+// (one 128-byte line per warp store).  The staged runs form a ring of `stages` buffers filled by TMA bulk copies
+// (cp.async.bulk -> mbarrier, issued by one thread `stages - 1` streams ahead): no register staging, no shared-memory
+// stores, and the global latency of a run is covered by the interpolation of the streams before it (history: a one-deep
+// register prefetch left 39 % of the stall samples on long_scoreboard and 20 % on the barrier: 0.79 of the HBM rate).
 template <int W, bool BE, bool FLT, bool ST, bool FB4>  // FB4: a frame is exactly one aligned 32-bit word (16-bit stereo)
 __global__ void __launch_bounds__(kN48Threads)
 norm48k_tile_kernel(const __grid_constant__ N48Src src, unsigned long long o_start, unsigned long long n_lerp, unsigned long long n_total,
                     unsigned rate, float prev_l, float prev_r, float* __restrict__ out_l, float* __restrict__ out_r, long long out_stride,
-                    unsigned n_streams, float* __restrict__ final_lr, int buf_bytes) {
+                    unsigned n_streams, float* __restrict__ final_lr, int buf_bytes, int stages) {
     extern __shared__ __align__(16) uint8_t n48_raw[];
+    __shared__ __align__(8) unsigned long long n48_bars[kN48MaxStages];
     const unsigned long long t0 = (unsigned long long)blockIdx.x * kN48Tile;   // first output of the tile
     const bool writes_final = final_lr != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     const bool passthrough = rate == 48000u;
@@ -239,35 +259,33 @@ norm48k_tile_kernel(const __grid_constant__ N48Src src, unsigned long long o_sta
     const int run = f_hi >= f_lo ? (int)((f_hi + 1) * fb - a_off) : 0;
     const long long safe = (long long)src.frames * fb - a_off;  // never read past the caller's buffer
     const int nvec = (int)min((long long)((run + 15) >> 4), safe >> 4);
-    uint4 pre[kN48MaxVec];
-    auto prefetch = [&](unsigned s) {
-        const uint4* a0 = reinterpret_cast<const uint4*>(src.base + (long long)s * src.stream_stride + a_off);
-#pragma unroll
-        for (int j = 0; j < kN48MaxVec; j++) {
-            const int v = threadIdx.x + j * kN48Threads;
-            if (v < nvec) pre[j] = ld_stream_v4_nv(a0 + v);
-        }
+    const uint32_t run_bytes = (uint32_t)nvec * 16u;
+    const unsigned n_it = blockIdx.y < n_streams ? (n_streams - blockIdx.y + gridDim.y - 1) / gridDim.y : 0;
+    auto issue = [&](unsigned it, int stage) {  // one thread: request the run of the CTA's it-th stream into ring slot `stage`
+        const unsigned s = blockIdx.y + it * gridDim.y;
+        const uint32_t bar = n48_smem_u32(&n48_bars[stage]);
+        n48_mbar_expect_tx(bar, run_bytes);
+        if (run_bytes) n48_bulk_load(n48_smem_u32(n48_raw + (size_t)stage * buf_bytes), src.base + (long long)s * src.stream_stride + a_off, run_bytes, bar);
     };
-    auto commit = [&](unsigned s, uint8_t* buf) {  // registers -> shared memory, plus the bytes after the last whole vector
-#pragma unroll
-        for (int j = 0; j < kN48MaxVec; j++) {
-            const int v = threadIdx.x + j * kN48Threads;
-            if (v < nvec) reinterpret_cast<uint4*>(buf)[v] = pre[j];
-        }
-        if (nvec * 16 < run) {
-            const uint8_t* a0 = src.base + (long long)s * src.stream_stride + a_off;
-            for (int b = nvec * 16 + threadIdx.x; b < run; b += kN48Threads) buf[b] = a0[b];
-        }
-    };
-
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < stages; i++) n48_mbar_init(n48_smem_u32(&n48_bars[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < stages - 1 && (unsigned)i < n_it; i++) issue((unsigned)i, i);
+    }
+    int cur = 0, nxt = stages - 1;  // ring slot of this iteration / of the request made in it
+    uint32_t phase = 0;
     unsigned s = blockIdx.y;
-    if (s < n_streams) prefetch(s);
-    int cur = 0;
-    for (; s < n_streams; s += gridDim.y, cur ^= 1) {
-        uint8_t* buf = n48_raw + cur * buf_bytes;
-        commit(s, buf);
-        __syncthreads();  // buf complete; the other buffer (read two streams ago) is free for the next commit
-        if (s + gridDim.y < n_streams) prefetch(s + gridDim.y);
+    for (unsigned it = 0; it < n_it; it++, s += gridDim.y) {
+        uint8_t* buf = n48_raw + (size_t)cur * buf_bytes;
+        if ((int)run_bytes < run) {  // the bytes after the last whole vector the caller's buffer holds (last tile of a stream only)
+            const uint8_t* a0 = src.base + (long long)s * src.stream_stride + a_off;
+            for (int b = (int)run_bytes + threadIdx.x; b < run; b += kN48Threads) buf[b] = a0[b];
+        }
+        __syncthreads();  // mbarriers initialised (first trip); every thread is done with the previous stream: its slot may be refilled
+        if (threadIdx.x == 0 && it + (unsigned)(stages - 1) < n_it) issue(it + (unsigned)(stages - 1), nxt);
+        n48_mbar_wait(n48_smem_u32(&n48_bars[cur]), phase);
+        if (++cur == stages) { cur = 0; phase ^= 1u; }
+        if (++nxt == stages) nxt = 0;
         const uint8_t* sm = buf + skew;  // frame f_lo
         float* pl = out_l + (long long)s * out_stride + t0 + threadIdx.x;
         float* pr = out_r + (long long)s * out_stride + t0 + threadIdx.x;
