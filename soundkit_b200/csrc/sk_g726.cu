@@ -287,9 +287,11 @@ __global__ void __launch_bounds__(kG726Threads) g726_decode_kernel(const uint8_t
     uint8_t* o = reinterpret_cast<uint8_t*>(outv) + stream * out_stride * OB;
     const bool vec = ((uintptr_t)o & 15) == 0;
 #ifndef G726_DEC_SUB
-#define G726_DEC_SUB 8
+#define G726_DEC_SUB 4
 #endif
-    constexpr int U = G726_DEC_SUB;  // samples decoded per trip of the resident loop (straight-line code: U x ~310 instructions)
+    // samples decoded per trip of the resident loop.  4, not 8: the 8-sample body (2 500 instructions, 40 KB) ran with 19 % of its stall
+    // samples on no_instructions (instruction-cache misses); the 4-sample body decodes 69.5 instead of 59.5 G samples/s
+    constexpr int U = G726_DEC_SUB;
     // whole 32-sample blocks: the next block's words are requested before the current block is decoded
     const size_t nblk = wordwise ? n / 32 : 0;
     const uint32_t* pw = reinterpret_cast<const uint32_t*>(p);
@@ -379,23 +381,32 @@ __global__ void __launch_bounds__(kG726Threads) g726_encode_kernel(const void* _
     const bool vec = ((uintptr_t)p & 15) == 0;
     const size_t bytes = n * BITS / 8;
     // whole 32-sample blocks = BITS output words, built as one multi-word integer (see g726_words_advance): each sub-block's
-    // 8 codes enter at the far end and the integer moves on, so after four sub-blocks the first codes sit in word 0
+    // codes enter at the far end and the integer moves on, so after four sub-blocks the first codes sit in word 0
     const size_t nblk = wordwise ? n / 32 : 0;
-    constexpr int NV = IB * 8 / 16;  // 128-bit loads per sub-block
-    uint4 nx[NV];
+#ifndef G726_ENC_SUB
+#define G726_ENC_SUB 4
+#endif
+    constexpr int U = G726_ENC_SUB;      // samples encoded per trip of the resident loop
+    constexpr int NW = U * IB / 4;       // input words per sub-block
+    uint32_t nx[NW];
     auto fetch = [&](size_t k) {
         if (vec) {
+            if constexpr (NW % 4 == 0) {
 #pragma unroll
-            for (int i = 0; i < NV; i++) nx[i] = ld_stream_v4(p + k * IB + i * 16);
-        } else {
-            uint32_t q[NV * 4];
-#pragma unroll
-            for (int j = 0; j < NV * 4; j++) {
-                if (IB == 2) q[j] = (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(p) + k + 2 * j) | (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(p) + k + 2 * j + 1) << 16;
-                else q[j] = __ldg(reinterpret_cast<const uint32_t*>(p) + k + j);
+                for (int i = 0; i < NW / 4; i++) {
+                    const uint4 v = ld_stream_v4(p + k * IB + i * 16);
+                    nx[4 * i] = v.x; nx[4 * i + 1] = v.y; nx[4 * i + 2] = v.z; nx[4 * i + 3] = v.w;
+                }
+            } else {
+                const uint2 v = ld_stream_v2(p + k * IB);
+                nx[0] = v.x; nx[1] = v.y;
             }
+        } else {
 #pragma unroll
-            for (int i = 0; i < NV; i++) nx[i] = make_uint4(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]);
+            for (int j = 0; j < NW; j++) {
+                if (IB == 2) nx[j] = (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(p) + k + 2 * j) | (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(p) + k + 2 * j + 1) << 16;
+                else nx[j] = __ldg(reinterpret_cast<const uint32_t*>(p) + k + j);
+            }
         }
     };
     if (nblk) fetch(0);
@@ -404,24 +415,24 @@ __global__ void __launch_bounds__(kG726Threads) g726_encode_kernel(const void* _
 #pragma unroll
         for (int i = 0; i < BITS; i++) w[i] = 0;
 #pragma unroll 1
-        for (int sb = 0; sb < 4; sb++) {
-            uint32_t q[NV * 4];
+        for (int sb = 0; sb < 32 / U; sb++) {
+            uint32_t q[NW];
 #pragma unroll
-            for (int i = 0; i < NV; i++) { q[4 * i] = nx[i].x; q[4 * i + 1] = nx[i].y; q[4 * i + 2] = nx[i].z; q[4 * i + 3] = nx[i].w; }
-            const size_t knext = blk * 32 + (sb + 1) * 8;
-            if (knext + 8 <= nblk * 32) fetch(knext);
+            for (int i = 0; i < NW; i++) q[i] = nx[i];
+            const size_t knext = blk * 32 + (sb + 1) * U;
+            if (knext + U <= nblk * 32) fetch(knext);
             uint64_t cw = 0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
+            for (int j = 0; j < U; j++) {
                 const int sample = IB == 2 ? (int)(int16_t)(q[j >> 1] >> (16 * (j & 1))) : (int)(int16_t)((int32_t)q[j] >> 16);
                 const uint64_t code = (uint64_t)g726_step<BITS, true>(c, sample, tab);
-                cw |= PACKING == 0 ? code << (8 * BITS - (j + 1) * BITS) : code << (j * BITS);
+                cw |= PACKING == 0 ? code << (U * BITS - (j + 1) * BITS) : code << (j * BITS);
             }
-            g726_words_advance<BITS, PACKING>(w);
-            constexpr int S = 8 * BITS, T = 32 * BITS - S;  // the sub-block occupies bits [T, T + S) counted from the first code
+            g726_words_advance<BITS, PACKING, U>(w);
+            constexpr int S = U * BITS, T = 32 * BITS - S;  // the sub-block occupies bits [T, T + S) counted from the first code
             if (PACKING == 0) {  // MSB first: the last S bits of the integer = the low end of the last words
                 w[BITS - 1] |= (uint32_t)cw;
-                if (S > 32) w[BITS - 2] |= (uint32_t)(cw >> 32);
+                if constexpr (S > 32) w[BITS - 2] |= (uint32_t)(cw >> 32);
             } else {
                 w[T / 32] |= (uint32_t)(cw << (T % 32));
                 if constexpr (T % 32 + S > 32) w[T / 32 + 1] |= (uint32_t)(cw >> (32 - T % 32));

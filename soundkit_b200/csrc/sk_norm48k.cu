@@ -186,7 +186,7 @@ __device__ __forceinline__ void n48_frame_raw(const uint8_t* p, bool fb4, float&
 }
 template <int W> __device__ __forceinline__ float n48_scale() { return W == 2 ? 1.0f / 32768.0f : (W == 3 ? 1.0f / 8388608.0f : 4.656612873077393e-10f); }
 
-constexpr int kN48MaxStages = 4;         // staged runs in flight per CTA (ring of shared-memory buffers)
+constexpr int kN48MaxStages = 8;         // staged runs in flight per CTA (ring of shared-memory buffers)
 constexpr int kN48MaxBufBytes = 48 << 10;  // largest run the tiled kernel stages (two stages of it still leave 2 CTAs per SM)
 
 __device__ __forceinline__ uint32_t n48_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -379,7 +379,7 @@ static int n48_launch(sk_ctx* ctx, const N48Src& src, unsigned long long o_start
     // source bytes one tile of outputs can touch (+ alignment slack); the staged kernel needs them in shared memory
     const unsigned long long span_frames = ((unsigned long long)kN48Tile * rate + 47999) / 48000 + 3;
     const unsigned long long span_bytes = span_frames * (unsigned long long)(src.width * src.channels) + 48;
-    const bool tiled = span_bytes + 32 <= (unsigned long long)kN48MaxVec * kN48Threads * 16 &&
+    const bool tiled = span_bytes + 32 <= (unsigned long long)kN48MaxBufBytes &&
                        (((uintptr_t)src.base | (uintptr_t)src.stream_stride) & 15) == 0;
     const unsigned long long groups = (n_total + 3) / 4;
     unsigned long long gx = (groups + kN48Threads - 1) / kN48Threads;
@@ -393,12 +393,14 @@ static int n48_launch(sk_ctx* ctx, const N48Src& src, unsigned long long o_start
     if (tiled) {
         const dim3 grid((unsigned)gx, gy);
         const int buf_bytes = (int)sk_round_up((size_t)span_bytes + 32, 16);
-        const size_t smem = 2 * (size_t)buf_bytes;
+        // ring depth: as many runs in flight as ~28 KB of shared memory per CTA hold (8 CTAs per SM), between 2 and kN48MaxStages
+        const int stages = (int)std::min<size_t>(kN48MaxStages, std::max<size_t>(2, (28u << 10) / (size_t)buf_bytes));
+        const size_t smem = (size_t)stages * (size_t)buf_bytes;
 #define N48_LAUNCH(W_, BE_, FLT_, ST_, FB4_)                                                                                                        \
         do {                                                                                                                                  \
             SK_CUDA(ctx, cudaFuncSetAttribute(norm48k_tile_kernel<W_, BE_, FLT_, ST_, FB4_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
             norm48k_tile_kernel<W_, BE_, FLT_, ST_, FB4_><<<grid, kN48Threads, smem, ctx->stream>>>(src, o_start, n_lerp, n_total, rate, prev_l, prev_r, \
-                                                                                              out_l, out_r, out_stride, (unsigned)n_streams, final_lr, buf_bytes); \
+                                                                                              out_l, out_r, out_stride, (unsigned)n_streams, final_lr, buf_bytes, stages); \
         } while (0)
 #define N48_LAUNCH_ST(W_, BE_, FLT_)                                                                  \
         do {                                                                                          \
