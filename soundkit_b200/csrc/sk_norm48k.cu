@@ -114,12 +114,17 @@ norm48k_kernel(const __grid_constant__ N48Src src, unsigned long long o_start, u
     }
 }
 
-// Tiled form (the fast path): a CTA owns kN48Tile consecutive outputs of one stream at a time.  The source bytes those
+// Tiled form (the fast path): a CTA owns 256 x OPT consecutive outputs of one stream at a time.  The source bytes those
 // outputs touch are one contiguous run, copied into shared memory with coalesced 128-bit loads (the gathers of the
 // direct kernel above become shared-memory reads).  Positions AND the byte offsets of the frames they select are
 // computed once per thread and reused for every stream of the CTA's grid.y slice, and the sample format is a template
 // parameter, so the per-stream work of an output is 4 shared-memory loads, 4 conversions and the lerp.
-constexpr int kN48Tile = kN48Threads * 4;
+// Outputs per thread and stream: one barrier, one mbarrier wait and one round of pointer arithmetic per OPT outputs.  Measured on
+// s16 stereo 44.1 kHz (B200): 4 -> 0.86, 8 -> 0.93, 16 -> 0.96 of the HBM copy rate.  16 whenever a tile's run fits the per-CTA
+// shared-memory budget, 4 for the widest formats / highest rates.
+constexpr int kN48OptWide = 16, kN48OptNarrow = 4;
+constexpr int kN48RingBytes = 48 << 10;   // shared memory a CTA aims to spend on its ring of staged runs: 3 runs in flight for s16 stereo.  Deeper is
+                                          // slower (measured: 6 stages 0.90, 3 stages 0.96 of the HBM rate; 8 vs 4 stages at 4 outputs per thread 0.86 vs 0.88)
 
 // W sample bytes at shared-memory address p (2- / 4-byte aligned for W = 2 / 4, any alignment for W = 3)
 template <int W>
@@ -169,8 +174,10 @@ __device__ __forceinline__ void n48_frame_raw(const uint8_t* p, bool fb4, float&
         if (ST && fb4) u = *reinterpret_cast<const uint32_t*>(p);
         else u = *reinterpret_cast<const uint16_t*>(p) | (ST ? (uint32_t)*reinterpret_cast<const uint16_t*>(p + 2) << 16 : 0u);
         if (BE) u = __byte_perm(u, 0, 0x2301);
-        l = (float)(int16_t)(u & 0xffffu);
-        r = ST ? (float)(int16_t)(u >> 16) : l;
+        // s16 -> float without I2F.S16 (a conversion-unit instruction that shares the memory-instruction queue with the LDS / STG
+        // of this loop: 17 % of the stall samples): s ^ 0x8000 = s + 32768 as the mantissa of 2^23, minus (2^23 + 32768), exact
+        l = __fsub_rn(__uint_as_float((u & 0xffffu) ^ 0x4B008000u), 8421376.0f);
+        r = ST ? __fsub_rn(__uint_as_float((u >> 16) ^ 0x4B008000u), 8421376.0f) : l;
     } else if (W == 3) {
         const uint32_t a = n48_lds<3>(p);
         l = (float)(((int32_t)(BE ? __byte_perm(a, 0, 0x0124) : __byte_perm(a, 0, 0x2104))) >> 8);
@@ -186,7 +193,7 @@ __device__ __forceinline__ void n48_frame_raw(const uint8_t* p, bool fb4, float&
 }
 template <int W> __device__ __forceinline__ float n48_scale() { return W == 2 ? 1.0f / 32768.0f : (W == 3 ? 1.0f / 8388608.0f : 4.656612873077393e-10f); }
 
-constexpr int kN48MaxStages = 8;         // staged runs in flight per CTA (ring of shared-memory buffers)
+constexpr int kN48MaxStages = 4;         // staged runs in flight per CTA (ring of shared-memory buffers)
 constexpr int kN48MaxBufBytes = 48 << 10;  // largest run the tiled kernel stages (two stages of it still leave 2 CTAs per SM)
 
 __device__ __forceinline__ uint32_t n48_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -205,18 +212,19 @@ __device__ __forceinline__ void n48_mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
 }
 
-// Outputs of a tile are dealt to threads round-robin (thread t owns outputs t, t + 256, t + 512, t + 768 of the tile):
+// Outputs of a tile are dealt to threads round-robin (thread t owns outputs t, t + 256, t + 512, ... of the tile):
 // consecutive lanes read consecutive source frames (conflict-free shared-memory reads) and write consecutive floats
 // (one 128-byte line per warp store).  The staged runs form a ring of `stages` buffers filled by TMA bulk copies
 // (cp.async.bulk -> mbarrier, issued by one thread `stages - 1` streams ahead): no register staging, no shared-memory
 // stores, and the global latency of a run is covered by the interpolation of the streams before it (history: a one-deep
 // register prefetch left 39 % of the stall samples on long_scoreboard and 20 % on the barrier: 0.79 of the HBM rate).
-template <int W, bool BE, bool FLT, bool ST, bool FB4>  // FB4: a frame is exactly one aligned 32-bit word (16-bit stereo)
+template <int W, bool BE, bool FLT, bool ST, bool FB4, int OPT>  // FB4: a frame is exactly one aligned 32-bit word (16-bit stereo)
 __global__ void __launch_bounds__(kN48Threads)
 norm48k_tile_kernel(const __grid_constant__ N48Src src, unsigned long long o_start, unsigned long long n_lerp, unsigned long long n_total,
                     unsigned rate, float prev_l, float prev_r, float* __restrict__ out_l, float* __restrict__ out_r, long long out_stride,
                     unsigned n_streams, float* __restrict__ final_lr, int buf_bytes, int stages) {
     extern __shared__ __align__(16) uint8_t n48_raw[];
+    constexpr int kN48Tile = kN48Threads * OPT, kN48Opt = OPT;
     __shared__ __align__(8) unsigned long long n48_bars[kN48MaxStages];
     const unsigned long long t0 = (unsigned long long)blockIdx.x * kN48Tile;   // first output of the tile
     const bool writes_final = final_lr != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
@@ -239,17 +247,17 @@ norm48k_tile_kernel(const __grid_constant__ N48Src src, unsigned long long o_sta
     // the common tile: every output interpolated from frames inside this buffer -> no per-output special cases
     const bool plain = t0 + kN48Tile <= n_lerp && first_lower >= 0 && !writes_final && t0 + kN48Tile <= n_total;
     const int fb = src.channels * src.width;
-    int off[4];   // byte offset of the output's lower frame from frame f_lo; -1: the carried previous frame; -2: tail output
-    float fr[4];
+    int off[kN48Opt];   // byte offset of the output's lower frame from frame f_lo; -1: the carried previous frame; -2: tail output
+    float fr[kN48Opt];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < kN48Opt; k++) {
         const unsigned long long i = t0 + (unsigned)(k * kN48Threads) + threadIdx.x;
         const long long f = lower_of(o_start + i, &fr[k]);
         off[k] = (i >= n_lerp) ? -2 : (f < 0 ? -1 : (int)(f - f_lo) * fb);
     }
     bool need_last = writes_final;
 #pragma unroll
-    for (int k = 0; k < 4; k++) need_last |= off[k] == -2 && t0 + (unsigned)(k * kN48Threads) + threadIdx.x < n_total;
+    for (int k = 0; k < kN48Opt; k++) need_last |= off[k] == -2 && t0 + (unsigned)(k * kN48Threads) + threadIdx.x < n_total;
 
     // ---- staging: the run [f_lo, f_hi] of a stream as 16-byte vectors around it.  Base and stride are 16-byte aligned on
     // this path, so the run's offset inside a stream, its length and its skew are the same for every stream.
@@ -292,7 +300,7 @@ norm48k_tile_kernel(const __grid_constant__ N48Src src, unsigned long long o_sta
         if (plain && !FLT) {
             constexpr bool fb4 = FB4;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < kN48Opt; k++) {
                 float ll, rl, lu, ru;
                 n48_frame_raw<W, BE, ST>(sm + off[k], fb4, ll, rl);
                 if (passthrough) { pl[k * kN48Threads] = __fmul_rn(ll, n48_scale<W>()); pr[k * kN48Threads] = __fmul_rn(rl, n48_scale<W>()); continue; }
@@ -302,7 +310,7 @@ norm48k_tile_kernel(const __grid_constant__ N48Src src, unsigned long long o_sta
             }
         } else if (plain) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < kN48Opt; k++) {
                 float ll, rl, lu, ru;
                 n48_frame<W, BE, FLT, ST>(sm + off[k], ll, rl);
                 if (passthrough) { pl[k * kN48Threads] = ll; pr[k * kN48Threads] = rl; continue; }
@@ -316,7 +324,7 @@ norm48k_tile_kernel(const __grid_constant__ N48Src src, unsigned long long o_sta
             if (need_last && src.frames) { last_l = n48_sample(sbase, src, src.frames - 1, 0); last_r = n48_sample(sbase, src, src.frames - 1, src.channels > 1 ? 1 : 0); }
             if (writes_final) { final_lr[2 * s] = last_l; final_lr[2 * s + 1] = last_r; }
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < kN48Opt; k++) {
                 const unsigned long long i = t0 + (unsigned)(k * kN48Threads) + threadIdx.x;
                 if (i >= n_total) continue;
                 float o_l, o_r;
@@ -377,8 +385,12 @@ static int n48_launch(sk_ctx* ctx, const N48Src& src, unsigned long long o_start
                       unsigned rate, float prev_l, float prev_r, float* out_l, float* out_r, long long out_stride, size_t n_streams,
                       float* final_lr) {
     // source bytes one tile of outputs can touch (+ alignment slack); the staged kernel needs them in shared memory
-    const unsigned long long span_frames = ((unsigned long long)kN48Tile * rate + 47999) / 48000 + 3;
-    const unsigned long long span_bytes = span_frames * (unsigned long long)(src.width * src.channels) + 48;
+    auto span_bytes_of = [&](int opt) {
+        const unsigned long long span_frames = ((unsigned long long)kN48Threads * opt * rate + 47999) / 48000 + 3;
+        return span_frames * (unsigned long long)(src.width * src.channels) + 48;
+    };
+    const int opt = span_bytes_of(kN48OptWide) + 32 <= (unsigned long long)kN48MaxBufBytes ? kN48OptWide : kN48OptNarrow;
+    const unsigned long long span_bytes = span_bytes_of(opt);
     const bool tiled = span_bytes + 32 <= (unsigned long long)kN48MaxBufBytes &&
                        (((uintptr_t)src.base | (uintptr_t)src.stream_stride) & 15) == 0;
     const unsigned long long groups = (n_total + 3) / 4;
@@ -391,16 +403,25 @@ static int n48_launch(sk_ctx* ctx, const N48Src& src, unsigned long long o_start
     if (gx < want) gy = (unsigned)std::min<unsigned long long>(n_streams, (want + gx - 1) / gx);
     if (gy > 65535u) gy = 65535u;
     if (tiled) {
+        const unsigned long long tile = (unsigned long long)kN48Threads * opt;
+        gx = std::max<unsigned long long>(1, (n_total + tile - 1) / tile);
+        gy = 1;
+        if (gx < want) gy = (unsigned)std::min<unsigned long long>(n_streams, (want + gx - 1) / gx);
+        if (gy > 65535u) gy = 65535u;
         const dim3 grid((unsigned)gx, gy);
         const int buf_bytes = (int)sk_round_up((size_t)span_bytes + 32, 16);
-        // ring depth: as many runs in flight as ~28 KB of shared memory per CTA hold (8 CTAs per SM), between 2 and kN48MaxStages
-        const int stages = (int)std::min<size_t>(kN48MaxStages, std::max<size_t>(2, (28u << 10) / (size_t)buf_bytes));
+        // ring depth: as many runs in flight as the ring budget holds, between 2 and kN48MaxStages
+        const int stages = (int)std::min<size_t>(kN48MaxStages, std::max<size_t>(2, (size_t)kN48RingBytes / (size_t)buf_bytes));
         const size_t smem = (size_t)stages * (size_t)buf_bytes;
+#define N48_LAUNCH_OPT(W_, BE_, FLT_, ST_, FB4_, OPT_)                                                                                             \
+        do {                                                                                                                                  \
+            SK_CUDA(ctx, cudaFuncSetAttribute(norm48k_tile_kernel<W_, BE_, FLT_, ST_, FB4_, OPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+            norm48k_tile_kernel<W_, BE_, FLT_, ST_, FB4_, OPT_><<<grid, kN48Threads, smem, ctx->stream>>>(src, o_start, n_lerp, n_total, rate, prev_l, prev_r, \
+                                                                                              out_l, out_r, out_stride, (unsigned)n_streams, final_lr, buf_bytes, stages); \
+        } while (0)
 #define N48_LAUNCH(W_, BE_, FLT_, ST_, FB4_)                                                                                                        \
         do {                                                                                                                                  \
-            SK_CUDA(ctx, cudaFuncSetAttribute(norm48k_tile_kernel<W_, BE_, FLT_, ST_, FB4_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-            norm48k_tile_kernel<W_, BE_, FLT_, ST_, FB4_><<<grid, kN48Threads, smem, ctx->stream>>>(src, o_start, n_lerp, n_total, rate, prev_l, prev_r, \
-                                                                                              out_l, out_r, out_stride, (unsigned)n_streams, final_lr, buf_bytes, stages); \
+            if (opt == kN48OptWide) N48_LAUNCH_OPT(W_, BE_, FLT_, ST_, FB4_, kN48OptWide); else N48_LAUNCH_OPT(W_, BE_, FLT_, ST_, FB4_, kN48OptNarrow); \
         } while (0)
 #define N48_LAUNCH_ST(W_, BE_, FLT_)                                                                  \
         do {                                                                                          \
@@ -415,6 +436,7 @@ static int n48_launch(sk_ctx* ctx, const N48Src& src, unsigned long long o_start
         else { if (be) N48_LAUNCH_ST(4, true, false); else N48_LAUNCH_ST(4, false, false); }
 #undef N48_LAUNCH_ST
 #undef N48_LAUNCH
+#undef N48_LAUNCH_OPT
     } else {
         norm48k_kernel<<<dim3((unsigned)gx, gy), kN48Threads, 0, ctx->stream>>>(src, o_start, n_lerp, n_total, rate, prev_l, prev_r, out_l, out_r,
                                                                                out_stride, (unsigned)n_streams, final_lr);
