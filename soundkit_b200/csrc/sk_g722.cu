@@ -36,24 +36,36 @@ __constant__ int c_g722_q6[32] = {0, 35, 72, 110, 150, 190, 233, 276, 323, 370, 
 __constant__ int c_g722_iln[32] = {0, 63, 62, 31, 30, 29, 28, 27, 26, 25, 24, 23, 22, 21, 20, 19, 18, 17, 16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 0};
 __constant__ int c_g722_ilp[32] = {0, 61, 60, 59, 58, 57, 56, 55, 54, 53, 52, 51, 50, 49, 48, 47, 46, 45, 44, 43, 42, 41, 40, 39, 38, 37, 36, 35, 34, 33, 32, 0};
 
-// small tables as literals (selected by 2-4 bit indices)
-__device__ __forceinline__ int g722_wl(int i) {  // WL[RL42[ril]] folded: index = ril (4 bits)
-    // rl42 = {0,7,6,5,4,3,2,1,7,6,5,4,3,2,1,0}; wl = {-60,-30,58,172,334,538,1198,3042}
-    constexpr int t[16] = {-60, 3042, 1198, 538, 334, 172, 58, -30, 3042, 1198, 538, 334, 172, 58, -30, -60};
-    return t[i];
+// WL[RL42[ril]] folded: index = ril (4 bits).  rl42 = {0,7,6,5,4,3,2,1,7,6,5,4,3,2,1,0}; wl = {-60,-30,58,172,334,538,1198,3042}
+__constant__ int c_g722_wl[16] = {-60, 3042, 1198, 538, 334, 172, 58, -30, 3042, 1198, 538, 334, 172, 58, -30, -60};
+
+// Every table the hot loop indexes with a per-lane value lives in SHARED memory: every lane of a warp is a different stream, so the
+// indices diverge, and the constant cache serves one address per cycle (ncu on the first version, all tables in constant memory:
+// 46 % of the decoder's stall samples on short_scoreboard).  One 16-byte row per 6-bit low-band code gathers what a step needs.
+struct G722Tab {
+    int4 low[64];  // [code]: {qm4[code >> 2], wl[code >> 2], qm6[code], 0}; the encoder reads (x, y) of row ril << 2
+    int ilb[32];
+    int q6[32];    // QUANTL decision levels (encoder)
+    int il[32];    // iln | ilp << 8 (encoder)
+};
+__device__ __forceinline__ void g722_tab_fill(G722Tab& T) {  // whole CTA; ends with a barrier
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) T.low[i] = make_int4(c_g722_qm4[i >> 2], c_g722_wl[i >> 2], c_g722_qm6[i], 0);
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) { T.ilb[i] = c_g722_ilb[i]; T.q6[i] = c_g722_q6[i]; T.il[i] = c_g722_iln[i] | (c_g722_ilp[i] << 8); }
+    __syncthreads();
 }
 __device__ __forceinline__ int g722_wh(int ihigh) {  // WH[RH2[ihigh]]: rh2 = {2,1,2,1}, wh = {0,-214,798}
     return (ihigh & 1) ? -214 : 798;
 }
-__device__ __forceinline__ int g722_qm2(int ihigh) {
-    constexpr int t[4] = {-7408, -1616, 7408, 1616};
-    return t[ihigh];
+__device__ __forceinline__ int g722_qm2(int ihigh) {  // {-7408, -1616, 7408, 1616}
+    const int mag = (ihigh & 1) ? 1616 : 7408;
+    return (ihigh & 2) ? mag : -mag;
 }
 
 // blocks 3L / 3H: SCALEL (base 8) / SCALEH (base 10)
-__device__ __forceinline__ int g722_scale(int nb, int base) {
+__device__ __forceinline__ int g722_scale(const G722Tab& T, int nb, int base) {
     const int wd1 = (nb >> 6) & 31, wd2 = base - (nb >> 11);
-    const int wd3 = wd2 < 0 ? (c_g722_ilb[wd1] << -wd2) : (c_g722_ilb[wd1] >> wd2);
+    const int v = T.ilb[wd1];
+    const int wd3 = wd2 < 0 ? (v << -wd2) : (v >> wd2);
     return wd3 << 2;
 }
 
@@ -128,18 +140,16 @@ __device__ __forceinline__ void g722_qmf(const int (&x)[24], int& sum_even_taps,
 }
 
 // one code byte -> two samples (libg722 Decoder::decode, 64 kbit/s, 16 kHz output)
-__device__ __forceinline__ void g722_decode_byte(G722State& s, int code, int& y0, int& y1) {
-    int wd1 = code & 0x3f;
+__device__ __forceinline__ void g722_decode_byte(const G722Tab& T, G722State& s, int code, int& y0, int& y1) {
+    const int4 row = T.low[code & 0x3f];
     const int ihigh = (code >> 6) & 3;
-    int wd2 = c_g722_qm6[wd1];
-    wd1 >>= 2;
-    wd2 = (s.lo.det * wd2) >> 15;                                   // 5L INVQBL
+    const int wd2 = (s.lo.det * row.z) >> 15;                       // 5L INVQBL
     int rlow = s.lo.s + wd2;                                        // 5L RECONS
     rlow = max(-16384, min(16383, rlow));                           // 6L LIMIT
-    const int dlowt = (s.lo.det * c_g722_qm4[wd1]) >> 15;           // 2L INVQAL
-    int nb = ((s.lo.nb * 127) >> 7) + g722_wl(wd1);                 // 3L LOGSCL
+    const int dlowt = (s.lo.det * row.x) >> 15;                     // 2L INVQAL
+    int nb = ((s.lo.nb * 127) >> 7) + row.y;                        // 3L LOGSCL
     s.lo.nb = max(0, min(18432, nb));
-    s.lo.det = g722_scale(s.lo.nb, 8);
+    s.lo.det = g722_scale(T, s.lo.nb, 8);
     g722_block4(s.lo, dlowt);
 
     const int dhigh = (s.hi.det * g722_qm2(ihigh)) >> 15;           // 2H INVQAH
@@ -147,7 +157,7 @@ __device__ __forceinline__ void g722_decode_byte(G722State& s, int code, int& y0
     rhigh = max(-16384, min(16383, rhigh));                         // 6H LIMIT
     nb = ((s.hi.nb * 127) >> 7) + g722_wh(ihigh);                   // 3H LOGSCH
     s.hi.nb = max(0, min(22528, nb));
-    s.hi.det = g722_scale(s.hi.nb, 10);
+    s.hi.det = g722_scale(T, s.hi.nb, 10);
     g722_block4(s.hi, dhigh);
 
 #pragma unroll
@@ -161,7 +171,7 @@ __device__ __forceinline__ void g722_decode_byte(G722State& s, int code, int& y0
 }
 
 // two samples -> one code byte (libg722 Encoder::encode)
-__device__ __forceinline__ int g722_encode_pair(G722State& s, int a0, int a1) {
+__device__ __forceinline__ int g722_encode_pair(const G722Tab& T, G722State& s, int a0, int a1) {
 #pragma unroll
     for (int i = 0; i < 22; i++) s.x[i] = s.x[i + 2];               // transmit QMF
     s.x[22] = a0;
@@ -172,15 +182,25 @@ __device__ __forceinline__ int g722_encode_pair(G722State& s, int a0, int a1) {
 
     const int el = sat16(xlow - s.lo.s);                            // 1L SUBTRA
     int wd = el >= 0 ? el : -(el + 1);                              // 1L QUANTL
-    int i = 1;
-    for (; i < 30; i++)
-        if (wd < ((c_g722_q6[i] * s.lo.det) >> 12)) break;
-    const int ilow = el < 0 ? c_g722_iln[i] : c_g722_ilp[i];
+    // the reference walks i = 1 .. 29 until wd < (q6[i] * det) >> 12.  The levels rise with i (det >= 0), so that index is 1 + the
+    // number of levels <= wd: a five-step descent over the sorted levels, no data-dependent branch (the walk made every warp pay
+    // for its slowest lane)
+    int pos = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const int k = pos + step;
+        const bool ge = wd >= ((T.q6[k & 31] * s.lo.det) >> 12);
+        pos = (k <= 29 && ge) ? k : pos;
+    }
+    const int i = pos + 1;
+    const int ilw = T.il[i];
+    const int ilow = el < 0 ? (ilw & 0xff) : (ilw >> 8);
     const int ril = ilow >> 2;                                      // 2L INVQAL
-    const int dlow = (s.lo.det * c_g722_qm4[ril]) >> 15;
-    int nb = ((s.lo.nb * 127) >> 7) + g722_wl(ril);                 // 3L LOGSCL
+    const int2 rr = *reinterpret_cast<const int2*>(&T.low[ril << 2]);
+    const int dlow = (s.lo.det * rr.x) >> 15;
+    int nb = ((s.lo.nb * 127) >> 7) + rr.y;                         // 3L LOGSCL
     s.lo.nb = max(0, min(18432, nb));
-    s.lo.det = g722_scale(s.lo.nb, 8);
+    s.lo.det = g722_scale(T, s.lo.nb, 8);
     g722_block4(s.lo, dlow);
 
     const int eh = sat16(xhigh - s.hi.s);                           // 1H SUBTRA
@@ -191,7 +211,7 @@ __device__ __forceinline__ int g722_encode_pair(G722State& s, int a0, int a1) {
     const int dhigh = (s.hi.det * g722_qm2(ihigh)) >> 15;           // 2H INVQAH
     nb = ((s.hi.nb * 127) >> 7) + g722_wh(ihigh);                   // 3H LOGSCH
     s.hi.nb = max(0, min(22528, nb));
-    s.hi.det = g722_scale(s.hi.nb, 10);
+    s.hi.det = g722_scale(T, s.hi.nb, 10);
     g722_block4(s.hi, dhigh);
     return (ihigh << 6) | ilow;
 }
@@ -200,6 +220,8 @@ __device__ __forceinline__ int g722_encode_pair(G722State& s, int a0, int a1) {
 template <int KIND>
 __global__ void __launch_bounds__(kG722Threads) g722_decode_kernel(const uint8_t* __restrict__ in, size_t in_stride, size_t n_streams, size_t bytes,
                                                                    void* __restrict__ outv, size_t out_stride, int32_t* __restrict__ state) {
+    __shared__ G722Tab T;
+    g722_tab_fill(T);
     const size_t stream = (size_t)blockIdx.x * kG722Threads + threadIdx.x;
     if (stream >= n_streams) return;
     G722State s;
@@ -224,7 +246,7 @@ __global__ void __launch_bounds__(kG722Threads) g722_decode_kernel(const uint8_t
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             int y0, y1;
-            g722_decode_byte(s, (int)((w >> (8 * k)) & 0xffu), y0, y1);
+            g722_decode_byte(T, s, (int)((w >> (8 * k)) & 0xffu), y0, y1);
             e[2 * k] = conv(y0); e[2 * k + 1] = conv(y1);
         }
         uint8_t* q = o + 2 * j * OB;
@@ -239,7 +261,7 @@ __global__ void __launch_bounds__(kG722Threads) g722_decode_kernel(const uint8_t
     }
     for (; j < bytes; j++) {
         int y0, y1;
-        g722_decode_byte(s, (int)p[j], y0, y1);
+        g722_decode_byte(T, s, (int)p[j], y0, y1);
         if (OB == 2) { uint16_t* h = reinterpret_cast<uint16_t*>(o) + 2 * j; h[0] = (uint16_t)conv(y0); h[1] = (uint16_t)conv(y1); }
         else { uint32_t* h = reinterpret_cast<uint32_t*>(o) + 2 * j; h[0] = conv(y0); h[1] = conv(y1); }
     }
@@ -250,6 +272,8 @@ __global__ void __launch_bounds__(kG722Threads) g722_decode_kernel(const uint8_t
 template <int KIND>
 __global__ void __launch_bounds__(kG722Threads) g722_encode_kernel(const void* __restrict__ inv, size_t in_stride, size_t n_streams, size_t n,
                                                                    uint8_t* __restrict__ out, size_t out_stride, int32_t* __restrict__ state) {
+    __shared__ G722Tab T;
+    g722_tab_fill(T);
     const size_t stream = (size_t)blockIdx.x * kG722Threads + threadIdx.x;
     if (stream >= n_streams) return;
     G722State s;
@@ -266,11 +290,11 @@ __global__ void __launch_bounds__(kG722Threads) g722_encode_kernel(const void* _
     for (; c + 4 <= codes; c += 4) {
         uint32_t w = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) w |= (uint32_t)g722_encode_pair(s, sample(2 * (c + k)), sample(2 * (c + k) + 1)) << (8 * k);
+        for (int k = 0; k < 4; k++) w |= (uint32_t)g722_encode_pair(T, s, sample(2 * (c + k)), sample(2 * (c + k) + 1)) << (8 * k);
         if (out_words) *reinterpret_cast<uint32_t*>(o + c) = w;
         else for (int k = 0; k < 4; k++) o[c + k] = (uint8_t)(w >> (8 * k));
     }
-    for (; c < codes; c++) o[c] = (uint8_t)g722_encode_pair(s, sample(2 * c), sample(2 * c + 1));
+    for (; c < codes; c++) o[c] = (uint8_t)g722_encode_pair(T, s, sample(2 * c), sample(2 * c + 1));
     g722_store(s, state, stream);
 }
 

@@ -400,8 +400,14 @@ def test_normalizer48k_error_states(ctx):
         n.push(np.zeros(8, np.uint8), 16, 0, False, 2, 8000)
 
 
-@pytest.mark.parametrize("bits,fmt,channels,rate", [(16, 0, 2, 44100), (24, 0, 2, 96000), (32, 1, 1, 16000), (16, 0, 2, 48000)])
-def test_normalizer48k_batch_dev_matches_oracle_per_stream(oracle, bits, fmt, channels, rate):
+@pytest.mark.parametrize("bits,fmt,channels,rate,be", [
+    (16, 0, 2, 44100, False), (24, 0, 2, 96000, False), (32, 1, 1, 16000, False), (16, 0, 2, 48000, False),
+    # every sample format through whole ("plain") tiles of the 16-outputs-per-thread form, both byte orders
+    (16, 0, 2, 44100, True), (16, 0, 1, 22050, False), (16, 0, 1, 32000, True), (24, 0, 2, 44100, False), (24, 0, 2, 32000, True),
+    (24, 0, 1, 8000, False), (32, 0, 2, 44100, False), (32, 0, 2, 24000, True), (32, 1, 2, 44100, True), (32, 1, 2, 48000, False),
+    # runs too wide for 16 outputs per thread (4-output form) and for any staged form (direct kernel)
+    (32, 1, 2, 96000, False), (32, 0, 2, 88200, True), (32, 1, 6, 96000, False)])
+def test_normalizer48k_batch_dev_matches_oracle_per_stream(oracle, bits, fmt, channels, rate, be):
     """device-resident batch of whole streams == push(whole) + finish() per stream; also the chunking-independence
     property of soundkit/src/audio_pipeline.rs:806-823 at a larger size (streams of 30 011 frames)"""
     import torch
@@ -413,17 +419,17 @@ def test_normalizer48k_batch_dev_matches_oracle_per_stream(oracle, bits, fmt, ch
     stride = (frames * fb + 15) // 16 * 16
     host = np.zeros((S, stride), np.uint8)
     for s in range(S):
-        host[s, : frames * fb] = _n48_source(bits, fmt, False, channels, frames, rng)
+        host[s, : frames * fb] = _n48_source(bits, fmt, be, channels, frames, rng)
     d_in = torch.from_numpy(host).cuda()
     n_out = c.normalize48k_out_frames(frames, rate)
     plane = (n_out + 3) // 4 * 4
     d_out = torch.full((S, 2, plane), float("nan"), dtype=torch.float32, device="cuda")
-    got_n = c.normalize48k_batch_dev(d_in, stride, S, frames, bits, fmt, False, channels, rate, d_out, 2 * plane, plane)
+    got_n = c.normalize48k_batch_dev(d_in, stride, S, frames, bits, fmt, be, channels, rate, d_out, 2 * plane, plane)
     torch.cuda.synchronize()
     assert got_n == n_out
     out = d_out.cpu().numpy()
     for s in range(S):
-        wl, wr = oracle.normalize48k([(host[s, : frames * fb], bits, fmt, False, channels, rate)])
+        wl, wr = oracle.normalize48k([(host[s, : frames * fb], bits, fmt, be, channels, rate)])
         assert len(wl) == n_out
         assert np.array_equal(out[s, 0, :n_out].view(np.uint32), wl.view(np.uint32))
         assert np.array_equal(out[s, 1, :n_out].view(np.uint32), wr.view(np.uint32))
@@ -431,7 +437,7 @@ def test_normalizer48k_batch_dev_matches_oracle_per_stream(oracle, bits, fmt, ch
     nz = c.normalizer48k()
     ls = []
     for a in range(0, frames, 4097):
-        ls.append(nz.push(host[0, a * fb:min(frames, a + 4097) * fb], bits, fmt, False, channels, rate)[0].copy())
+        ls.append(nz.push(host[0, a * fb:min(frames, a + 4097) * fb], bits, fmt, be, channels, rate)[0].copy())
     ls.append(nz.finish()[0].copy())
     assert np.array_equal(np.concatenate(ls).view(np.uint32), out[0, 0, :n_out].view(np.uint32))
     c.close()
