@@ -74,6 +74,13 @@ int sk_ensure_dev_out(sk_ctx* ctx, size_t bytes);
 int sk_ensure_stats(sk_ctx* ctx);  // device counters (zeroed on first use)
 // host -> device through the pinned stage (chunked), device -> host likewise; both synchronous wrt host
 int sk_h2d(sk_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+// Small host-pointer calls: the kernel reads and writes the context's pinned staging buffer directly over PCIe (pinned
+// allocations are device-addressable at the same address), so a call is memcpy + one launch + one synchronize + memcpy
+// instead of two DMA copies, one launch and two synchronizes.  sk_small_begin returns false when the call is too large for
+// this path (the caller then stages through device memory).
+constexpr size_t kSkSmallCallBytes = 64u << 10;
+bool sk_small_begin(sk_ctx* ctx, const void* in_host, size_t in_bytes, size_t out_bytes, void** in_dev, void** out_dev);
+int sk_small_end(sk_ctx* ctx, void* out_host, const void* out_dev, size_t out_bytes);
 int sk_d2h(sk_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 
 static inline size_t sk_round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -193,6 +193,22 @@ int sk_d2h(sk_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
     return SK_OK;
 }
 
+bool sk_small_begin(sk_ctx* ctx, const void* in_host, size_t in_bytes, size_t out_bytes, void** in_dev, void** out_dev) {
+    if (in_bytes > kSkSmallCallBytes || out_bytes > 4 * kSkSmallCallBytes) return false;
+    if (sk_ensure_host(ctx, 2 * kStagePiece) != SK_OK) return false;  // (the large path reports the allocation failure)
+    char* stage = (char*)ctx->h_stage;
+    memcpy(stage, in_host, in_bytes);
+    *in_dev = stage;
+    *out_dev = stage + kStagePiece;
+    return true;
+}
+int sk_small_end(sk_ctx* ctx, void* out_host, const void* out_dev, size_t out_bytes) {
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) SK_FAIL(ctx, SK_E_CUDA, "small call failed: %s", cudaGetErrorString(e));
+    memcpy(out_host, out_dev, out_bytes);
+    return SK_OK;
+}
+
 // ---- FFMA peak microbenchmark ----------------------------------------------------------------
 // 16 independent accumulator chains per thread, operands in registers; the measured rate is the
 // denominator of the resampler's FP32 roofline (BASELINE.md section 2 asks for it "in the same run").

@@ -254,6 +254,11 @@ extern "C" int sk_pcm_flat_convert(sk_ctx* ctx, int op, const uint8_t* in, size_
     if (!in || !out) SK_FAIL(ctx, SK_E_ARG, "null buffer");
     SK_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc;
+    void *s_in, *s_out;
+    if (sk_small_begin(ctx, in, n * I.in_b, n * I.out_b, &s_in, &s_out)) {
+        if ((rc = sk_pcm_flat_convert_dev(ctx, op, (const uint8_t*)s_in, n * I.in_b, s_out))) return rc;
+        return sk_small_end(ctx, out, s_out, n * I.out_b);
+    }
     if ((rc = sk_ensure_dev_in(ctx, n * I.in_b))) return rc;
     if ((rc = sk_ensure_dev_out(ctx, n * I.out_b))) return rc;
     if ((rc = sk_h2d(ctx, ctx->d_in, in, n * I.in_b))) return rc;
