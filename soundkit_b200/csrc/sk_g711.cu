@@ -14,6 +14,8 @@
 //           scale (see g711_enc_fast).  A 64 KiB shared-memory table of the same function measured 0.51 of the HBM rate.
 // Both directions launch a LARGE grid of short-lived CTAs (grid_for in sk_pcm.cu): persistent grid-stride forms of the
 // same loops topped out at 0.85-0.89 of the copy rate, this form runs at 1.02-1.08.
+#include <algorithm>
+
 #include "sk_common.cuh"
 
 // ---- per-sample reference arithmetic (device) ------------------------------------------------
@@ -263,6 +265,8 @@ static int grid_for(sk_ctx* ctx, size_t work_threads, int threads) {
     return (int)(need < cap ? need : cap);
 }
 
+constexpr size_t kG711SmallN = 4096;  // below this a launch is latency, not bandwidth: one scalar CTA per 256 samples
+
 extern "C" int sk_g711_decode_dev(sk_ctx* ctx, int law, const uint8_t* in, size_t n, int out_kind, void* out) {
     if (!ctx) return SK_E_ARG;
     if (law != SK_LAW_MULAW && law != SK_LAW_ALAW) SK_FAIL(ctx, SK_E_ARG, "unknown G.711 law %d", law);
@@ -270,8 +274,9 @@ extern "C" int sk_g711_decode_dev(sk_ctx* ctx, int law, const uint8_t* in, size_
     if (n == 0) return SK_OK;
     if (!in || !out) SK_FAIL(ctx, SK_E_ARG, "null buffer");
     SK_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (!aligned16(in) || !aligned16(out)) {
-        g711_decode_scalar_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(in, out, n, law, out_kind);
+    if (!aligned16(in) || !aligned16(out) || n < kG711SmallN) {  // small calls: per-sample arithmetic, no table to build
+        const unsigned sgrid = (unsigned)std::min<size_t>((size_t)ctx->num_sms * 8, (n + 255) / 256);
+        g711_decode_scalar_kernel<<<sgrid, 256, 0, ctx->stream>>>(in, out, n, law, out_kind);
         SK_LAUNCH_CHECK(ctx);
         return SK_OK;
     }
@@ -291,8 +296,9 @@ extern "C" int sk_g711_encode_dev(sk_ctx* ctx, int law, int in_kind, const void*
     if (n == 0) return SK_OK;
     if (!in || !out) SK_FAIL(ctx, SK_E_ARG, "null buffer");
     SK_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (!aligned16(in) || !aligned16(out)) {
-        g711_encode_scalar_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(in, out, n, law, in_kind);
+    if (!aligned16(in) || !aligned16(out) || n < kG711SmallN) {
+        const unsigned sgrid = (unsigned)std::min<size_t>((size_t)ctx->num_sms * 8, (n + 255) / 256);
+        g711_encode_scalar_kernel<<<sgrid, 256, 0, ctx->stream>>>(in, out, n, law, in_kind);
         SK_LAUNCH_CHECK(ctx);
         return SK_OK;
     }

@@ -1,0 +1,39 @@
+#!/usr/bin/env python3
+"""tools/kbench_int.py — times the integer-step fused chain (s24le stereo -> f32 mono, streaming semantics) for every integer
+ratio the library instantiates, device resident, CUDA events.  Development aid; bench.py stays the contract."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    from soundkit_b200 import capi
+    ctx = capi.Context(0)
+    ctx.use_torch_stream()
+    out = {}
+    for in_rate, out_rate in ((48000, 24000), (48000, 16000), (48000, 12000), (48000, 8000), (96000, 8000), (32000, 16000), (44100, 22050)):
+        S, frames = 16, in_rate * 120
+        n_out = ctx.batch_plan(in_rate, out_rate, frames, capi.SEM_STREAMING)
+        stride = (frames * 6 + 15) // 16 * 16
+        raw = torch.randint(0, 256, (S, stride), dtype=torch.uint8, device="cuda")
+        o = torch.empty((S, n_out), dtype=torch.float32, device="cuda")
+        d = capi.BatchDesc(raw.data_ptr(), stride, S, frames, 24, capi.FMT_SIGNED, 0, 2, capi.MODE_B, in_rate, out_rate, capi.SEM_STREAMING,
+                           capi.MIX_SCALE_THEN_SUM, o.data_ptr(), n_out, 0)
+        ctx.normalize_batch_dev(d); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e9
+        for _ in range(5):
+            e0.record(); ctx.normalize_batch_dev(d); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e-3)
+        out[f"{in_rate}->{out_rate}"] = {"TFLOP/s": round(1024.0 * S * n_out / best / 1e12, 2), "G frames/s": round(S * n_out / best / 1e9, 2),
+                                         "GB/s": round((S * frames * 6 + S * n_out * 4) / best / 1e9, 1), "ms": round(best * 1e3, 3)}
+        del raw, o
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
