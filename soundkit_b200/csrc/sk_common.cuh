@@ -80,6 +80,9 @@ int sk_h2d(sk_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 // this path (the caller then stages through device memory).
 constexpr size_t kSkSmallCallBytes = 64u << 10;
 bool sk_small_begin(sk_ctx* ctx, const void* in_host, size_t in_bytes, size_t out_bytes, void** in_dev, void** out_dev);
+// the two halves of the pinned staging buffer (kSkStageHalf bytes each: inputs / outputs of a zero-copy call); null on allocation failure
+constexpr size_t kSkStageHalf = 8u << 20;
+char* sk_stage_half(sk_ctx* ctx, int half);
 int sk_small_end(sk_ctx* ctx, void* out_host, const void* out_dev, size_t out_bytes);
 int sk_d2h(sk_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 

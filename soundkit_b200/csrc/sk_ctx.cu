@@ -130,7 +130,7 @@ int sk_ensure_dev_out(sk_ctx* ctx, size_t bytes) { return ensure_dev(ctx, &ctx->
 
 // Host buffers of the drop-in API are pageable (Rust Vec / slices): stage through pinned memory in
 // 8 MiB pieces so the DMA engine runs at full PCIe rate and the pinned footprint stays bounded.
-static const size_t kStagePiece = 8u << 20;
+static const size_t kStagePiece = kSkStageHalf;
 // the two slot events live in the context (created once): a small call costs no event create / destroy
 static int stage_events(sk_ctx* ctx) {
     for (int i = 0; i < 2; i++)
@@ -193,6 +193,10 @@ int sk_d2h(sk_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
     return SK_OK;
 }
 
+char* sk_stage_half(sk_ctx* ctx, int half) {
+    if (sk_ensure_host(ctx, 2 * kStagePiece) != SK_OK) return nullptr;
+    return (char*)ctx->h_stage + (half ? kStagePiece : 0);
+}
 bool sk_small_begin(sk_ctx* ctx, const void* in_host, size_t in_bytes, size_t out_bytes, void** in_dev, void** out_dev) {
     if (in_bytes > kSkSmallCallBytes || out_bytes > 4 * kSkSmallCallBytes) return false;
     if (sk_ensure_host(ctx, 2 * kStagePiece) != SK_OK) return false;  // (the large path reports the allocation failure)

@@ -976,6 +976,8 @@ extern "C" int sk_resampler_copy_table(const sk_resampler* r, float* out65536) {
     return SK_OK;
 }
 
+static int rows_copy(sk_ctx* ctx, float* dst, size_t dst_pitch, const float* src, size_t src_pitch, size_t count, size_t rows);
+
 static int resampler_run(sk_resampler* r, const float* const* in, size_t frames, float* const* out, size_t* n_out) {
     sk_ctx* ctx = r->ctx;
     SK_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -984,12 +986,28 @@ static int resampler_run(sk_resampler* r, const float* const* in, size_t frames,
     history_shift_kernel<<<r->channels, 2 * SINC_LEN, 0, ctx->stream>>>(r->d_buf, plane, r->chunk);
     SK_LAUNCH_CHECK(ctx);
     int rc;
-    for (int c = 0; c < r->channels; c++) {
-        float* dst = r->d_buf + (size_t)c * plane + 2 * SINC_LEN;
-        if (in && frames) {
-            if ((rc = sk_h2d(ctx, dst, in[c], frames * sizeof(float)))) return rc;
+    // A 4096-frame chunk is a latency-bound call: the chunk goes through the pinned staging buffer, ONE copy kernel reads it from
+    // there (zero copy) into every channel's row, the FIR writes its outputs straight back into pinned memory and the call
+    // synchronises once (history: an H2D and a D2H staging copy per channel, each with its own synchronize: 75-87 us per call).
+    char* const s_in = sk_stage_half(ctx, 0);
+    char* const s_out = sk_stage_half(ctx, 1);
+    const bool zero_copy = s_in && (size_t)r->channels * r->chunk * sizeof(float) <= kSkStageHalf &&
+                           (size_t)r->channels * r->out_plane * sizeof(float) <= kSkStageHalf;
+    if (zero_copy) {
+        for (int c = 0; c < r->channels; c++) {
+            float* row = reinterpret_cast<float*>(s_in) + (size_t)c * r->chunk;
+            if (in && frames) memcpy(row, in[c], frames * sizeof(float));
+            if (frames < r->chunk) memset(row + (in ? frames : 0), 0, (r->chunk - (in ? frames : 0)) * sizeof(float));
         }
-        if (frames < r->chunk) SK_CUDA(ctx, cudaMemsetAsync(dst + frames, 0, (r->chunk - frames) * sizeof(float), ctx->stream));
+        if ((rc = rows_copy(ctx, r->d_buf + 2 * SINC_LEN, plane, reinterpret_cast<const float*>(s_in), r->chunk, r->chunk, (size_t)r->channels))) return rc;
+    } else {
+        for (int c = 0; c < r->channels; c++) {
+            float* dst = r->d_buf + (size_t)c * plane + 2 * SINC_LEN;
+            if (in && frames) {
+                if ((rc = sk_h2d(ctx, dst, in[c], frames * sizeof(float)))) return rc;
+            }
+            if (frames < r->chunk) SK_CUDA(ctx, cudaMemsetAsync(dst + frames, 0, (r->chunk - frames) * sizeof(float), ctx->stream));
+        }
     }
     // index walk of this chunk
     WalkOut w;
@@ -1038,10 +1056,18 @@ static int resampler_run(sk_resampler* r, const float* const* in, size_t frames,
         src.width = 0; src.channels = r->channels; src.scale = 1.0f;
         src.origin = 2 * SINC_LEN; src.valid_lo = -(long long)(2 * SINC_LEN); src.valid_hi = (long long)r->chunk;
         OutDesc dst;
-        dst.base = r->d_out; dst.stream_stride = 0; dst.lane_stride = (long long)r->out_plane; dst.mix = SK_MIX_NONE; dst.n_out = (long long)n;
+        dst.base = zero_copy ? reinterpret_cast<float*>(s_out) : r->d_out;
+        dst.stream_stride = 0; dst.lane_stride = (long long)r->out_plane; dst.mix = SK_MIX_NONE; dst.n_out = (long long)n;
         if ((rc = run_plan(ctx, src, dst, &p, r->in_rate, r->out_rate, 1, r->channels))) return rc;
-        for (int c = 0; c < r->channels; c++)
-            if ((rc = sk_d2h(ctx, out[c], r->d_out + (size_t)c * r->out_plane, n * sizeof(float)))) return rc;
+        if (zero_copy) {
+            SK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            for (int c = 0; c < r->channels; c++) memcpy(out[c], reinterpret_cast<const float*>(s_out) + (size_t)c * r->out_plane, n * sizeof(float));
+        } else {
+            for (int c = 0; c < r->channels; c++)
+                if ((rc = sk_d2h(ctx, out[c], r->d_out + (size_t)c * r->out_plane, n * sizeof(float)))) return rc;
+        }
+    } else if (zero_copy) {
+        SK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the staged chunk must be consumed before the next call overwrites it
     }
     r->last_index = next_last;
     if (n_out) *n_out = n;
