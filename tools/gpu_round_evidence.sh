@@ -1,5 +1,7 @@
+# tools/gpu_round_evidence.sh [name] — on the GPU box: the driver's checks in order (pytest -m gpu -x, smoke, bench both arms) plus the ncu launch list of the
+# bench command and one ncu --set full pass over every HBM-bound / codec kernel (tools/ncu_targets.py); outputs under gpurun_out/<name>/
 set -x
-D=gpurun_out/r02f
+D=gpurun_out/${1:-evidence}
 mkdir -p $D
 (time python -m pytest tests -m gpu -x -q 2>&1 | tail -5) > $D/pytest_gpu.log 2>&1
 python -c "import __graft_entry__ as g; g.smoke()" > $D/smoke.log 2>&1
