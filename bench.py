@@ -375,6 +375,12 @@ def latency_table(ctx, np):
     ro = O.Resampler(48000, 16000, 4096, 2)
     out["resampler_chunk_4096x2ch_48k_16k"] = {"gpu_us": med_us(lambda: r.process(x), 100), "cpu_port_us": med_us(lambda: ro.process(x), 100)}
     r.close()
+    # one 20 ms block (882 frames of s16 stereo 44.1 kHz) through the streaming 48 kHz normalizer (StreamingStereo48kNormalizer::push)
+    blk = rng.integers(0, 256, 882 * 4, dtype=np.uint8)
+    gn, on = ctx.normalizer48k(), O.Normalizer48k()
+    out["normalizer48k_push_882_frames_s16_stereo_44k1"] = {"gpu_us": med_us(lambda: gn.push(blk, 16, 0, False, 2, 44100), 100),
+                                                            "cpu_port_us": med_us(lambda: on.push(blk, 16, 0, False, 2, 44100), 100)}
+    gn.close()
     # BASELINE configs[0] (C1): one 60 s s16le stereo 48 kHz stream -> f32 mono 16 kHz via downsample_audio, single thread
     frames = 2_880_000
     pcm = rng.integers(-20000, 20000, frames * 2).astype(np.int16).view(np.uint8)

@@ -521,21 +521,40 @@ extern "C" int sk_norm48k_push(sk_norm48k* n, const uint8_t* data, size_t bytes,
     SK_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc;
     const size_t plane = sk_round_up((size_t)count, 4) + 4;
-    if ((rc = sk_ensure_dev_in(ctx, bytes))) return rc;
-    if ((rc = sk_ensure_dev_out(ctx, (2 * plane + 4) * sizeof(float)))) return rc;
-    if ((rc = sk_h2d(ctx, ctx->d_in, data, bytes))) return rc;
-    N48Src src;
-    if ((rc = n48_fill_src(ctx, &src, ctx->d_in, 0, bits, fmt, big_endian, channels, start, frames))) return rc;
-    float* d_out = (float*)ctx->d_out;
-    float* d_final = d_out + 2 * plane;
     // 48 kHz sources: output index == source frame index
     const unsigned long long o_start = rate == 48000u ? start : n->output_frames;
-    if ((rc = n48_launch(ctx, src, o_start, count, count, rate, n->prev_l, n->prev_r, d_out, d_out + plane, 0, 1, d_final))) return rc;
     float fin[2];
-    if ((rc = sk_d2h(ctx, fin, d_final, sizeof(fin)))) return rc;
-    if (count) {
-        if ((rc = sk_d2h(ctx, left, d_out, (size_t)count * sizeof(float)))) return rc;
-        if ((rc = sk_d2h(ctx, right, d_out + plane, (size_t)count * sizeof(float)))) return rc;
+    char* const s_in = sk_stage_half(ctx, 0);
+    char* const s_out = sk_stage_half(ctx, 1);
+    if (s_in && bytes <= kSkStageHalf && (2 * plane + 4) * sizeof(float) <= kSkStageHalf) {
+        // a pushed block is a latency-bound call: the kernel reads the block from the pinned staging buffer and writes both planes and
+        // the carried frame straight back into it (zero copy): one launch, one synchronize instead of four
+        memcpy(s_in, data, bytes);
+        N48Src src;
+        if ((rc = n48_fill_src(ctx, &src, s_in, 0, bits, fmt, big_endian, channels, start, frames))) return rc;
+        float* d_out = reinterpret_cast<float*>(s_out);
+        float* d_final = d_out + 2 * plane;
+        if ((rc = n48_launch(ctx, src, o_start, count, count, rate, n->prev_l, n->prev_r, d_out, d_out + plane, 0, 1, d_final))) return rc;
+        SK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        memcpy(fin, d_final, sizeof(fin));
+        if (count) {
+            memcpy(left, d_out, (size_t)count * sizeof(float));
+            memcpy(right, d_out + plane, (size_t)count * sizeof(float));
+        }
+    } else {
+        if ((rc = sk_ensure_dev_in(ctx, bytes))) return rc;
+        if ((rc = sk_ensure_dev_out(ctx, (2 * plane + 4) * sizeof(float)))) return rc;
+        if ((rc = sk_h2d(ctx, ctx->d_in, data, bytes))) return rc;
+        N48Src src;
+        if ((rc = n48_fill_src(ctx, &src, ctx->d_in, 0, bits, fmt, big_endian, channels, start, frames))) return rc;
+        float* d_out = (float*)ctx->d_out;
+        float* d_final = d_out + 2 * plane;
+        if ((rc = n48_launch(ctx, src, o_start, count, count, rate, n->prev_l, n->prev_r, d_out, d_out + plane, 0, 1, d_final))) return rc;
+        if ((rc = sk_d2h(ctx, fin, d_final, sizeof(fin)))) return rc;
+        if (count) {
+            if ((rc = sk_d2h(ctx, left, d_out, (size_t)count * sizeof(float)))) return rc;
+            if ((rc = sk_d2h(ctx, right, d_out + plane, (size_t)count * sizeof(float)))) return rc;
+        }
     }
     n->output_frames += count;
     n->source_frames = end;

@@ -520,6 +520,53 @@ def test_g726_encode_decode_match_oracle(ctx, oracle, suffix, bits, packing):
     assert np.array_equal(ctx.g726_encode(bits, packing, ctx.g726_state(), x32), oracle.G726(bits, packing).encode((x32 >> 16).astype(np.int16)))
 
 
+@pytest.mark.parametrize("suffix,bits", G726_RATES)
+@pytest.mark.parametrize("packing", [0, 1])
+def test_g726_batch_dev_every_layout_takes_the_same_values(oracle, suffix, bits, packing):
+    """the batch kernels have three code paths per stream — whole 32-sample blocks of code words, the per-sample tail, and the
+    all-tail form of a stream that does not start on a word / vector boundary — and three output kinds: every combination of
+    stream stride (aligned, +1, +2 bytes), output stride (aligned, odd) and a length that is not a multiple of 32 samples must
+    give the oracle's values, in both directions"""
+    import torch
+    c = capi.Context(0)
+    c.use_torch_stream()
+    gs, gb = capi.G726_GROUP[bits]
+    S = 37
+    groups = (32 * 5 + 3 * gs) // gs + 1   # a few whole blocks plus a tail that is not a block
+    nbytes, n = groups * gb, groups * gs
+    for in_pad, out_pad in ((0, 0), (1, 1), (2, 3), (0, 1), (3, 0)):
+        stride = (nbytes + 15) // 16 * 16 + in_pad
+        codes = RNG.integers(0, 256, (S, stride), dtype=np.uint8)
+        d_codes = torch.from_numpy(codes).cuda()
+        ostride = (n + 7) // 8 * 8 + out_pad
+        want = [oracle.G726(bits, packing).decode(codes[s, :nbytes]) for s in range(S)]
+        for kind, dt in ((capi.KIND_I16, torch.int16), (capi.KIND_I32, torch.int32), (capi.KIND_F32, torch.float32)):
+            d_out = torch.zeros((S, ostride), dtype=dt, device="cuda")
+            c.g726_decode_batch_dev(bits, packing, d_codes, stride, S, nbytes, kind, d_out, ostride)
+            torch.cuda.synchronize()
+            out = d_out.cpu().numpy()
+            for s in range(S):
+                ref = want[s]
+                if kind == capi.KIND_I32:
+                    ref = ref.astype(np.int32) << 16
+                elif kind == capi.KIND_F32:
+                    ref = ref.astype(np.float32) / np.float32(32768.0)
+                assert np.array_equal(out[s, :n].view(np.uint8), ref.view(np.uint8)), (in_pad, out_pad, kind, s)
+                assert not out[s, n:].any()  # nothing written past the stream's samples
+        # encode: i16 and i32 samples at the same odd strides
+        x = RNG.integers(-32768, 32768, (S, ostride)).astype(np.int16)
+        for kind in (capi.KIND_I16, capi.KIND_I32):
+            d_x = torch.from_numpy(x if kind == capi.KIND_I16 else (x.astype(np.int32) << 16) | 0x1234).cuda()
+            d_enc = torch.zeros((S, stride), dtype=torch.uint8, device="cuda")
+            c.g726_encode_batch_dev(bits, packing, kind, d_x, ostride, S, n, d_enc, stride)
+            torch.cuda.synchronize()
+            enc = d_enc.cpu().numpy()
+            for s in range(S):
+                assert np.array_equal(enc[s, :nbytes], oracle.G726(bits, packing).encode(x[s, :n])), (in_pad, out_pad, kind, s)
+                assert not enc[s, nbytes:].any()
+    c.close()
+
+
 def test_g726_argument_errors(ctx):
     st = ctx.g726_state()
     with pytest.raises(capi.SoundkitError, match="whole number of 3-byte code groups"):
