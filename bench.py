@@ -342,6 +342,14 @@ def extras(ctx, torch, peaks, only=None):
             n_per = 4096.0 * out_rate / in_rate
             P = 1 if in_rate % out_rate == 0 else 2
             res[f"stream_batch_{in_rate}_to_{out_rate}_{S}x{ch}ch_chunk4096"] = flop_entry((512.0 * P + 3) * S * ch * n_per * chunks, t, S * ch * n_per * chunks)
+            if hasattr(rb, "process_in_place_dev"):
+                # the same pushes with the producer writing in place (sk_resampler_batch_input_dev): no append copy.  The rows keep
+                # whatever the last copying push left there; the FIR's cost does not depend on the data
+                def run_in_place():
+                    for _ in range(chunks):
+                        rb.process_in_place_dev(4096, o)
+                t = timed(run_in_place, reps=3)
+                res[f"stream_batch_{in_rate}_to_{out_rate}_{S}x{ch}ch_chunk4096_in_place"] = flop_entry((512.0 * P + 3) * S * ch * n_per * chunks, t, S * ch * n_per * chunks)
             rb.close()
             del x, o
     if want("latency"):

@@ -234,6 +234,11 @@ double sk_resampler_batch_last_index(const sk_resampler_batch*);
  * whole 4096-frame chunk that is pending; *n_out = frames produced per channel (0 while less than a chunk is pending) */
 int    sk_resampler_batch_process_dev(sk_resampler_batch*, const float* in, size_t in_stream_stride, size_t in_ch_stride,
                                       size_t frames, float* out, size_t out_stream_stride, size_t out_ch_stride, size_t* n_out);
+/* Zero-copy form of the append inside process (`accum.extend_from_slice`, :1985-1992): *in = where the next push's frames of lane
+ * (stream 0, channel 0) go inside the handle's device rows, *lane_pitch = floats between consecutive (stream, channel) lanes.  A
+ * device-side producer writes up to max_push_frames frames per lane there and then calls sk_resampler_batch_process_dev with
+ * in == NULL (strides ignored).  Valid until the next process / flush call on this handle. */
+int    sk_resampler_batch_input_dev(sk_resampler_batch*, float** in, size_t* lane_pitch);
 /* StreamingResampler::flush (:2017-2059): zero-pad the remainder to one chunk, drop the padding's share of the output
  * (round(padded * out / in) frames); with nothing pending: one chunk of zeros, untrimmed */
 int    sk_resampler_batch_flush_dev(sk_resampler_batch*, float* out, size_t out_stream_stride, size_t out_ch_stride, size_t* n_out);

@@ -121,6 +121,7 @@ extern "C" {
     pub fn sk_resampler_batch_last_index(b: *const sk_resampler_batch) -> c_double;
     pub fn sk_resampler_batch_process_dev(b: *mut sk_resampler_batch, input: *const c_float, in_stream_stride: usize, in_ch_stride: usize, frames: usize,
                                           out: *mut c_float, out_stream_stride: usize, out_ch_stride: usize, n_out: *mut usize) -> c_int;
+    pub fn sk_resampler_batch_input_dev(b: *mut sk_resampler_batch, input: *mut *mut c_float, lane_pitch: *mut usize) -> c_int;
     pub fn sk_resampler_batch_flush_dev(b: *mut sk_resampler_batch, out: *mut c_float, out_stream_stride: usize, out_ch_stride: usize,
                                         n_out: *mut usize) -> c_int;
 

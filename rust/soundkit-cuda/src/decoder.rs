@@ -201,6 +201,13 @@ impl StreamingResamplerBatch {
             .map_err(|e| format!("Resample failed: {e}")))?;
         Ok(n)
     }
+    /// Where a device-side producer writes the next push (zero-copy append): device address of lane (stream 0, channel 0) and the
+    /// pitch in floats between (stream, channel) lanes; follow it with `process_dev(std::ptr::null(), 0, 0, frames, ..)`.
+    pub fn input_dev(&mut self) -> Result<(*mut f32, usize), String> {
+        let (mut p, mut pitch) = (std::ptr::null_mut(), 0usize);
+        with_ctx(|ctx| check(ctx, unsafe { sys::sk_resampler_batch_input_dev(self.handle, &mut p, &mut pitch) }))?;
+        Ok((p, pitch))
+    }
     /// # Safety
     /// as `process_dev`
     pub unsafe fn flush_dev(&mut self, output: *mut f32, out_stream_stride: usize, out_ch_stride: usize) -> Result<usize, String> {

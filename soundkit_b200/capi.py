@@ -42,7 +42,7 @@ EXPORTS = (
     "sk_resampler_create", "sk_resampler_destroy", "sk_resampler_out_max", "sk_resampler_last_index",
     "sk_resampler_process", "sk_resampler_process_partial", "sk_resampler_copy_table",
     "sk_resampler_batch_create", "sk_resampler_batch_destroy", "sk_resampler_batch_out_cap", "sk_resampler_batch_pending",
-    "sk_resampler_batch_last_index", "sk_resampler_batch_process_dev", "sk_resampler_batch_flush_dev",
+    "sk_resampler_batch_last_index", "sk_resampler_batch_process_dev", "sk_resampler_batch_input_dev", "sk_resampler_batch_flush_dev",
     "sk_normalize_batch_plan", "sk_normalize_batch_dev", "sk_normalize_batch_pcm_dev", "sk_normalize_batch", "sk_normalize_stream",
     "sk_norm48k_create", "sk_norm48k_destroy", "sk_norm48k_push", "sk_norm48k_finish", "sk_norm48k_source_frames",
     "sk_norm48k_output_frames", "sk_norm48k_source_sample_rate", "sk_norm48k_source_channels", "sk_norm48k_max_output",
@@ -135,6 +135,7 @@ def load():
         "sk_resampler_batch_last_index": (C.c_double, [vp]),
         "sk_resampler_batch_process_dev": (i, [vp, vp, sz, sz, sz, vp, sz, sz, psz]),
         "sk_resampler_batch_flush_dev": (i, [vp, vp, sz, sz, psz]),
+        "sk_resampler_batch_input_dev": (i, [vp, C.POINTER(vp), psz]),
         "sk_normalize_batch_plan": (i, [vp, u32, u32, sz, i, psz]),
         "sk_normalize_batch_dev": (i, [vp, C.POINTER(BatchDesc)]),
         "sk_normalize_batch": (i, [vp, C.POINTER(BatchDesc)]),
@@ -562,6 +563,20 @@ class ResamplerBatch:
         n = C.c_size_t(0)
         self.ctx._ck(self.ctx.L.sk_resampler_batch_process_dev(self.h, C.c_void_p(x.data_ptr()), x.stride(0), x.stride(1), x.shape[2],
                                                               C.c_void_p(out.data_ptr()), out.stride(0), out.stride(1), C.byref(n)))
+        return n.value
+
+    def input_dev(self):
+        """(device address, lane pitch in floats) of where the next push's frames go inside the handle's rows (zero-copy append)"""
+        ptr, pitch = C.c_void_p(), C.c_size_t(0)
+        self.ctx._ck(self.ctx.L.sk_resampler_batch_input_dev(self.h, C.byref(ptr), C.byref(pitch)))
+        return ptr.value, pitch.value
+
+    def process_in_place_dev(self, frames, out):
+        """the frames were written at input_dev(): StreamingResampler::process without the append copy"""
+        assert out.stride(2) == 1 and out.shape[2] >= self.out_max
+        n = C.c_size_t(0)
+        self.ctx._ck(self.ctx.L.sk_resampler_batch_process_dev(self.h, None, 0, 0, frames, C.c_void_p(out.data_ptr()), out.stride(0), out.stride(1),
+                                                              C.byref(n)))
         return n.value
 
     def flush_dev(self, out):

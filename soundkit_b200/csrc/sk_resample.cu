@@ -1292,11 +1292,13 @@ extern "C" int sk_resampler_batch_process_dev(sk_resampler_batch* b, const float
     if (n_out) *n_out = 0;
     if (frames > b->max_push) SK_FAIL(ctx, SK_E_ARG, "push of %zu frames exceeds max_push_frames %zu", frames, b->max_push);
     if (!frames) return SK_OK;
-    if (!in || !out) SK_FAIL(ctx, SK_E_ARG, "null buffer");
+    if (!out) SK_FAIL(ctx, SK_E_ARG, "null buffer");
     SK_CUDA(ctx, cudaSetDevice(ctx->device));
-    // append behind the pending frames: one 2-D copy per channel plane set
+    // append behind the pending frames: one 2-D copy per channel plane set (in == NULL: the producer has written the frames in
+    // place, see sk_resampler_batch_input_dev)
     float* row0 = b->d_rows[b->cur] + b->pad + 2 * SINC_LEN + b->pending;
-    if (in_ch_stride * (size_t)b->channels == in_stream_stride || b->channels == 1 || b->n_streams == 1) {
+    if (!in) {
+    } else if (in_ch_stride * (size_t)b->channels == in_stream_stride || b->channels == 1 || b->n_streams == 1) {
         // lanes are equally spaced in the source: a single 2-D copy
         const size_t lane_pitch = b->channels == 1 ? in_stream_stride : in_ch_stride;
         if (int rc = rows_copy(ctx, row0, b->row, in, lane_pitch, frames, b->n_streams * (size_t)b->channels)) return rc;
@@ -1311,6 +1313,16 @@ extern "C" int sk_resampler_batch_process_dev(sk_resampler_batch* b, const float
     int rc = batch_run_chunks(b, chunks, chunks * STREAM_CHUNK, out, out_stream_stride, out_ch_stride, 0, n_out);
     if (rc) return rc;
     return batch_carry(b, chunks * STREAM_CHUNK, total);
+}
+
+// Where the next push's frames go inside the handle's row buffer: lane (stream s, channel c) starts at *in + (s * channels + c) *
+// *lane_pitch floats.  A device-side producer that writes there and then calls process_dev with in == NULL saves the append copy
+// (a quarter of the time of a 4096-frame push).  Valid until the next process / flush call on this handle.
+extern "C" int sk_resampler_batch_input_dev(sk_resampler_batch* b, float** in, size_t* lane_pitch) {
+    if (!b || !in || !lane_pitch) return SK_E_ARG;
+    *in = b->d_rows[b->cur] + b->pad + 2 * SINC_LEN + b->pending;
+    *lane_pitch = b->row;
+    return SK_OK;
 }
 
 // StreamingResampler::flush (soundkit-decoder/src/lib.rs:2017-2059): a pending remainder is zero padded to one chunk and the

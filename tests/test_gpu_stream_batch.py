@@ -70,6 +70,49 @@ def test_batch_streaming_matches_oracle_push_by_push(oracle, rates, n_streams, c
         c.close()
 
 
+class _DevRows:
+    """lanes x frames f32 view of device memory at a raw address (torch reads __cuda_array_interface__)"""
+
+    def __init__(self, ptr, lanes, frames, pitch_floats):
+        self.__cuda_array_interface__ = {"shape": (lanes, frames), "typestr": "<f4", "data": (ptr, False), "version": 2, "strides": (pitch_floats * 4, 4)}
+
+
+@pytest.mark.parametrize("rates", [(48000, 16000), (44100, 48000), (48000, 24000)])
+def test_batch_streaming_in_place_append_equals_the_copy_form(rates):
+    """sk_resampler_batch_input_dev: a device-side producer writes each push straight into the handle's rows and calls process with
+    in == NULL; every push must produce exactly what the copying form produces (which the test above pins to the oracle)"""
+    import torch
+    i, o = rates
+    n_streams, channels = 9, 2
+    rng = np.random.default_rng(i + o)
+    total = sum(PUSHES)
+    x = torch.from_numpy(rng.uniform(-0.5, 0.5, (n_streams, channels, total)).astype(np.float32)).cuda()
+    c = capi.Context(0)
+    c.use_torch_stream()
+    try:
+        ra, rb = c.resampler_batch(i, o, channels, n_streams, max_push=8192), c.resampler_batch(i, o, channels, n_streams, max_push=8192)
+        oa = torch.zeros((n_streams, channels, ra.out_max), dtype=torch.float32, device="cuda")
+        ob = torch.zeros_like(oa)
+        pos = 0
+        for k, n in enumerate(PUSHES):
+            na = ra.process_dev(x[:, :, pos:pos + n], oa)
+            ptr, pitch = rb.input_dev()
+            rows = torch.as_tensor(_DevRows(ptr, n_streams * channels, n, pitch), device="cuda")
+            rows.copy_(x[:, :, pos:pos + n].reshape(n_streams * channels, n))
+            nb = rb.process_in_place_dev(n, ob)
+            torch.cuda.synchronize()
+            assert na == nb, k
+            assert torch.equal(oa[:, :, :na].view(torch.int32), ob[:, :, :nb].view(torch.int32)), k
+            pos += n
+        assert ra.pending == rb.pending
+        na, nb = ra.flush_dev(oa), rb.flush_dev(ob)
+        torch.cuda.synchronize()
+        assert na == nb and torch.equal(oa[:, :, :na].view(torch.int32), ob[:, :, :nb].view(torch.int32))
+        ra.close(); rb.close()
+    finally:
+        c.close()
+
+
 def test_batch_streaming_argument_errors():
     c = capi.Context(0)
     try:
