@@ -441,8 +441,17 @@ template <int STEP> __host__ __device__ constexpr int tma_lead() { return STEP %
 template <int STEP> __host__ __device__ constexpr int tma_frames() { return ((tma_lead<STEP>() + int_window<STEP>() + 7) / 8) * 8; }
 template <int STEP> __host__ __device__ constexpr int tma_lane_stride() { return ((tma_frames<STEP>() + 8 + 31) / 32) * 32 + IntCfg<STEP>::SKEW; }
 template <int STEP, int SRCW> __host__ __device__ constexpr int tma_raw_bytes() { return tma_frames<STEP>() * 2 * SRCW; }
+// Raw-byte buffers of the TMA staging.  Step 3 (the headline shape: 2 CTAs per SM by registers) requests tile k + 2 while tile k
+// is convolved, into a second buffer.  The other steps are limited by shared memory instead (their windows are STEP / 3 times
+// longer per output): ONE buffer, refilled for tile k + 1 as soon as tile k has been converted — the request still has the whole
+// FIR of tile k to arrive — brings a third CTA per SM back.  SK_INT_NRAW overrides for A/B builds.
+#ifdef SK_INT_NRAW
+template <int STEP> __host__ __device__ constexpr int tma_raw_buffers() { return SK_INT_NRAW; }
+#else
+template <int STEP> __host__ __device__ constexpr int tma_raw_buffers() { return STEP == 3 ? 2 : 1; }
+#endif
 template <int STEP, int SRCW> __host__ __device__ constexpr int tma_smem_bytes() {
-    return 2 * tma_lane_stride<STEP>() * (int)sizeof(float) + 2 * tma_raw_bytes<STEP, SRCW>() + 64;
+    return 2 * tma_lane_stride<STEP>() * (int)sizeof(float) + tma_raw_buffers<STEP>() * tma_raw_bytes<STEP, SRCW>() + 64;
 }
 
 // 4 interleaved stereo frames (FB words in memory order) -> 4 L and 4 R f32 samples.  Everything about
@@ -548,13 +557,14 @@ resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant
     constexpr int WS = tma_lane_stride<STEP>();
     constexpr int FB = 2 * SRCW;  // bytes per stereo frame
     constexpr int RAWB = tma_raw_bytes<STEP, SRCW>();
+    constexpr int NB = tma_raw_buffers<STEP>();  // raw buffers == tiles requested ahead
     // the word one past the tile's window is only read (against a zero coefficient) when the last output's offset is odd; the
     // converted region must then reach it
     static_assert(((LEAD + STEP * (R - 1)) & 1) == 0 || WF > LEAD + int_window<STEP>(), "stage one more frame for this STEP / R");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     float* win = reinterpret_cast<float*>(smem_raw);
     uint8_t* raw = smem_raw + 2 * WS * sizeof(float);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(raw + 2 * RAWB);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(raw + NB * RAWB);
     __shared__ TileGeom geoms[4];
 
     // Tiles are handed out by ticket (one atomic per tile), not by a static stride: the three co-resident CTAs of an SM do not
@@ -586,7 +596,7 @@ resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant
         g.g_lo = (int)((b_lo - wa * FB + 4 * FB - 1) / (4 * FB));  // groups of 4 frames fully inside the copied bytes
         g.g_hi = (int)((b_hi - wa * FB) / (4 * FB));
         geoms[k & 3] = g;
-        const int buf = (int)(k & 1);
+        const int buf = (int)(k % NB);
         const uint32_t bar = smem_u32(&bars[buf]);
         const uint32_t bytes = (uint32_t)(b_hi - b_lo);
         mbar_expect_tx(bar, bytes);
@@ -598,7 +608,7 @@ resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant
         mbar_init(smem_u32(&bars[1]), 1);
         mbar_fence_init();
         issue(0);
-        issue(1);
+        if (NB == 2) issue(1);
     }
     __syncthreads();
 
@@ -606,8 +616,8 @@ resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant
     for (unsigned k = 0;; k++) {
         const TileGeom g = geoms[k & 3];
         if (g.stream < 0) break;  // tickets are monotonic: nothing was requested for this or any later k
-        const int buf = (int)(k & 1);
-        mbar_wait(smem_u32(&bars[buf]), (k >> 1) & 1);
+        const int buf = (int)(k % NB);
+        mbar_wait(smem_u32(&bars[buf]), (k / NB) & 1);
 
         const uint8_t* rb = raw + buf * RAWB;
         bool big;
@@ -621,7 +631,7 @@ resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant
                                  : convert_window<SRCW, WF, WS, false, false, false>(rb, win, src, g.stream, g.wa, g.g_lo, g.g_hi);
         }
         const int any_big = __syncthreads_or((int)big);  // windows ready, raw[buf] free
-        if (threadIdx.x == 0) issue(k + 2);
+        if (threadIdx.x == 0) issue(k + NB);
 
         // ---- FIR
         const float* w = win + lane * WS + STEP * R * b;

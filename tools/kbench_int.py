@@ -15,7 +15,10 @@ def main():
     ctx = capi.Context(0)
     ctx.use_torch_stream()
     out = {}
+    only = os.environ.get("KB_ONLY")  # e.g. "48000-8000": one ratio (ncu target)
     for in_rate, out_rate in ((48000, 24000), (48000, 16000), (48000, 12000), (48000, 8000), (96000, 8000), (32000, 16000), (44100, 22050)):
+        if only and only != f"{in_rate}-{out_rate}":
+            continue
         S, frames = 16, in_rate * 120
         n_out = ctx.batch_plan(in_rate, out_rate, frames, capi.SEM_STREAMING)
         stride = (frames * 6 + 15) // 16 * 16
