@@ -389,6 +389,11 @@ def latency_table(ctx, np):
     out["normalizer48k_push_882_frames_s16_stereo_44k1"] = {"gpu_us": med_us(lambda: gn.push(blk, 16, 0, False, 2, 44100), 100),
                                                             "cpu_port_us": med_us(lambda: on.push(blk, 16, 0, False, 2, 44100), 100)}
     gn.close()
+    # a 1 s utterance (s16le stereo 48 kHz -> f32 mono 16 kHz) through the same call: the short-clip regime of downsample_audio
+    clip = rng.integers(-20000, 20000, 48000 * 2).astype(np.int16).view(np.uint8)
+    out["downsample_audio_1s_s16_stereo"] = {
+        "gpu_us": med_us(lambda: ctx.normalize_stream(clip, 16, 0, False, 2, capi.MODE_A, 48000, 16000, capi.SEM_ONESHOT, capi.MIX_SUM_THEN_SCALE), 100),
+        "cpu_port_us": med_us(lambda: O.mixdown_to_mono_f32(O.downsample_audio(clip, 16, 0, 2, 48000, 16000, threads=1)), 20)}
     # BASELINE configs[0] (C1): one 60 s s16le stereo 48 kHz stream -> f32 mono 16 kHz via downsample_audio, single thread
     frames = 2_880_000
     pcm = rng.integers(-20000, 20000, frames * 2).astype(np.int16).view(np.uint8)

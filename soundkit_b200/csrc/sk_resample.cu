@@ -745,6 +745,22 @@ extern "C" int sk_normalize_stream(sk_ctx* ctx, const uint8_t* in, size_t bytes,
     const size_t plane = sk_round_up(n, 4);
     // device staging: input bytes in d_in; output planes in a private allocation (d_out may be used as mix scratch)
     const size_t in_bytes = frames * B * channels;
+    // short clips (an utterance, a decoder's AudioData block) are latency-bound calls: the chain reads the clip from the pinned staging
+    // buffer and writes its result planes straight back into it (zero copy): one synchronize, no staging DMA
+    char* const s_in = sk_stage_half(ctx, 0);
+    char* const s_out = sk_stage_half(ctx, 1);
+    if (s_in && in_bytes <= ((size_t)1 << 20) && plane * planes * sizeof(float) <= kSkStageHalf) {
+        memcpy(s_in, in, in_bytes);
+        sk_batch_desc d;
+        memset(&d, 0, sizeof(d));
+        d.in = s_in; d.in_stride = in_bytes; d.n_streams = 1; d.frames = frames; d.bits = bits; d.fmt = fmt; d.big_endian = big_endian;
+        d.channels = channels; d.scale_mode = scale_mode; d.in_rate = in_rate; d.out_rate = out_rate; d.semantics = semantics; d.mix_mode = mix;
+        d.out = reinterpret_cast<float*>(s_out); d.out_stride = plane * planes; d.out_stride_ch = plane;
+        if ((rc = sk_normalize_batch_dev(ctx, &d))) return rc;
+        SK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int c = 0; c < planes; c++) memcpy(out + (size_t)c * out_cap_per_plane, reinterpret_cast<const float*>(s_out) + (size_t)c * plane, n * sizeof(float));
+        return SK_OK;
+    }
     if ((rc = sk_ensure_dev_in(ctx, in_bytes + 16))) return rc;
     if ((rc = sk_h2d(ctx, ctx->d_in, in, in_bytes))) return rc;
     // result planes in the context's grow-only d_res (d_out may serve as the mix scratch of the unfused arms): this is the
