@@ -191,6 +191,24 @@ __device__ __forceinline__ void n48_frame_raw(const uint8_t* p, bool fb4, float&
         else r = l;
     }
 }
+// Two consecutive packed s24 stereo frames (the lower and upper frame of one output: 12 bytes at any alignment) as four UNSCALED
+// sample values: 4 aligned word loads, 3 funnel shifts and 3 byte permutes, instead of a pair of loads and a funnel shift per
+// sample (s24 stereo ran at 0.70 of the HBM rate against 0.93-0.98 for the 16- and 32-bit formats: the loop is bound by its
+// shared-memory instructions).  The staged run has 16 spare bytes behind it.
+template <bool BE>
+__device__ __forceinline__ void n48_s24_stereo_pair(const uint8_t* p, float& ll, float& rl, float& lu, float& ru) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>((uintptr_t)p & ~(uintptr_t)3);
+    const int sh = 8 * (int)((uintptr_t)p & 3);
+    const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3];
+    const uint32_t u0 = __funnelshift_r(w0, w1, sh), u1 = __funnelshift_r(w1, w2, sh), u2 = __funnelshift_r(w2, w3, sh);  // bytes 0-3, 4-7, 8-11
+    // every sample lands in the top three bytes of a word (its low byte is don't-care), then one arithmetic shift
+    const uint32_t a = BE ? __byte_perm(u0, 0, 0x0122) : __byte_perm(u0, 0, 0x2100);     // L0 = bytes 0, 1, 2
+    const uint32_t b = BE ? __byte_perm(u0, u1, 0x3455) : __byte_perm(u0, u1, 0x5433);   // R0 = bytes 3, 4, 5
+    const uint32_t c = BE ? __byte_perm(u1, u2, 0x2344) : __byte_perm(u1, u2, 0x4322);   // L1 = bytes 6, 7, 8
+    const uint32_t d = BE ? __byte_perm(u2, 0, 0x1233) : u2;                              // R1 = bytes 9, 10, 11
+    ll = (float)(((int32_t)a) >> 8); rl = (float)(((int32_t)b) >> 8);
+    lu = (float)(((int32_t)c) >> 8); ru = (float)(((int32_t)d) >> 8);
+}
 template <int W> __device__ __forceinline__ float n48_scale() { return W == 2 ? 1.0f / 32768.0f : (W == 3 ? 1.0f / 8388608.0f : 4.656612873077393e-10f); }
 
 constexpr int kN48MaxStages = 4;         // staged runs in flight per CTA (ring of shared-memory buffers)
@@ -302,9 +320,13 @@ norm48k_tile_kernel(const __grid_constant__ N48Src src, unsigned long long o_sta
 #pragma unroll
             for (int k = 0; k < kN48Opt; k++) {
                 float ll, rl, lu, ru;
-                n48_frame_raw<W, BE, ST>(sm + off[k], fb4, ll, rl);
-                if (passthrough) { pl[k * kN48Threads] = __fmul_rn(ll, n48_scale<W>()); pr[k * kN48Threads] = __fmul_rn(rl, n48_scale<W>()); continue; }
-                n48_frame_raw<W, BE, ST>(sm + off[k] + fb, fb4, lu, ru);
+                if (W == 3 && ST && fb == 6 && !passthrough) {  // packed s24 stereo: both frames of the output from one 16-byte read
+                    n48_s24_stereo_pair<BE>(sm + off[k], ll, rl, lu, ru);
+                } else {
+                    n48_frame_raw<W, BE, ST>(sm + off[k], fb4, ll, rl);
+                    if (passthrough) { pl[k * kN48Threads] = __fmul_rn(ll, n48_scale<W>()); pr[k * kN48Threads] = __fmul_rn(rl, n48_scale<W>()); continue; }
+                    n48_frame_raw<W, BE, ST>(sm + off[k] + fb, fb4, lu, ru);
+                }
                 pl[k * kN48Threads] = __fmul_rn(__fadd_rn(ll, __fmul_rn(__fsub_rn(lu, ll), fr[k])), n48_scale<W>());
                 pr[k * kN48Threads] = __fmul_rn(__fadd_rn(rl, __fmul_rn(__fsub_rn(ru, rl), fr[k])), n48_scale<W>());
             }
