@@ -143,7 +143,7 @@ def test_endian_swap_matches_reference_hashes(ctx):
 
 # ---------------------------------------------------------------------------------------------- planar
 @pytest.mark.parametrize("bits,fmt", [(16, 0), (24, 0), (32, 0), (32, 1)])
-@pytest.mark.parametrize("channels", [1, 2, 3, 6])
+@pytest.mark.parametrize("channels", [1, 2, 3, 4, 6, 8])  # 3 .. 16 channels: the shared-memory tile kernel (4 / 8: its swizzled form)
 @pytest.mark.parametrize("mode", [capi.MODE_A, capi.MODE_B])
 @pytest.mark.parametrize("be", [False, True])
 def test_pcm_to_planar_f32(ctx, oracle, bits, fmt, channels, mode, be):
@@ -164,7 +164,7 @@ def test_pcm_to_planar_mode_b_rejects_partial_frame(ctx):
 
 
 @pytest.mark.parametrize("kind", ["i16", "s24", "f32"])
-@pytest.mark.parametrize("channels", [1, 2, 5])
+@pytest.mark.parametrize("channels", [1, 2, 5, 8, 16, 17])
 def test_deinterleave_typed(ctx, oracle, kind, channels):
     bps = {"i16": 2, "s24": 3, "f32": 4}[kind]
     for frames in (0, 3, 8, 1001, 40000):
