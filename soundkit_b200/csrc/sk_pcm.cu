@@ -722,6 +722,58 @@ __global__ void interleave_scalar_kernel(const float* __restrict__ planar, size_
     }
 }
 
+// 3 .. 16 channels: the mirror image of deint_tile_kernel.  Thread f reads sample f of every channel plane (each warp load is 128
+// contiguous bytes of one plane), quantises and drops the bytes at their interleaved place in a shared-memory tile (XOR-swizzled
+// where the frame size is a multiple of 16 bytes); the CTA then writes the tile with coalesced 128-bit stores.
+template <int BITS, bool ISFLOAT>
+__global__ void __launch_bounds__(kPcmThreads) interleave_tile_kernel(const float* __restrict__ planar, size_t frames, uint8_t* __restrict__ out, size_t ntiles,
+                                                                      int CH, int swz, int fpt) {
+    constexpr int OB = BITS / 8;
+    extern __shared__ __align__(16) uint32_t il_tile[];
+    uint8_t* tile8 = reinterpret_cast<uint8_t*>(il_tile);
+    const int tile_frames = fpt * kTileFrames;
+    const int nvec = tile_frames * CH * OB / 16;
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (int j = 0; j < fpt; j++) {
+            const int f = j * kTileFrames + threadIdx.x;
+            const float* x = planar + t * (size_t)tile_frames + f;
+            for (int c = 0; c < CH; c++) {
+                const uint32_t r = quantize<BITS, ISFLOAT>(__ldg(x + (size_t)c * frames));
+                const int bo = (f * CH + c) * OB;
+                if (OB == 3) {
+                    tile8[bo] = (uint8_t)r; tile8[bo + 1] = (uint8_t)(r >> 8); tile8[bo + 2] = (uint8_t)(r >> 16);
+                } else {
+                    int w = bo >> 2;
+                    w ^= (w >> 5) & swz;
+                    if (OB == 4) il_tile[w] = r;
+                    else reinterpret_cast<uint16_t*>(il_tile)[2 * w + ((bo >> 1) & 1)] = (uint16_t)r;
+                }
+            }
+        }
+        __syncthreads();
+        uint4* q = reinterpret_cast<uint4*>(out + t * (size_t)tile_frames * (size_t)(CH * OB));
+        for (int v = threadIdx.x; v < nvec; v += kPcmThreads) {
+            const int w = 4 * v;
+            const int k = OB == 3 ? 0 : ((w >> 5) & swz);
+            st_stream_v4(q + v, make_uint4(il_tile[w ^ k], il_tile[(w + 1) ^ k], il_tile[(w + 2) ^ k], il_tile[(w + 3) ^ k]));
+        }
+        __syncthreads();  // the tile is free for the next frames
+    }
+}
+template <int BITS, bool ISFLOAT>
+static size_t launch_interleave_tile(sk_ctx* ctx, const float* planar, size_t frames, int channels, uint8_t* out) {
+    constexpr int OB = BITS / 8;
+    const int row = channels * OB;
+    const int fpt = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(4, 64 / row), frames / kTileFrames));
+    const size_t ntiles = frames / ((size_t)fpt * kTileFrames);
+    if (!ntiles) return 0;
+    const int swz = (OB != 3 && row % 16 == 0) ? 7 : 0;
+    const size_t smem = (size_t)fpt * kTileFrames * row + 16;
+    interleave_tile_kernel<BITS, ISFLOAT><<<(unsigned)std::min<size_t>(ntiles, (size_t)1 << 20), kPcmThreads, smem, ctx->stream>>>(planar, frames, out, ntiles, channels,
+                                                                                                                                swz, fpt);
+    return ntiles * (size_t)fpt * kTileFrames;
+}
+
 template <int BITS, int CH, bool ISFLOAT>
 static size_t launch_interleave_vec(sk_ctx* ctx, const float* planar, size_t frames, uint8_t* out) {
     constexpr int OB = BITS / 8;
@@ -747,6 +799,12 @@ extern "C" int sk_planar_f32_to_pcm_dev(sk_ctx* ctx, const float* planar, size_t
         SK_IV(16, 1, false) SK_IV(16, 2, false) SK_IV(24, 1, false) SK_IV(24, 2, false)
         SK_IV(32, 1, false) SK_IV(32, 2, false) SK_IV(32, 1, true) SK_IV(32, 2, true)
 #undef SK_IV
+        if (done) SK_LAUNCH_CHECK(ctx);
+    } else if (aligned16(out) && channels >= 3 && channels <= kTileMaxCh) {
+        if (isf) done = launch_interleave_tile<32, true>(ctx, planar, frames, channels, out);
+        else if (bits == 16) done = launch_interleave_tile<16, false>(ctx, planar, frames, channels, out);
+        else if (bits == 24) done = launch_interleave_tile<24, false>(ctx, planar, frames, channels, out);
+        else done = launch_interleave_tile<32, false>(ctx, planar, frames, channels, out);
         if (done) SK_LAUNCH_CHECK(ctx);
     }
     if (done < frames) {

@@ -182,9 +182,9 @@ def test_interleave_i16_and_stereo_to_mono(ctx, oracle):
 
 
 @pytest.mark.parametrize("bits,fmt", [(16, 0), (24, 0), (32, 0), (32, 1)])
-@pytest.mark.parametrize("channels", [1, 2, 4])
+@pytest.mark.parametrize("channels", [1, 2, 3, 4, 6, 8, 17])  # 3 .. 16 channels: the shared-memory tile kernel
 def test_planar_f32_to_pcm(ctx, oracle, bits, fmt, channels):
-    for frames in (0, 5, 64, 4100):
+    for frames in (0, 5, 64, 4100, 33001):
         x = np.frombuffer(_flat_input("f32le", frames * channels).tobytes(), np.float32).reshape(channels, frames).copy()
         if frames > 10:
             x[0, :8] = [0.5 / 32767, 1.5 / 32767, -0.5 / 32768, -1.5 / 32768, 2.5 / 32767, 1e-30, -1e-30, 0.99999994]
