@@ -39,6 +39,7 @@ struct sk_ctx {
     std::map<std::string, sk_plan*> plans;            // batch plans keyed by rate/frames/semantics (bounded LRU, sk_resample.cu)
     uint64_t plan_clock = 0;
     void* d_res = nullptr;   size_t d_res_cap = 0;     // result planes of sk_normalize_stream (grow-only; no per-call cudaMalloc)
+    void* d_rows = nullptr;  size_t d_rows_cap = 0;    // planar f32 rows of the two-pass chain for mono / multi-channel sources (sk_resample.cu)
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};     // pinned-stage slot events of sk_h2d / sk_d2h (created once)
     size_t batch_slab_bytes = (size_t)256 << 20;      // input bytes per slab of the sk_normalize_batch pipeline (sk_ctx_set_batch_slab_bytes)
     bool resample_fast = false;                       // sk_ctx_set_resample_mode: opt-in tolerance mode of the general-ratio resampler

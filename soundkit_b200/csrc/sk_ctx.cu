@@ -45,6 +45,7 @@ extern "C" void sk_ctx_destroy(sk_ctx* ctx) {
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_tmp) cudaFree(ctx->d_tmp);
     if (ctx->d_res) cudaFree(ctx->d_res);
+    if (ctx->d_rows) cudaFree(ctx->d_rows);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     for (int i = 0; i < 2; i++)
         if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);

@@ -651,6 +651,62 @@ extern "C" int sk_normalize_batch_dev(sk_ctx* ctx, const sk_batch_desc* d) {
     dst.base = d->out; dst.stream_stride = (long long)d->out_stride; dst.lane_stride = (long long)d->out_stride_ch;
     dst.n_out = (long long)plan->n_out;
     int mix = d->channels == 1 ? SK_MIX_NONE : d->mix_mode;  // a mono source is never downmixed (emit_resampled_chunks)
+    // Mono and multi-channel sources at integer ratios: TWO passes instead of the scalar-staging FIR (0.16 / 0.29 of FP32 peak for
+    // mono / 6 channels) — (1) interleaved PCM -> planar f32 rows with the HBM-rate conversion kernels, (2) the persistent TMA FIR
+    // for planar rows (resample_int_planar_kernel), two lanes per tile: the channel pairs of a stream, or pairs of mono streams —
+    // in slabs that bound the scratch.  Same values: both forms convolve the same converted f32 samples in rubato's order.
+    if (plan->integer_step && d->channels != 2 && d->frames >= 4 && d->frames % 4 == 0 && (((uintptr_t)d->in | (uintptr_t)d->in_stride) & 15) == 0 &&
+        plan->n_out > 0) {
+        const size_t row_floats = d->frames * (size_t)d->channels;  // one stream's planes
+        const size_t plane = sk_round_up(plan->n_out, 4), per_stream_out = plane * d->channels;
+        size_t slab = std::max<size_t>(1, ((size_t)1 << 28) / std::max(row_floats, per_stream_out));  // <= 1 GiB per scratch
+        slab = std::min(slab, d->n_streams);
+        if (slab > 1 && d->channels == 1) slab &= ~(size_t)1;  // mono streams are convolved in pairs
+        if (ctx->d_rows_cap < slab * row_floats * sizeof(float)) {
+            if (ctx->d_rows) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->d_rows); ctx->d_rows = nullptr; ctx->d_rows_cap = 0; }
+            const size_t cap = sk_round_up(slab * row_floats * sizeof(float), (size_t)1 << 20);
+            if (cudaMalloc(&ctx->d_rows, cap) != cudaSuccess) SK_FAIL(ctx, SK_E_ALLOC, "device alloc of %zu bytes failed", cap);
+            ctx->d_rows_cap = cap;
+        }
+        float* rows = (float*)ctx->d_rows;
+        float* scratch = nullptr;
+        if (mix != SK_MIX_NONE) {
+            if ((rc = sk_ensure_dev_out(ctx, slab * per_stream_out * sizeof(float)))) return rc;
+            scratch = (float*)ctx->d_out;
+        }
+        for (size_t s0 = 0; s0 < d->n_streams; s0 += slab) {
+            const size_t ns = std::min(slab, d->n_streams - s0);
+            if ((rc = sk_pcm_to_planar_f32_dev(ctx, (const uint8_t*)d->in + s0 * d->in_stride, d->in_stride, ns, d->frames, d->bits, d->fmt, d->big_endian,
+                                               d->channels, d->scale_mode, rows, row_floats)))
+                return rc;
+            SrcDesc s2;
+            memset(&s2, 0, sizeof(s2));
+            s2.base = (const uint8_t*)rows; s2.stream_stride = (long long)(row_floats * sizeof(float)); s2.lane_stride = (long long)(d->frames * sizeof(float));
+            s2.width = 0; s2.channels = d->channels; s2.scale = 1.0f; s2.origin = 0; s2.valid_lo = 0; s2.valid_hi = (long long)d->frames;
+            OutDesc d2;
+            d2.n_out = (long long)plan->n_out; d2.mix = SK_MIX_NONE;
+            if (mix != SK_MIX_NONE) { d2.base = scratch; d2.stream_stride = (long long)per_stream_out; d2.lane_stride = (long long)plane; }
+            else { d2.base = d->out + s0 * d->out_stride; d2.stream_stride = (long long)d->out_stride; d2.lane_stride = (long long)d->out_stride_ch; }
+            if (d->channels == 1 && ns >= 2) {
+                // pairs of mono streams as the two lanes of a tile (an odd last stream goes alone)
+                SrcDesc sp = s2; OutDesc dp = d2;
+                sp.stream_stride = 2 * s2.stream_stride; sp.lane_stride = s2.stream_stride; sp.channels = 2;
+                dp.stream_stride = 2 * d2.stream_stride; dp.lane_stride = d2.stream_stride;
+                if ((rc = run_plan(ctx, sp, dp, plan, d->in_rate, d->out_rate, ns / 2, 2))) return rc;
+                if (ns & 1) {
+                    SrcDesc sl = s2; OutDesc dl = d2;
+                    sl.base += (long long)(ns - 1) * s2.stream_stride; dl.base += (long long)(ns - 1) * d2.stream_stride;
+                    if ((rc = run_plan(ctx, sl, dl, plan, d->in_rate, d->out_rate, 1, 1))) return rc;
+                }
+            } else if ((rc = run_plan(ctx, s2, d2, plan, d->in_rate, d->out_rate, ns, d->channels))) {
+                return rc;
+            }
+            if (mix != SK_MIX_NONE &&
+                (rc = sk_mixdown_batch_dev(ctx, scratch, per_stream_out, plane, plan->n_out, d->channels, mix, d->out + s0 * d->out_stride, d->out_stride, ns)))
+                return rc;
+        }
+        return SK_OK;
+    }
     if (mix != SK_MIX_NONE && (d->channels != 2 || !plan->integer_step)) {
         // unfused: resample to a planar scratch, then mix down stream by stream
         const size_t plane = sk_round_up(plan->n_out, 4);

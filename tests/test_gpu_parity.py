@@ -347,6 +347,60 @@ def test_batch_dev_matches_per_stream_and_linearity():
     ctx.close()
 
 
+@pytest.mark.parametrize("channels,bits,fmt", [(1, 16, 0), (1, 24, 0), (1, 32, 1), (3, 16, 0), (6, 24, 0), (6, 32, 1)])
+@pytest.mark.parametrize("rates", [(48000, 16000), (48000, 8000), (32000, 16000)])
+def test_batch_dev_mono_and_multichannel_two_pass_chain(oracle, channels, bits, fmt, rates):
+    """mono and > 2-channel sources at integer ratios take two passes (interleaved PCM -> planar f32 rows, then the persistent
+    TMA FIR for planar rows; mono streams are convolved in pairs, an odd last stream alone): every stream of a batch must equal
+    the oracle bit for bit, unmixed and mixed down, both semantics"""
+    import torch
+    i, o = rates
+    c = capi.Context(0)
+    c.use_torch_stream()
+    S, frames = 5, 20000  # 5: two pairs + a lone stream for mono; frames % 4 == 0 (the two-pass form's condition)
+    fb = channels * bits // 8
+    stride = (frames * fb + 15) // 16 * 16
+    rng = np.random.default_rng(channels * 100 + bits + i)
+    host = np.zeros((S, stride), np.uint8)
+    for st in range(S):
+        if fmt == 1:
+            host[st, : frames * fb] = rng.uniform(-1, 1, frames * channels).astype(np.float32).view(np.uint8)
+        else:
+            host[st, : frames * fb] = rng.integers(0, 256, frames * fb, dtype=np.uint8)
+    d_in = torch.from_numpy(host).cuda()
+    for sem in (capi.SEM_ONESHOT, capi.SEM_STREAMING):
+        n = c.batch_plan(i, o, frames, sem)
+        plane = (n + 3) // 4 * 4
+        # unmixed: one plane per channel (downsample_audio / the streaming resampler per channel)
+        out = torch.full((S, channels, plane), float("nan"), dtype=torch.float32, device="cuda")
+        c.normalize_batch_dev(capi.BatchDesc(d_in.data_ptr(), stride, S, frames, bits, fmt, 0, channels, capi.MODE_A, i, o, sem, capi.MIX_NONE,
+                                             out.data_ptr(), channels * plane, plane))
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        for st in range(S):
+            data = host[st, : frames * fb]
+            if sem == capi.SEM_ONESHOT:
+                want = oracle.downsample_audio(data, bits, fmt, channels, i, o)
+            else:
+                planar = oracle.pcm_to_planar_f32(data, bits, fmt, False, channels, capi.MODE_A)
+                r = oracle.Stream(i, o, channels)
+                want = np.concatenate([r.process(planar), r.flush()], axis=1)
+            assert want.shape == (channels, n)
+            assert np.array_equal(got[st, :, :n].view(np.uint32), want.view(np.uint32)), (sem, st)
+        if channels > 1 and fmt == 0:
+            # mixed down to mono (apply_output_options' arm): decoder convention, scale-then-sum
+            mono = torch.full((S, plane), float("nan"), dtype=torch.float32, device="cuda")
+            c.normalize_batch_dev(capi.BatchDesc(d_in.data_ptr(), stride, S, frames, bits, fmt, 0, channels, capi.MODE_B, i, o, capi.SEM_STREAMING,
+                                                 capi.MIX_SCALE_THEN_SUM, mono.data_ptr(), plane, 0))
+            torch.cuda.synchronize()
+            gm = mono.cpu().numpy()
+            nm = c.batch_plan(i, o, frames, capi.SEM_STREAMING)
+            for st in (0, S - 1):
+                want = oracle.normalize_chain_mono(host[st, : frames * fb], bits, 0, False, channels, i, o)
+                assert np.array_equal(gm[st, :nm].view(np.uint32), want.view(np.uint32)), st
+    c.close()
+
+
 # ---------------------------------------------------------------------------------------------- 8(f) row 2: 48 kHz stereo normalizer
 def _n48_source(bits, fmt, be, channels, frames, rng):
     if fmt == 1:
