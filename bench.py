@@ -259,6 +259,17 @@ def extras(ctx, torch, peaks, only=None):
         t = timed(lambda: ctx.normalize_batch_pcm_dev(d, 16, 0, o, ostride), reps=3)
         res["chain_s24_stereo_48k_to_s16_mono_16k_bytes"] = flop_entry(1024.0 * S * n_out, t, S * n_out)
         del raw, o
+        # a mono source through the same chain (s16le mono 48 kHz -> f32 mono 16 kHz, 16 streams x 600 s): conversion to planar rows + the
+        # planar TMA FIR over pairs of streams
+        S = 16
+        stride = (frames * 2 + 15) // 16 * 16
+        raw = torch.randint(0, 256, (S, stride), dtype=torch.uint8, device="cuda")
+        o = torch.empty((S, n_out), dtype=torch.float32, device="cuda")
+        d = capi.BatchDesc(raw.data_ptr(), stride, S, frames, 16, capi.FMT_SIGNED, 0, 1, capi.MODE_B, 48000, 16000, capi.SEM_STREAMING,
+                           capi.MIX_NONE, o.data_ptr(), n_out, 0)
+        t = timed(lambda: ctx.normalize_batch_dev(d), reps=3)
+        res["chain_s16_mono_48k_to_f32_mono_16k"] = flop_entry(512.0 * S * n_out, t, S * n_out)
+        del raw, o
     if want("flat"):
         # a few of the remaining R1 entry points (soundkit/src/audio_bytes.rs flat functions, f32_channels_to_bytes)
         n = 1 << 28
