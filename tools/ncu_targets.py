@@ -54,6 +54,21 @@ def main():
     ctx.g726_encode_batch_dev(4, 0, capi.KIND_I16, p6, k, S, k, c6, k // 2)
     ctx.g722_decode_batch_dev(c6, k // 2, S, k // 2, capi.KIND_I16, p6, k)
     ctx.g722_encode_batch_dev(capi.KIND_I16, p6, k, S, k, c6, k // 2)
+    # multi-channel conversion both ways (shared-memory tile kernels) and the mono chain (conversion pass + planar TMA FIR)
+    S, ch, frames = 8, 6, 960000
+    raw = torch.randint(0, 256, (S, frames * ch * 2), dtype=torch.uint8, device="cuda")
+    o = torch.empty((S, ch, frames), dtype=torch.float32, device="cuda")
+    ctx.pcm_to_planar_f32_dev(raw, raw.stride(0), S, frames, 16, 0, False, ch, capi.MODE_B, o, ch * frames)
+    b = torch.empty((frames * ch * 2,), dtype=torch.uint8, device="cuda")
+    ctx.planar_f32_to_pcm_dev(o[0], frames, ch, 16, 0, b)
+    del raw, o, b
+    S, frames = 16, 5760000
+    raw = torch.randint(0, 256, (S, frames * 2), dtype=torch.uint8, device="cuda")
+    n_out = ctx.batch_plan(48000, 16000, frames, capi.SEM_STREAMING)
+    o = torch.empty((S, n_out), dtype=torch.float32, device="cuda")
+    ctx.normalize_batch_dev(capi.BatchDesc(raw.data_ptr(), raw.stride(0), S, frames, 16, capi.FMT_SIGNED, 0, 1, capi.MODE_B, 48000, 16000, capi.SEM_STREAMING,
+                                           capi.MIX_NONE, o.data_ptr(), n_out, 0))
+    del raw, o
     torch.cuda.synchronize()
     print("launched", ctx.launches, "kernels")
 
