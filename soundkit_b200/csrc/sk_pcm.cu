@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(kPcmThreads) deint_tile_kernel(const uint8_t* 
 
 // any channel count / alignment / tail frames: one thread per sample
 __global__ void deint_scalar_kernel(const uint8_t* __restrict__ in, size_t in_stride, uint8_t* __restrict__ out, size_t out_stride_bytes,
-                                    size_t frames, size_t first_frame, int B, int CH, int be, int conv, float scale) {
+                                    size_t frames, size_t plane, size_t first_frame, int B, int CH, int be, int conv, float scale) {
     const uint8_t* sin = in + (size_t)blockIdx.y * in_stride;
     uint8_t* sout = out + (size_t)blockIdx.y * out_stride_bytes;
     const size_t total = (frames - first_frame) * (size_t)CH;
@@ -503,21 +503,21 @@ __global__ void deint_scalar_kernel(const uint8_t* __restrict__ in, size_t in_st
             case CONV_RAW_I32: r = planar_apply<CONV_RAW_I32>(raw, scale); break;
             default: r = planar_apply<CONV_RAW_I16>(raw, scale); break;
         }
-        if (conv == CONV_RAW_I16) reinterpret_cast<uint16_t*>(sout)[(size_t)c * frames + f] = (uint16_t)r;
-        else reinterpret_cast<uint32_t*>(sout)[(size_t)c * frames + f] = r;
+        if (conv == CONV_RAW_I16) reinterpret_cast<uint16_t*>(sout)[(size_t)c * plane + f] = (uint16_t)r;
+        else reinterpret_cast<uint32_t*>(sout)[(size_t)c * plane + f] = r;
     }
 }
 
 template <int B, int CH, bool BE, int CONV>
-static size_t launch_deint_vec(sk_ctx* ctx, const uint8_t* in, size_t in_stride, uint8_t* out, size_t out_stride_bytes, size_t frames,
-                               size_t n_streams, float scale) {
+static size_t launch_deint_vec(sk_ctx* ctx, const uint8_t* in, size_t in_stride, uint8_t* out, size_t out_stride_bytes, size_t frames, size_t plane,
+                               size_t n_streams, float scale) {  // `plane`: elements between channel planes (the kernels' `frames` argument is that stride)
     constexpr int OB = CONV == CONV_RAW_I16 ? 2 : 4;
     constexpr int G = (OB == 2) ? 8 : ((B == 3) ? 8 * (CH == 1 ? 2 : 1) : (B == 2 && CH == 1 ? 8 : 4));
     if (B == 3 && CH == 2 && OB == 4 && frames >= 256) {  // warp-tiled path for packed 24-bit stereo
         const size_t ntiles = frames / 256;
         const size_t ctas = (ntiles + kPcmThreads / 32 - 1) / (kPcmThreads / 32);
         dim3 grid((unsigned)std::max<size_t>(1, std::min<size_t>((ctas + 1) / 2, (size_t)1 << 22)), (unsigned)n_streams);  // short-lived CTAs (grid_for)
-        deint_s24_stereo_kernel<BE, CONV><<<grid, kPcmThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride_bytes, frames, ntiles, scale);
+        deint_s24_stereo_kernel<BE, CONV><<<grid, kPcmThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride_bytes, plane, ntiles, scale);
         return ntiles * 256;
     }
     size_t ngroups = frames / G;
@@ -526,13 +526,13 @@ static size_t launch_deint_vec(sk_ctx* ctx, const uint8_t* in, size_t in_stride,
     // keep total CTAs bounded for big batches: the grid-stride loop covers the rest
     if (n_streams > 1) grid.x = (unsigned)((ngroups + (size_t)kPcmThreads * 8 - 1) / ((size_t)kPcmThreads * 8));
     if (grid.x < 1) grid.x = 1;
-    deint_kernel<B, CH, BE, CONV><<<grid, kPcmThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride_bytes, frames, ngroups, scale);
+    deint_kernel<B, CH, BE, CONV><<<grid, kPcmThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride_bytes, plane, ngroups, scale);
     return ngroups * G;
 }
 
 // dispatch on (B, CH, BE, CONV); returns frames covered by the vector kernel (0 = none)
 static size_t dispatch_deint_vec(sk_ctx* ctx, int B, int CH, bool be, int conv, const uint8_t* in, size_t in_stride, uint8_t* out,
-                                 size_t out_stride_bytes, size_t frames, size_t n_streams, float scale) {
+                                 size_t out_stride_bytes, size_t frames, size_t plane, size_t n_streams, float scale) {
     if (CH >= 3 && CH <= kTileMaxCh && conv != CONV_RAW_I16 && frames >= (size_t)kTileFrames) {
         const int row = CH * B;  // bytes between the same channel of consecutive frames
         const int fpt = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(4, 64 / row), frames / kTileFrames));  // <= 16 KB of tile
@@ -542,7 +542,7 @@ static size_t dispatch_deint_vec(sk_ctx* ctx, int B, int CH, bool be, int conv, 
         const dim3 grid((unsigned)std::min<size_t>(ntiles, (size_t)1 << 20), (unsigned)n_streams);
 #define SK_DT(B_, BE_, CONV_) \
         if (B == B_ && be == BE_ && conv == CONV_) { \
-            deint_tile_kernel<B_, BE_, CONV_><<<grid, kPcmThreads, smem, ctx->stream>>>(in, in_stride, out, out_stride_bytes, frames, ntiles, CH, swz, fpt, scale); \
+            deint_tile_kernel<B_, BE_, CONV_><<<grid, kPcmThreads, smem, ctx->stream>>>(in, in_stride, out, out_stride_bytes, plane, ntiles, CH, swz, fpt, scale); \
             return ntiles * (size_t)fpt * kTileFrames; \
         }
         SK_DT(2, false, CONV_F32_SCALED) SK_DT(2, true, CONV_F32_SCALED) SK_DT(3, false, CONV_F32_SCALED) SK_DT(3, true, CONV_F32_SCALED)
@@ -552,7 +552,7 @@ static size_t dispatch_deint_vec(sk_ctx* ctx, int B, int CH, bool be, int conv, 
     }
 #define SK_DV(B_, CH_, BE_, CONV_) \
     if (B == B_ && CH == CH_ && be == BE_ && conv == CONV_) \
-        return launch_deint_vec<B_, CH_, BE_, CONV_>(ctx, in, in_stride, out, out_stride_bytes, frames, n_streams, scale);
+        return launch_deint_vec<B_, CH_, BE_, CONV_>(ctx, in, in_stride, out, out_stride_bytes, frames, plane, n_streams, scale);
 #define SK_DV_CH(B_, BE_, CONV_) SK_DV(B_, 1, BE_, CONV_) SK_DV(B_, 2, BE_, CONV_)
     SK_DV_CH(2, false, CONV_F32_SCALED) SK_DV_CH(2, true, CONV_F32_SCALED)
     SK_DV_CH(3, false, CONV_F32_SCALED) SK_DV_CH(3, true, CONV_F32_SCALED)
@@ -568,15 +568,16 @@ static size_t dispatch_deint_vec(sk_ctx* ctx, int B, int CH, bool be, int conv, 
 
 // common driver: vector kernel on the aligned body, scalar kernel on everything else
 static int run_deint(sk_ctx* ctx, int B, int CH, bool be, int conv, const uint8_t* in, size_t in_stride, void* outv, size_t out_stride_bytes,
-                     size_t frames, size_t n_streams, float scale) {
+                     size_t frames, size_t n_streams, float scale, size_t plane = 0) {  // plane: elements between channel planes (0 = frames)
+    if (!plane) plane = frames;
     if (!frames || !n_streams) return SK_OK;
     uint8_t* out = (uint8_t*)outv;
     const int OB = conv == CONV_RAW_I16 ? 2 : 4;
     size_t done = 0;
-    bool vec_ok = aligned16(in) && aligned16(out) && (in_stride % 16 == 0) && (out_stride_bytes % 16 == 0) && ((frames * OB) % 16 == 0) &&
+    bool vec_ok = aligned16(in) && aligned16(out) && (in_stride % 16 == 0) && (out_stride_bytes % 16 == 0) && ((plane * OB) % 16 == 0) &&
                   n_streams <= 65535;
     if (vec_ok) {
-        done = dispatch_deint_vec(ctx, B, CH, be, conv, in, in_stride, out, out_stride_bytes, frames, n_streams, scale);
+        done = dispatch_deint_vec(ctx, B, CH, be, conv, in, in_stride, out, out_stride_bytes, frames, plane, n_streams, scale);
         if (done) SK_LAUNCH_CHECK(ctx);
     }
     if (done < frames) {
@@ -585,7 +586,7 @@ static int run_deint(sk_ctx* ctx, int B, int CH, bool be, int conv, const uint8_
             dim3 grid(grid_for(ctx, (frames - done) * CH, 256), (unsigned)ns);
             if (ns > 1 && grid.x > 64) grid.x = 64;
             deint_scalar_kernel<<<grid, 256, 0, ctx->stream>>>(in + s0 * in_stride, in_stride, out + s0 * out_stride_bytes, out_stride_bytes,
-                                                               frames, done, B, CH, be ? 1 : 0, conv, scale);
+                                                               frames, plane, done, B, CH, be ? 1 : 0, conv, scale);
             SK_LAUNCH_CHECK(ctx);
         }
     }
@@ -613,6 +614,16 @@ extern "C" int sk_pcm_to_planar_f32_dev(sk_ctx* ctx, const uint8_t* in, size_t i
     if (!in || !out) SK_FAIL(ctx, SK_E_ARG, "null buffer");
     SK_CUDA(ctx, cudaSetDevice(ctx->device));
     return run_deint(ctx, bits / 8, channels, be, conv, in, in_stride, out, out_stride * sizeof(float), frames, n_streams, scale);
+}
+
+// internal (sk_resample.cu: the two-pass chain): as sk_pcm_to_planar_f32_dev, channel planes `plane` floats apart (>= frames) so that every
+// plane can start on a 16-byte boundary whatever the stream length
+int sk_pcm_to_planar_rows_dev(sk_ctx* ctx, const uint8_t* in, size_t in_stride, size_t n_streams, size_t frames, int bits, int fmt, int big_endian,
+                              int channels, int scale_mode, float* out, size_t out_stride, size_t plane) {
+    int conv; float scale; bool be;
+    if (!planar_f32_conv(bits, fmt, big_endian, scale_mode, &conv, &scale, &be)) SK_FAIL(ctx, SK_E_ARG, "unsupported bits per sample %d", bits);
+    if (!frames || !n_streams) return SK_OK;
+    return run_deint(ctx, bits / 8, channels, be, conv, in, in_stride, out, out_stride * sizeof(float), frames, n_streams, scale, plane);
 }
 
 extern "C" int sk_pcm_to_planar_f32(sk_ctx* ctx, const uint8_t* in, size_t bytes, int bits, int fmt, int big_endian, int channels, int scale_mode,

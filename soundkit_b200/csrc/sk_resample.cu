@@ -628,7 +628,9 @@ extern "C" int sk_normalize_batch_plan(sk_ctx* ctx, uint32_t in_rate, uint32_t o
     return SK_OK;
 }
 
-// sk_pcm.cu: whole-batch mixdown / mono quantiser (blockIdx.y = stream)
+// sk_pcm.cu: interleaved PCM -> planar f32 with an explicit plane stride; whole-batch mixdown / mono quantiser (blockIdx.y = stream)
+int sk_pcm_to_planar_rows_dev(sk_ctx* ctx, const uint8_t* in, size_t in_stride, size_t n_streams, size_t frames, int bits, int fmt, int big_endian,
+                              int channels, int scale_mode, float* out, size_t out_stride, size_t plane);
 int sk_mixdown_batch_dev(sk_ctx* ctx, const float* planar, size_t in_stream_stride, size_t plane_stride, size_t frames, int channels, int mix_mode,
                          float* out, size_t out_stream_stride, size_t n_streams);
 int sk_quantize_mono_batch_dev(sk_ctx* ctx, const float* in, size_t in_stream_stride, size_t n, int bits, int fmt, uint8_t* out, size_t out_stream_bytes,
@@ -655,9 +657,9 @@ extern "C" int sk_normalize_batch_dev(sk_ctx* ctx, const sk_batch_desc* d) {
     // mono / 6 channels) — (1) interleaved PCM -> planar f32 rows with the HBM-rate conversion kernels, (2) the persistent TMA FIR
     // for planar rows (resample_int_planar_kernel), two lanes per tile: the channel pairs of a stream, or pairs of mono streams —
     // in slabs that bound the scratch.  Same values: both forms convolve the same converted f32 samples in rubato's order.
-    if (plan->integer_step && d->channels != 2 && d->frames >= 4 && d->frames % 4 == 0 && (((uintptr_t)d->in | (uintptr_t)d->in_stride) & 15) == 0 &&
-        plan->n_out > 0) {
-        const size_t row_floats = d->frames * (size_t)d->channels;  // one stream's planes
+    if (plan->integer_step && d->channels != 2 && d->frames >= 4 && plan->n_out > 0) {
+        const size_t in_plane = sk_round_up(d->frames, 4);           // floats between the planes of a stream: every plane 16-byte aligned
+        const size_t row_floats = in_plane * (size_t)d->channels;   // one stream's planes
         const size_t plane = sk_round_up(plan->n_out, 4), per_stream_out = plane * d->channels;
         size_t slab = std::max<size_t>(1, ((size_t)1 << 28) / std::max(row_floats, per_stream_out));  // <= 1 GiB per scratch
         slab = std::min(slab, d->n_streams);
@@ -676,12 +678,12 @@ extern "C" int sk_normalize_batch_dev(sk_ctx* ctx, const sk_batch_desc* d) {
         }
         for (size_t s0 = 0; s0 < d->n_streams; s0 += slab) {
             const size_t ns = std::min(slab, d->n_streams - s0);
-            if ((rc = sk_pcm_to_planar_f32_dev(ctx, (const uint8_t*)d->in + s0 * d->in_stride, d->in_stride, ns, d->frames, d->bits, d->fmt, d->big_endian,
-                                               d->channels, d->scale_mode, rows, row_floats)))
+            if ((rc = sk_pcm_to_planar_rows_dev(ctx, (const uint8_t*)d->in + s0 * d->in_stride, d->in_stride, ns, d->frames, d->bits, d->fmt, d->big_endian,
+                                                d->channels, d->scale_mode, rows, row_floats, in_plane)))
                 return rc;
             SrcDesc s2;
             memset(&s2, 0, sizeof(s2));
-            s2.base = (const uint8_t*)rows; s2.stream_stride = (long long)(row_floats * sizeof(float)); s2.lane_stride = (long long)(d->frames * sizeof(float));
+            s2.base = (const uint8_t*)rows; s2.stream_stride = (long long)(row_floats * sizeof(float)); s2.lane_stride = (long long)(in_plane * sizeof(float));
             s2.width = 0; s2.channels = d->channels; s2.scale = 1.0f; s2.origin = 0; s2.valid_lo = 0; s2.valid_hi = (long long)d->frames;
             OutDesc d2;
             d2.n_out = (long long)plan->n_out; d2.mix = SK_MIX_NONE;
