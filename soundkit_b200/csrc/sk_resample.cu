@@ -1305,7 +1305,22 @@ static int batch_run_chunks(sk_resampler_batch* b, size_t chunks, size_t valid, 
         OutDesc dst;
         dst.base = out; dst.stream_stride = (long long)out_stream_stride; dst.lane_stride = (long long)out_ch_stride; dst.mix = SK_MIX_NONE;
         dst.n_out = (long long)n;
-        int rc = run_plan(ctx, src, dst, &p, b->in_rate, b->out_rate, b->n_streams, b->channels);
+        int rc;
+        if (p.integer_step && b->channels == 1 && b->n_streams >= 2) {
+            // mono streams: the integer-step kernels convolve two lanes per tile, so pairs of streams go as the two lanes of one
+            // (an odd last stream alone) instead of leaving the second lane of every tile empty
+            SrcDesc sp = src; OutDesc dp = dst;
+            sp.stream_stride = 2 * src.stream_stride; sp.lane_stride = src.stream_stride; sp.channels = 2;
+            dp.stream_stride = 2 * dst.stream_stride; dp.lane_stride = dst.stream_stride;
+            rc = run_plan(ctx, sp, dp, &p, b->in_rate, b->out_rate, b->n_streams / 2, 2);
+            if (!rc && (b->n_streams & 1)) {
+                SrcDesc sl = src; OutDesc dl = dst;
+                sl.base += (long long)(b->n_streams - 1) * src.stream_stride; dl.base += (long long)(b->n_streams - 1) * dst.stream_stride;
+                rc = run_plan(ctx, sl, dl, &p, b->in_rate, b->out_rate, 1, 1);
+            }
+        } else {
+            rc = run_plan(ctx, src, dst, &p, b->in_rate, b->out_rate, b->n_streams, b->channels);
+        }
         if (rc) return rc;
     }
     b->last_index = last;
