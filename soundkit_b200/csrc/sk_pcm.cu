@@ -425,6 +425,32 @@ __global__ void __launch_bounds__(kPcmThreads) deint_s24_stereo_kernel(const uin
     }
 }
 
+// One channel (16- / 24-bit in, 4-byte samples out): a lane's group is 2 or 4 output vectors, so the direct form above stores every
+// 2nd / 4th vector of a run per instruction (half-written sectors: 0.75-0.78 of the HBM rate).  Same cure as the flat kernels: a
+// WARP owns 32 consecutive groups and the vectors change lanes through warp-private shared memory (warp_load_spans /
+// warp_store_spans), so every global access is a whole contiguous 512-byte run.  grid.y = stream.
+template <int B, bool BE, int CONV>
+__global__ void __launch_bounds__(kPcmThreads) deint_mono_kernel(const uint8_t* __restrict__ in, size_t in_stride, uint8_t* __restrict__ out,
+                                                                  size_t out_stride_bytes, size_t ntiles, float scale) {
+    constexpr int G = B == 3 ? 16 : 8;
+    constexpr int NV_IN = G * B / 16, NV_OUT = G * 4 / 16;
+    constexpr int NVX = NV_IN > NV_OUT ? NV_IN : NV_OUT;
+    __shared__ uint4 xch_all[kPcmWarps][NVX * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint4* xch = xch_all[warp];
+    const uint8_t* sin = in + (size_t)blockIdx.y * in_stride;
+    uint8_t* sout = out + (size_t)blockIdx.y * out_stride_bytes;
+    for (size_t t = (size_t)blockIdx.x * kPcmWarps + warp; t < ntiles; t += (size_t)gridDim.x * kPcmWarps) {
+        uint32_t w[NV_IN * 4 + 1];
+        warp_load_spans<NV_IN>(xch, reinterpret_cast<const uint4*>(sin + t * (size_t)(32 * G * B)), w, lane);
+        w[NV_IN * 4] = 0u;
+        uint32_t o[G];
+#pragma unroll
+        for (int k = 0; k < G; k++) o[k] = planar_apply<CONV>(get_sample<B, BE>(w, k), scale);
+        warp_store_spans<NV_OUT>(xch, reinterpret_cast<uint4*>(sout + t * (size_t)(32 * G * 4)), o, lane);
+    }
+}
+
 // 3 .. 16 channels (5.1 / 7.1 beds): a CTA copies a tile of 256 frames into shared memory with coalesced 128-bit loads, then thread f
 // walks the channels of frame f, so that every warp store is 128 contiguous bytes of one channel plane.  Reading sample (f, c)
 // from 32 lanes is a stride of CH * B bytes; where that is a multiple of 16 bytes (all 32 reads in 8 or fewer banks) the tile is
@@ -533,6 +559,19 @@ static size_t launch_deint_vec(sk_ctx* ctx, const uint8_t* in, size_t in_stride,
 // dispatch on (B, CH, BE, CONV); returns frames covered by the vector kernel (0 = none)
 static size_t dispatch_deint_vec(sk_ctx* ctx, int B, int CH, bool be, int conv, const uint8_t* in, size_t in_stride, uint8_t* out,
                                  size_t out_stride_bytes, size_t frames, size_t plane, size_t n_streams, float scale) {
+    if (CH == 1 && (B == 2 || B == 3) && conv == CONV_F32_SCALED) {  // mono 16- / 24-bit -> f32: warp-tiled stores
+        const size_t tile = (size_t)32 * (B == 3 ? 16 : 8);
+        const size_t ntiles = frames / tile;
+        if (ntiles) {
+            const size_t ctas = (ntiles + kPcmWarps - 1) / kPcmWarps;
+            const dim3 grid((unsigned)std::max<size_t>(1, std::min<size_t>((ctas + 1) / 2, (size_t)1 << 22)), (unsigned)n_streams);
+            if (B == 2) { if (be) deint_mono_kernel<2, true, CONV_F32_SCALED><<<grid, kPcmThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride_bytes, ntiles, scale);
+                          else deint_mono_kernel<2, false, CONV_F32_SCALED><<<grid, kPcmThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride_bytes, ntiles, scale); }
+            else { if (be) deint_mono_kernel<3, true, CONV_F32_SCALED><<<grid, kPcmThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride_bytes, ntiles, scale);
+                   else deint_mono_kernel<3, false, CONV_F32_SCALED><<<grid, kPcmThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride_bytes, ntiles, scale); }
+            return ntiles * tile;
+        }
+    }
     if (CH >= 3 && CH <= kTileMaxCh && conv != CONV_RAW_I16 && frames >= (size_t)kTileFrames) {
         const int row = CH * B;  // bytes between the same channel of consecutive frames
         const int fpt = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(4, 64 / row), frames / kTileFrames));  // <= 16 KB of tile
