@@ -444,14 +444,15 @@ template <int STEP, int SRCW> __host__ __device__ constexpr int tma_raw_bytes() 
 // Raw-byte buffers of the TMA staging.  Step 3 (the headline shape: 2 CTAs per SM by registers) requests tile k + 2 while tile k
 // is convolved, into a second buffer.  The other steps are limited by shared memory instead (their windows are STEP / 3 times
 // longer per output): ONE buffer, refilled for tile k + 1 as soon as tile k has been converted — the request still has the whole
-// FIR of tile k to arrive — brings a third CTA per SM back.  SK_INT_NRAW overrides for A/B builds.
+// FIR of tile k to arrive — brings a third CTA per SM back.  The same holds for 32-bit sources at step 3: two 39 KB raw buffers beside
+// the 39 KB of windows left ONE CTA per SM (s32 / f32 stereo ran at 48.9 instead of 59 TFLOP/s).  SK_INT_NRAW overrides for A/B builds.
 #ifdef SK_INT_NRAW
-template <int STEP> __host__ __device__ constexpr int tma_raw_buffers() { return SK_INT_NRAW; }
+template <int STEP, int SRCW> __host__ __device__ constexpr int tma_raw_buffers() { return SK_INT_NRAW; }
 #else
-template <int STEP> __host__ __device__ constexpr int tma_raw_buffers() { return STEP == 3 ? 2 : 1; }
+template <int STEP, int SRCW> __host__ __device__ constexpr int tma_raw_buffers() { return STEP == 3 && SRCW <= 3 ? 2 : 1; }
 #endif
 template <int STEP, int SRCW> __host__ __device__ constexpr int tma_smem_bytes() {
-    return 2 * tma_lane_stride<STEP>() * (int)sizeof(float) + tma_raw_buffers<STEP>() * tma_raw_bytes<STEP, SRCW>() + 64;
+    return 2 * tma_lane_stride<STEP>() * (int)sizeof(float) + tma_raw_buffers<STEP, SRCW>() * tma_raw_bytes<STEP, SRCW>() + 64;
 }
 
 // 4 interleaved stereo frames (FB words in memory order) -> 4 L and 4 R f32 samples.  Everything about
@@ -557,7 +558,7 @@ resample_int_tma_kernel(const __grid_constant__ Taps taps, const __grid_constant
     constexpr int WS = tma_lane_stride<STEP>();
     constexpr int FB = 2 * SRCW;  // bytes per stereo frame
     constexpr int RAWB = tma_raw_bytes<STEP, SRCW>();
-    constexpr int NB = tma_raw_buffers<STEP>();  // raw buffers == tiles requested ahead
+    constexpr int NB = tma_raw_buffers<STEP, SRCW>();  // raw buffers == tiles requested ahead
     // the word one past the tile's window is only read (against a zero coefficient) when the last output's offset is odd; the
     // converted region must then reach it
     static_assert(((LEAD + STEP * (R - 1)) & 1) == 0 || WF > LEAD + int_window<STEP>(), "stage one more frame for this STEP / R");
