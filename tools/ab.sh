@@ -9,6 +9,6 @@ for v in default "$@"; do
 import sys, json
 for ln in sys.stdin:
     if ln.startswith('{'):
-        d = json.loads(ln); print('value', round(d['value']), 'Msamples/s  frac', round(d['roofline']['frac'], 4), ' e2e', round(d['e2e']['value']), 'match', d['e2e']['matches_device_path'])
+        d = json.loads(ln); print('value', round(d['value']), 'Msamples/s  frac', round(d['roofline']['frac'], 4), ' e2e', round(d['e2e']['value']), 'bit-exact', d['parity']['bit_exact'], d['parity']['e2e_equals_device_path'])
 "
 done
